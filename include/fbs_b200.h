@@ -1,0 +1,138 @@
+/*
+ * fbs_b200.h -- C ABI of the B200 encrypted executor for tfhe_fbs_map circuits.
+ *
+ * The reference (ssmiler/tfhe_fbs_map) has no FFI: its operator API for this path is the Python method
+ * LutExecEnv.eval (reference fbs_mapper/fbs_exec_env.py:208-229) and BitExecEnv.eval
+ * (reference fbs_mapper/bit_exec_env.py:173-194), called from the CLI at reference
+ * fbs_mapper/map_circuit.py:140,174.  The entry points below are what a ctypes binding of that path
+ * binds (INTEGRATION.md shows the stub); each cites the reference interface it stands in for.
+ *
+ * Conventions: plain pointers and sizes, no C++/torch types.  Every function returns FBS_OK (0) or a
+ * negative error code and never throws/aborts; fbs_last_error() returns the message of the calling
+ * thread's last failure.  "dev" pointers are CUDA device pointers on the context's device; `stream` is a
+ * cudaStream_t passed as void* (NULL = default stream).  One context per host thread.
+ */
+#ifndef FBS_B200_H
+#define FBS_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FBS_OK 0
+#define FBS_ERR_ARG (-1)      /* invalid argument / unsupported parameter shape */
+#define FBS_ERR_CUDA (-2)     /* CUDA runtime failure (message has the CUDA error string) */
+#define FBS_ERR_STATE (-3)    /* call order violated (e.g. eval before keygen) */
+#define FBS_ERR_NOMEM (-4)
+
+/* TFHE parameter set.  Ciphertext modulus is P = 2^64 - 2^32 + 1. */
+typedef struct fbs_params {
+    int32_t n;          /* small LWE dimension                         */
+    int32_t k;          /* GLWE dimension                              */
+    int32_t N;          /* polynomial size (power of two, 256..2048)   */
+    int32_t bsk_l;      /* blind-rotate decomposition levels           */
+    int32_t bsk_beta;   /* log2 blind-rotate base                      */
+    int32_t ks_l;       /* key-switch levels                           */
+    int32_t ks_beta;    /* log2 key-switch base (<= 8)                 */
+    int32_t reserved;
+    uint64_t lwe_noise; /* round(sigma_lwe  * P)                       */
+    uint64_t glwe_noise;/* round(sigma_glwe * P)                       */
+} fbs_params;
+
+/*
+ * Levelised FBS program: flat arrays produced from LutExecEnv.instructions (reference
+ * fbs_exec_env.py:63-70) by tfhe_fbs_map_b200/levelize.py.  A "wire" is an Input or Bootstrap node
+ * (reference fbs_exec_env.py:30-35,51-61) and lives in a ciphertext slot; LinearProd nodes (reference
+ * fbs_exec_env.py:37-49) are never stored, they appear as CSR rows over wire slots.  Level lv holds the
+ * lincombs [lc_level_ptr[lv], lc_level_ptr[lv+1]) and the bootstraps [bs_level_ptr[lv], bs_level_ptr[lv+1]);
+ * a lincomb of level lv only reads slots written by inputs or by bootstraps of levels < lv.
+ */
+typedef struct fbs_prog_desc {
+    int32_t p;            /* plaintext modulus = --fbs_size (reference map_circuit.py:98)           */
+    int32_t n_inputs, n_lincombs, n_boots, n_levels, n_slots, n_outputs, reserved;
+    const int32_t *lc_level_ptr;  /* [n_levels+1]                                                 */
+    const int32_t *bs_level_ptr;  /* [n_levels+1]                                                 */
+    const int32_t *lc_ptr;        /* [n_lincombs+1] CSR row pointers                              */
+    const int32_t *lc_slot;       /* [nnz] operand wire slot                                      */
+    const int32_t *lc_coef;       /* [nnz] integer coefficient (reference fbs_exec_env.py:215-217)*/
+    const int32_t *lc_const;      /* [n_lincombs] const_coef                                      */
+    const int32_t *bs_lc;         /* [n_boots] lincomb feeding this bootstrap                     */
+    const int32_t *bs_slot;       /* [n_boots] output wire slot                                   */
+    const int32_t *bs_tab_ptr;    /* [n_boots+1] into bs_tab                                      */
+    const uint8_t *bs_tab;        /* table entries (reference fbs_exec_env.py:218-220)            */
+    const int32_t *bs_mode;       /* [n_boots] s = tv[x]+tv[x+p] (map_to_fbs.py:81-98), 1 if len<=p */
+    const int32_t *in_slot;       /* [n_inputs]                                                   */
+    const int32_t *out_ptr;       /* [n_outputs+1] outputs are lincombs too (1-x, pass-through, const) */
+    const int32_t *out_slot, *out_coef, *out_const;
+} fbs_prog_desc;
+
+typedef struct fbs_run_stats {
+    int64_t n_pbs;         /* bootstraps executed (nodes x instances)          */
+    int64_t n_launches;    /* CUDA kernels launched by this call               */
+    float ms_total;        /* device time of the call (CUDA events)            */
+    float ms_encrypt, ms_lincomb, ms_keyswitch, ms_blind_rotate, ms_decrypt;
+    float reserved[2];
+} fbs_run_stats;
+
+typedef struct fbs_ctx fbs_ctx;    /* device, secret keys, BSK (NTT domain), KSK, scratch */
+typedef struct fbs_prog fbs_prog;  /* device-resident levelised program tied to one ctx    */
+
+const char *fbs_last_error(void);
+int fbs_abi_version(void);
+
+/* ---- context / keys ------------------------------------------------------------------------------ */
+int fbs_ctx_create(const fbs_params *params, int device, uint64_t seed, fbs_ctx **out);
+int fbs_keygen(fbs_ctx *ctx);                 /* seeded, deterministic: identical on every rank/device */
+int fbs_ctx_destroy(fbs_ctx *ctx);
+int fbs_ctx_info(const fbs_ctx *ctx, int32_t *sm_count, int64_t *bsk_bytes, int64_t *ksk_bytes, int32_t *br_smem_bytes);
+
+/* ---- program ------------------------------------------------------------------------------------- */
+int fbs_prog_load(fbs_ctx *ctx, const fbs_prog_desc *desc, fbs_prog **out);   /* host arrays are copied */
+int fbs_prog_free(fbs_prog *prog);
+
+/* ---- one-call evaluation with HOST buffers: the drop-in for LutExecEnv.eval ------------------------
+ * in  : [n_inputs][B] bits, row-major (one row per Input in instruction order, reference fbs_exec_env.py:213-214)
+ * out : [n_outputs][B] values mod 2p (one row per entry of LutExecEnv.outputs, reference fbs_exec_env.py:225-229)
+ * inst_offset/B_total number the instances globally so that sharded ranks encrypt with distinct randomness.
+ * Instances are processed in chunks that fit `max_wire_bytes` of device memory (0 = default budget). */
+int fbs_eval_bits(fbs_ctx *ctx, fbs_prog *prog, const uint8_t *in, int64_t B, int64_t inst_offset, int64_t B_total,
+                  uint64_t enc_seed, size_t max_wire_bytes, uint8_t *out, fbs_run_stats *stats);
+
+/* ---- split form with device-resident ciphertexts (timing, multi-GPU node sharding) ------------------
+ * wires_dev: [n_slots][B][k*N+1] uint64, caller-allocated (fbs_wires_bytes). */
+int fbs_wires_bytes(const fbs_ctx *ctx, const fbs_prog *prog, int64_t B, size_t *bytes);
+int fbs_encrypt_inputs(fbs_ctx *ctx, fbs_prog *prog, const uint8_t *in_dev, int64_t B, int64_t inst_offset,
+                       int64_t B_total, uint64_t enc_seed, uint64_t *wires_dev, void *stream);
+/* runs bootstraps [node_begin, node_end) of level `level` (indices relative to the level; -1,-1 = all) */
+int fbs_run_level(fbs_ctx *ctx, fbs_prog *prog, int32_t level, int32_t node_begin, int32_t node_end, int64_t B,
+                  uint64_t *wires_dev, void *stream, fbs_run_stats *stats);
+int fbs_run(fbs_ctx *ctx, fbs_prog *prog, int64_t B, uint64_t *wires_dev, void *stream, fbs_run_stats *stats);
+int fbs_decrypt_outputs(fbs_ctx *ctx, fbs_prog *prog, int64_t B, const uint64_t *wires_dev, uint8_t *out_dev, void *stream);
+
+/* ---- PBS micro-benchmark (BASELINE.json configs[4]) -------------------------------------------------
+ * count independent bootstraps: encrypt msgs[i] in Z_2p, bootstrap with tables[i*2p .. i*2p+tlen[i]),
+ * decrypt into out[i].  Host buffers.  `resident` != 0 keeps ciphertexts on the device across the timed
+ * part so stats->ms_* cover key-switch + blind rotation only. */
+int fbs_pbs_batch(fbs_ctx *ctx, int32_t p, const uint8_t *msgs, const uint8_t *tables, const uint8_t *tlen,
+                  const int32_t *modes, int64_t count, uint64_t enc_seed, uint8_t *out, fbs_run_stats *stats);
+
+/* ---- cleartext evaluation of the same program on the GPU ---------------------------------------------
+ * The literal counterpart of the reference's hot loop (fbs_exec_env.py:218-220 / bit_exec_env.py:183-185):
+ * integer lincomb + table look-up per (node, instance).  Needs no keys. */
+int fbs_clear_eval(fbs_ctx *ctx, fbs_prog *prog, const uint8_t *in, int64_t B, uint8_t *out, fbs_run_stats *stats);
+
+/* ---- parity taps (used by tests/ only; product code never calls them) ------------------------------- */
+int fbs_debug_get_keys(fbs_ctx *ctx, uint8_t *s_lwe, uint8_t *s_big, uint64_t *ksk, uint64_t *bsk_coef);
+int fbs_debug_ntt(fbs_ctx *ctx, uint64_t *polys_host, int64_t count, int32_t inverse);
+/* one PBS per input ciphertext with every intermediate: ks [count][n+1] u64, ms [count][n+1] u16, acc [count][(k+1)N] */
+int fbs_debug_pbs(fbs_ctx *ctx, int32_t p, const uint64_t *in_cts, const uint8_t *tables, const uint8_t *tlen,
+                  const int32_t *modes, int64_t count, uint64_t *out_cts, uint64_t *tap_ks, uint16_t *tap_ms, uint64_t *tap_acc);
+int fbs_debug_encrypt(fbs_ctx *ctx, int32_t p, const int32_t *msgs, const uint64_t *ct_ids, int64_t count, uint64_t enc_seed, uint64_t *out_cts);
+int fbs_debug_decrypt(fbs_ctx *ctx, int32_t p, const uint64_t *cts, int64_t count, int32_t *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FBS_B200_H */

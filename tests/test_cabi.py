@@ -1,0 +1,52 @@
+"""The C-ABI library: builds for sm_100a, loads, and exports every symbol include/fbs_b200.h declares.
+No compute calls here (no GPU in the build container)."""
+import ctypes
+import os
+import re
+import subprocess
+
+import pytest
+
+from conftest import ROOT
+from tfhe_fbs_map_b200 import backend, build
+
+HEADER = os.path.join(ROOT, "include", "fbs_b200.h")
+
+
+def declared_functions():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(fbs_[a-z0-9_]+)\s*\(", src)))
+
+
+@pytest.fixture(scope="module")
+def libpath():
+    return build.build()
+
+
+def test_header_and_binding_agree():
+    assert set(declared_functions()) == set(backend.EXPORTS)
+
+
+def test_library_exports_every_declared_symbol(libpath):
+    lib = ctypes.CDLL(libpath)
+    for fn in declared_functions():
+        assert hasattr(lib, fn), fn
+    lib.fbs_abi_version.restype = ctypes.c_int
+    assert lib.fbs_abi_version() == 1
+
+
+def test_library_is_sm100a_with_tma(libpath):
+    out = subprocess.run(["cuobjdump", "-lelf", libpath], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+    sass = subprocess.run(["cuobjdump", "-sass", "-fun", "_Z14k_blind_rotateILi11ELi1ELi1ELb1EEv6BRArgs", libpath],
+                          capture_output=True, text=True).stdout
+    assert "UBLKCP" in sass          # cp.async.bulk = TMA bulk copy streams the bootstrapping key
+    assert "IMAD.WIDE" in sass       # the arithmetic runs on the integer pipes
+
+
+def test_errors_are_codes_not_crashes(libpath):
+    lib = backend.load_library(libpath)
+    rc = lib.fbs_ctx_create(None, 0, 0, None)
+    assert rc == -1 and b"null" in lib.fbs_last_error()
+    assert lib.fbs_keygen(None) == -1

@@ -1,0 +1,642 @@
+// api.cu -- C ABI of the B200 encrypted executor (include/fbs_b200.h): contexts, key generation, level
+// scheduler, host-buffer evaluation, parity taps.  No CPU fallback anywhere: every compute entry point
+// launches the CUDA kernels in kernels.cuh or fails.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <algorithm>
+#include "../../include/fbs_b200.h"
+#include "kernels.cuh"
+
+// ------------------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+static int fail(int code, const std::string &msg) { g_err = msg; return code; }
+#define CK(call)                                                                                          \
+    do {                                                                                                  \
+        cudaError_t e_ = (call);                                                                          \
+        if (e_ != cudaSuccess)                                                                            \
+            return fail(FBS_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_) + " (" __FILE__ ":" + std::to_string(__LINE__) + ")"); \
+    } while (0)
+#define CKR(expr) do { int r_ = (expr); if (r_ != FBS_OK) return r_; } while (0)
+
+extern "C" const char *fbs_last_error(void) { return g_err.c_str(); }
+extern "C" int fbs_abi_version(void) { return 1; }
+
+// ------------------------------------------------------------------------------------------------------
+// blind-rotate kernel variants
+// ------------------------------------------------------------------------------------------------------
+typedef cudaError_t (*br_launch_fn)(const BRArgs &, long long grid, size_t smem, cudaStream_t);
+struct BRVariant { int logN, k, l; bool bsk_smem; int threads; size_t (*smem)(int n); br_launch_fn launch; cudaError_t (*prepare)(size_t smem); };
+
+template <int LOGN, int K, int L, bool SM>
+static cudaError_t br_launch(const BRArgs &a, long long grid, size_t smem, cudaStream_t st)
+{
+    k_blind_rotate<LOGN, K, L, SM><<<(unsigned)grid, BRCfg<LOGN, K, L, SM>::THREADS, smem, st>>>(a);
+    return cudaGetLastError();
+}
+template <int LOGN, int K, int L, bool SM>
+static cudaError_t br_prepare(size_t smem)
+{
+    return cudaFuncSetAttribute(k_blind_rotate<LOGN, K, L, SM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+}
+template <int LOGN, int K, int L, bool SM> static size_t br_smem(int n) { return BRCfg<LOGN, K, L, SM>::smem_bytes(n); }
+#define BRV(LOGN, K, L, SM) { LOGN, K, L, SM, BRCfg<LOGN, K, L, SM>::THREADS, br_smem<LOGN, K, L, SM>, br_launch<LOGN, K, L, SM>, br_prepare<LOGN, K, L, SM> }
+static const BRVariant g_br_variants[] = {
+    BRV(11, 1, 1, true),    // set A
+    BRV(11, 1, 2, false),   // set C (row does not fit shared memory next to the accumulator: BSK read from L2)
+    BRV(10, 2, 1, true),    // set S
+    BRV(8, 1, 2, true), BRV(8, 2, 1, true), BRV(9, 1, 1, true), BRV(10, 1, 3, true),   // toy sets (tests)
+};
+
+typedef void (*ntt_launch_fn)(const u64 *, u64 *, int, const u64 *, const u64 *, u64, long long, cudaStream_t);
+template <int LOGN>
+static void ntt_launch(const u64 *in, u64 *out, int mode, const u64 *pr, const u64 *pir, u64 ninv, long long count, cudaStream_t st)
+{
+    k_ntt<LOGN><<<(unsigned)count, NttPlan<LOGN>::T, 0, st>>>(in, out, mode, pr, pir, ninv);
+}
+static ntt_launch_fn ntt_for(int logN)
+{
+    switch (logN) { case 8: return ntt_launch<8>; case 9: return ntt_launch<9>; case 10: return ntt_launch<10>; case 11: return ntt_launch<11>; }
+    return nullptr;
+}
+
+// ------------------------------------------------------------------------------------------------------
+struct fbs_ctx {
+    fbs_params P; int device = 0; u64 seed = 0; int logN = 0, sm_count = 0;
+    bool have_keys = false;
+    const BRVariant *br = nullptr; size_t br_smem = 0;
+    u8 *d_s_lwe = nullptr, *d_s_big = nullptr;
+    u64 *d_ksk = nullptr, *d_colsum = nullptr, *d_bsk = nullptr, *d_bsk_coef = nullptr;
+    u64 *d_psi_rev = nullptr, *d_psi_inv_rev = nullptr, *d_gad_bsk = nullptr, *d_gad_ks = nullptr;
+    u64 ninv = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[8] = {};
+    // grow-only level scratch
+    u8 *d_digits = nullptr; size_t cap_digits = 0;
+    u64 *d_body = nullptr; size_t cap_body = 0;
+    u16 *d_ms = nullptr; size_t cap_ms = 0;
+    // staging for host-buffer calls
+    u8 *d_io = nullptr; size_t cap_io = 0;
+    u64 *d_wires = nullptr; size_t cap_wires = 0;
+};
+struct fbs_prog {
+    fbs_ctx *ctx = nullptr;
+    int32_t p = 0, n_inputs = 0, n_lincombs = 0, n_boots = 0, n_levels = 0, n_slots = 0, n_outputs = 0;
+    std::vector<int32_t> lc_level_ptr, bs_level_ptr, bs_lc;
+    int max_lc_per_level = 0;
+    int32_t *d_i32 = nullptr; u8 *d_tab = nullptr;        // one arena for all int32 arrays
+    int32_t *d_lc_level_ptr, *d_bs_level_ptr, *d_lc_ptr, *d_lc_slot, *d_lc_coef, *d_lc_const, *d_bs_lc, *d_bs_slot,
+        *d_bs_tab_ptr, *d_bs_mode, *d_in_slot, *d_out_ptr, *d_out_slot, *d_out_coef, *d_out_const;
+};
+
+template <class T> static int dev_alloc(T **p, size_t count)
+{
+    *p = nullptr;
+    if (count == 0) count = 1;
+    CK(cudaMalloc((void **)p, count * sizeof(T)));
+    return FBS_OK;
+}
+template <class T> static int grow(T **p, size_t *cap, size_t need)
+{
+    if (need <= *cap) return FBS_OK;
+    if (*p) CK(cudaFree(*p));
+    *p = nullptr; *cap = 0;
+    size_t want = need + need / 8;
+    CK(cudaMalloc((void **)p, want * sizeof(T)));
+    *cap = want;
+    return FBS_OK;
+}
+static u32 bitrev32(u32 x, int bits) { u32 r = 0; for (int i = 0; i < bits; i++) { r = (r << 1) | (x & 1); x >>= 1; } return r; }
+
+// ------------------------------------------------------------------------------------------------------
+extern "C" int fbs_ctx_create(const fbs_params *params, int device, uint64_t seed, fbs_ctx **out)
+{
+    if (!params || !out) return fail(FBS_ERR_ARG, "fbs_ctx_create: null argument");
+    const fbs_params &P = *params;
+    int logN = 0; while ((1 << logN) < P.N) logN++;
+    if ((1 << logN) != P.N) return fail(FBS_ERR_ARG, "N must be a power of two");
+    if (P.ks_beta < 1 || P.ks_beta > 8 || P.ks_l < 1 || P.ks_l > 8 || P.ks_beta * P.ks_l > 40)
+        return fail(FBS_ERR_ARG, "unsupported key-switch decomposition (need 1<=ks_beta<=8, 1<=ks_l<=8)");
+    if (P.bsk_beta * P.bsk_l > 48 || P.bsk_beta < 2) return fail(FBS_ERR_ARG, "unsupported blind-rotate decomposition");
+    if (P.n < 1 || P.n > 4095) return fail(FBS_ERR_ARG, "n out of range");
+    const BRVariant *br = nullptr;
+    for (const BRVariant &v : g_br_variants) if (v.logN == logN && v.k == P.k && v.l == P.bsk_l) { br = &v; break; }
+    if (!br) return fail(FBS_ERR_ARG, "no blind-rotate kernel compiled for (N=" + std::to_string(P.N) + ", k=" + std::to_string(P.k) + ", l=" + std::to_string(P.bsk_l) + ")");
+    int ndev = 0;
+    CK(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return fail(FBS_ERR_ARG, "no such CUDA device");
+    CK(cudaSetDevice(device));
+    fbs_ctx *c = new fbs_ctx();
+    c->P = P; c->device = device; c->seed = seed; c->logN = logN; c->br = br;
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    c->sm_count = prop.multiProcessorCount;
+    c->br_smem = br->smem(P.n);
+    if (c->br_smem > (size_t)prop.sharedMemPerBlockOptin)
+        return fail(FBS_ERR_ARG, "blind-rotate kernel needs " + std::to_string(c->br_smem) + " B shared memory, device offers " + std::to_string(prop.sharedMemPerBlockOptin));
+    CK(br->prepare(c->br_smem));
+    CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    for (auto &e : c->ev) CK(cudaEventCreate(&e));
+    // twiddles psi^bitrev(i): 7 generates Z_P^*
+    const int N = P.N;
+    std::vector<u64> pr(N), pir(N);
+    const u64 psi = gl_pow_host(7, (GL_P - 1) / (2ULL * N)), psi_inv = gl_pow_host(psi, GL_P - 2);
+    for (int i = 0; i < N; i++) { u32 r = bitrev32((u32)i, logN); pr[i] = gl_pow_host(psi, r); pir[i] = gl_pow_host(psi_inv, r); }
+    c->ninv = gl_pow_host((u64)N, GL_P - 2);
+    CKR(dev_alloc(&c->d_psi_rev, N)); CKR(dev_alloc(&c->d_psi_inv_rev, N));
+    CK(cudaMemcpy(c->d_psi_rev, pr.data(), 8 * N, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(c->d_psi_inv_rev, pir.data(), 8 * N, cudaMemcpyHostToDevice));
+    std::vector<u64> gb(8, 0), gk(8, 0);
+    for (int j = 0; j < P.bsk_l; j++) gb[j] = fbs_gadget_host(P.bsk_beta, j);
+    for (int j = 0; j < P.ks_l; j++) gk[j] = fbs_gadget_host(P.ks_beta, j);
+    CKR(dev_alloc(&c->d_gad_bsk, 8)); CKR(dev_alloc(&c->d_gad_ks, 8));
+    CK(cudaMemcpy(c->d_gad_bsk, gb.data(), 64, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(c->d_gad_ks, gk.data(), 64, cudaMemcpyHostToDevice));
+    *out = c;
+    return FBS_OK;
+}
+
+extern "C" int fbs_keygen(fbs_ctx *c)
+{
+    if (!c) return fail(FBS_ERR_ARG, "fbs_keygen: null ctx");
+    CK(cudaSetDevice(c->device));
+    const fbs_params &P = c->P; const int n = P.n, k = P.k, N = P.N, l = P.bsk_l, lk = P.ks_l, D = k * N;
+    cudaStream_t st = c->stream;
+    if (!c->d_s_lwe) { CKR(dev_alloc(&c->d_s_lwe, n)); CKR(dev_alloc(&c->d_s_big, D)); }
+    k_gen_bits<<<(n + 255) / 256, 256, 0, st>>>(c->d_s_lwe, n, c->seed, DOM_SLWE);
+    k_gen_bits<<<(D + 255) / 256, 256, 0, st>>>(c->d_s_big, D, c->seed, DOM_SGLWE);
+    const size_t R = (size_t)D * lk;
+    if (!c->d_ksk) { CKR(dev_alloc(&c->d_ksk, R * (n + 1))); CKR(dev_alloc(&c->d_colsum, n + 1)); }
+    k_gen_ksk<<<(unsigned)R, 256, 0, st>>>(c->d_ksk, n, lk, c->seed, c->d_s_lwe, c->d_s_big, P.lwe_noise, c->d_gad_ks);
+    k_ksk_colsum<<<(n + 1 + 127) / 128, 128, 0, st>>>(c->d_ksk, (int)R, n + 1, c->d_colsum);
+    const int rows = (k + 1) * l;
+    const size_t total = (size_t)n * rows * (k + 1) * N;
+    if (!c->d_bsk) { CKR(dev_alloc(&c->d_bsk, total)); CKR(dev_alloc(&c->d_bsk_coef, total)); }
+    k_gen_bsk_fill<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(c->d_bsk_coef, k, N, c->seed, P.glwe_noise, total);
+    k_bsk_body<<<n * rows, 256, (size_t)N * 9, st>>>(c->d_bsk_coef, k, N, l, c->d_s_lwe, c->d_s_big, c->d_gad_bsk);
+    ntt_launch_fn nf = ntt_for(c->logN);
+    if (!nf) return fail(FBS_ERR_ARG, "no NTT kernel for this N");
+    nf(c->d_bsk_coef, c->d_bsk, 2, c->d_psi_rev, c->d_psi_inv_rev, c->ninv, (long long)(total / N), st);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(st));
+    // the coefficient-domain copy is only a parity tap: keep it for toy sizes, drop it for real key sizes
+    if (total * 8 > (64u << 20)) { CK(cudaFree(c->d_bsk_coef)); c->d_bsk_coef = nullptr; }
+    c->have_keys = true;
+    return FBS_OK;
+}
+
+extern "C" int fbs_ctx_destroy(fbs_ctx *c)
+{
+    if (!c) return FBS_OK;
+    cudaSetDevice(c->device);
+    void *ptrs[] = {c->d_s_lwe, c->d_s_big, c->d_ksk, c->d_colsum, c->d_bsk, c->d_bsk_coef, c->d_psi_rev, c->d_psi_inv_rev,
+                    c->d_gad_bsk, c->d_gad_ks, c->d_digits, c->d_body, c->d_ms, c->d_io, c->d_wires};
+    for (void *p : ptrs) if (p) cudaFree(p);
+    for (auto &e : c->ev) if (e) cudaEventDestroy(e);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return FBS_OK;
+}
+extern "C" int fbs_ctx_info(const fbs_ctx *c, int32_t *sm_count, int64_t *bsk_bytes, int64_t *ksk_bytes, int32_t *br_smem_bytes)
+{
+    if (!c) return fail(FBS_ERR_ARG, "null ctx");
+    const fbs_params &P = c->P;
+    if (sm_count) *sm_count = c->sm_count;
+    if (bsk_bytes) *bsk_bytes = (int64_t)P.n * (P.k + 1) * P.bsk_l * (P.k + 1) * P.N * 8;
+    if (ksk_bytes) *ksk_bytes = (int64_t)P.k * P.N * P.ks_l * (P.n + 1) * 8;
+    if (br_smem_bytes) *br_smem_bytes = (int32_t)c->br_smem;
+    return FBS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// program
+// ------------------------------------------------------------------------------------------------------
+extern "C" int fbs_prog_load(fbs_ctx *c, const fbs_prog_desc *d, fbs_prog **out)
+{
+    if (!c || !d || !out) return fail(FBS_ERR_ARG, "fbs_prog_load: null argument");
+    if (d->p < 2 || d->p > 128) return fail(FBS_ERR_ARG, "p out of range");
+    CK(cudaSetDevice(c->device));
+    const int nnz = d->n_lincombs ? d->lc_ptr[d->n_lincombs] : 0;
+    const int onz = d->n_outputs ? d->out_ptr[d->n_outputs] : 0;
+    const int tabn = d->n_boots ? d->bs_tab_ptr[d->n_boots] : 0;
+    // validation: slots in range, tables <= 2p and <= 64 entries, levels monotone
+    for (int i = 0; i < nnz; i++) if (d->lc_slot[i] < 0 || d->lc_slot[i] >= d->n_slots) return fail(FBS_ERR_ARG, "lincomb operand slot out of range");
+    for (int i = 0; i < onz; i++) if (d->out_slot[i] < 0 || d->out_slot[i] >= d->n_slots) return fail(FBS_ERR_ARG, "output operand slot out of range");
+    for (int i = 0; i < d->n_inputs; i++) if (d->in_slot[i] < 0 || d->in_slot[i] >= d->n_slots) return fail(FBS_ERR_ARG, "input slot out of range");
+    for (int q = 0; q < d->n_boots; q++) {
+        const int L = d->bs_tab_ptr[q + 1] - d->bs_tab_ptr[q];
+        if (L < 1 || L > 2 * d->p || L > 64) return fail(FBS_ERR_ARG, "bootstrap table longer than 2p (or 64) entries");
+        if (d->bs_slot[q] < 0 || d->bs_slot[q] >= d->n_slots) return fail(FBS_ERR_ARG, "bootstrap slot out of range");
+        if (d->bs_lc[q] < 0 || d->bs_lc[q] >= d->n_lincombs) return fail(FBS_ERR_ARG, "bootstrap lincomb index out of range");
+    }
+    fbs_prog *g = new fbs_prog();
+    g->ctx = c; g->p = d->p; g->n_inputs = d->n_inputs; g->n_lincombs = d->n_lincombs; g->n_boots = d->n_boots;
+    g->n_levels = d->n_levels; g->n_slots = d->n_slots; g->n_outputs = d->n_outputs;
+    g->lc_level_ptr.assign(d->lc_level_ptr, d->lc_level_ptr + d->n_levels + 1);
+    g->bs_level_ptr.assign(d->bs_level_ptr, d->bs_level_ptr + d->n_levels + 1);
+    g->bs_lc.assign(d->bs_lc, d->bs_lc + d->n_boots);
+    for (int lv = 0; lv < d->n_levels; lv++) {
+        g->max_lc_per_level = std::max(g->max_lc_per_level, g->lc_level_ptr[lv + 1] - g->lc_level_ptr[lv]);
+        for (int q = g->bs_level_ptr[lv]; q < g->bs_level_ptr[lv + 1]; q++) {
+            if (g->bs_lc[q] < g->lc_level_ptr[lv] || g->bs_lc[q] >= g->lc_level_ptr[lv + 1]) { delete g; return fail(FBS_ERR_ARG, "bootstrap uses a lincomb of another level"); }
+            if (q > g->bs_level_ptr[lv] && g->bs_lc[q] < g->bs_lc[q - 1]) { delete g; return fail(FBS_ERR_ARG, "bootstraps of a level must be sorted by lincomb index"); }
+        }
+    }
+    struct Piece { const int32_t *src; size_t n; int32_t **dst; };
+    Piece pieces[] = {
+        {d->lc_level_ptr, (size_t)d->n_levels + 1, &g->d_lc_level_ptr}, {d->bs_level_ptr, (size_t)d->n_levels + 1, &g->d_bs_level_ptr},
+        {d->lc_ptr, (size_t)d->n_lincombs + 1, &g->d_lc_ptr}, {d->lc_slot, (size_t)nnz, &g->d_lc_slot}, {d->lc_coef, (size_t)nnz, &g->d_lc_coef},
+        {d->lc_const, (size_t)d->n_lincombs, &g->d_lc_const}, {d->bs_lc, (size_t)d->n_boots, &g->d_bs_lc}, {d->bs_slot, (size_t)d->n_boots, &g->d_bs_slot},
+        {d->bs_tab_ptr, (size_t)d->n_boots + 1, &g->d_bs_tab_ptr}, {d->bs_mode, (size_t)d->n_boots, &g->d_bs_mode}, {d->in_slot, (size_t)d->n_inputs, &g->d_in_slot},
+        {d->out_ptr, (size_t)d->n_outputs + 1, &g->d_out_ptr}, {d->out_slot, (size_t)onz, &g->d_out_slot}, {d->out_coef, (size_t)onz, &g->d_out_coef},
+        {d->out_const, (size_t)d->n_outputs, &g->d_out_const}};
+    size_t tot = 0;
+    for (auto &pc : pieces) tot += pc.n + 4;
+    std::vector<int32_t> host(tot, 0);
+    if (dev_alloc(&g->d_i32, tot) != FBS_OK) { delete g; return FBS_ERR_CUDA; }
+    size_t off = 0;
+    for (auto &pc : pieces) {
+        if (pc.n && pc.src) memcpy(host.data() + off, pc.src, pc.n * 4);
+        *pc.dst = g->d_i32 + off;
+        off += (pc.n + 3) & ~(size_t)3;
+    }
+    CK(cudaMemcpy(g->d_i32, host.data(), tot * 4, cudaMemcpyHostToDevice));
+    if (dev_alloc(&g->d_tab, (size_t)tabn + 16) != FBS_OK) { delete g; return FBS_ERR_CUDA; }
+    if (tabn) CK(cudaMemcpy(g->d_tab, d->bs_tab, tabn, cudaMemcpyHostToDevice));
+    *out = g;
+    return FBS_OK;
+}
+extern "C" int fbs_prog_free(fbs_prog *g)
+{
+    if (!g) return FBS_OK;
+    cudaSetDevice(g->ctx->device);
+    if (g->d_i32) cudaFree(g->d_i32);
+    if (g->d_tab) cudaFree(g->d_tab);
+    delete g;
+    return FBS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// level scheduler
+// ------------------------------------------------------------------------------------------------------
+static inline size_t ct_words(const fbs_ctx *c) { return (size_t)c->P.k * c->P.N + 1; }
+
+extern "C" int fbs_wires_bytes(const fbs_ctx *c, const fbs_prog *g, int64_t B, size_t *bytes)
+{
+    if (!c || !g || !bytes || B < 1) return fail(FBS_ERR_ARG, "fbs_wires_bytes: bad argument");
+    *bytes = (size_t)g->n_slots * (size_t)B * ct_words(c) * 8;
+    return FBS_OK;
+}
+
+extern "C" int fbs_encrypt_inputs(fbs_ctx *c, fbs_prog *g, const uint8_t *in_dev, int64_t B, int64_t inst_offset, int64_t B_total,
+                                  uint64_t enc_seed, uint64_t *wires_dev, void *stream)
+{
+    if (!c || !g || !in_dev || !wires_dev || B < 1) return fail(FBS_ERR_ARG, "fbs_encrypt_inputs: bad argument");
+    if (!c->have_keys) return fail(FBS_ERR_STATE, "fbs_encrypt_inputs before fbs_keygen");
+    CK(cudaSetDevice(c->device));
+    if (g->n_inputs == 0) return FBS_OK;
+    EncArgs a{};
+    a.msgs = in_dev; a.in_slot = g->d_in_slot; a.out = wires_dev; a.s_big = c->d_s_big;
+    a.B = B; a.inst_offset = inst_offset; a.B_total = B_total; a.D = c->P.k * c->P.N; a.p = g->p;
+    a.enc_seed = enc_seed; a.noise_scale = c->P.glwe_noise;
+    k_encrypt<<<(unsigned)((long long)g->n_inputs * B), 256, 0, (cudaStream_t)stream>>>(a);
+    CK(cudaGetLastError());
+    return FBS_OK;
+}
+
+template <int LK> static void launch_lc(const LCArgs &a, long long tiles, cudaStream_t st) { k_lincomb_decomp<LK><<<(unsigned)tiles, 256, 0, st>>>(a); }
+
+static int run_level_impl(fbs_ctx *c, fbs_prog *g, int level, int nb, int ne, int64_t B, u64 *wires, cudaStream_t st,
+                          fbs_run_stats *stats, u64 *tap_ks, u64 *tap_acc, bool timed)
+{
+    const int b0 = g->bs_level_ptr[level], b1 = g->bs_level_ptr[level + 1];
+    if (nb < 0 && ne < 0) { nb = 0; ne = b1 - b0; }
+    if (nb < 0 || ne > b1 - b0 || nb > ne) return fail(FBS_ERR_ARG, "fbs_run_level: node range outside the level");
+    if (nb == ne) return FBS_OK;
+    const fbs_params &P = c->P;
+    const int D = P.k * P.N, n = P.n;
+    const int node0 = b0 + nb, node1 = b0 + ne;
+    const int lc0 = g->bs_lc[node0], lc1 = g->bs_lc[node1 - 1] + 1;     // bootstraps are sorted by lincomb
+    const long long M = (long long)(lc1 - lc0) * B, tiles = (M + 15) / 16;
+    const size_t R = (size_t)D * P.ks_l;
+    CKR(grow(&c->d_digits, &c->cap_digits, (size_t)tiles * R * 16));
+    CKR(grow(&c->d_body, &c->cap_body, (size_t)tiles * 16));
+    CKR(grow(&c->d_ms, &c->cap_ms, (size_t)tiles * 16 * (n + 1)));
+    if (timed) CK(cudaEventRecord(c->ev[0], st));
+    LCArgs la{};
+    la.wires = wires; la.lc_ptr = g->d_lc_ptr; la.lc_slot = g->d_lc_slot; la.lc_coef = g->d_lc_coef; la.lc_const = g->d_lc_const;
+    la.digits = c->d_digits; la.body = c->d_body; la.B = B; la.M = M; la.lc_begin = lc0; la.D = D; la.p = g->p; la.ks_beta = P.ks_beta;
+    switch (P.ks_l) {
+    case 1: launch_lc<1>(la, tiles, st); break; case 2: launch_lc<2>(la, tiles, st); break; case 3: launch_lc<3>(la, tiles, st); break;
+    case 4: launch_lc<4>(la, tiles, st); break; case 5: launch_lc<5>(la, tiles, st); break; case 6: launch_lc<6>(la, tiles, st); break;
+    case 7: launch_lc<7>(la, tiles, st); break; default: launch_lc<8>(la, tiles, st); break;
+    }
+    CK(cudaGetLastError());
+    if (timed) CK(cudaEventRecord(c->ev[1], st));
+    KSArgs ka{};
+    ka.digits = c->d_digits; ka.body = c->d_body; ka.ksk = c->d_ksk; ka.colsum = c->d_colsum; ka.ms = c->d_ms; ka.tap_ks = tap_ks;
+    ka.M = M; ka.R = (int)R; ka.n = n; ka.ks_beta = P.ks_beta; ka.log2_2N = c->logN + 1;
+    dim3 kgrid((unsigned)((n + 1 + 127) / 128), (unsigned)tiles);
+    if (tiles > 65535) {     // gridDim.y limit: run in slabs of tiles
+        for (long long t0 = 0; t0 < tiles; t0 += 65535) {
+            KSArgs kb = ka; long long tn = std::min<long long>(65535, tiles - t0);
+            kb.digits += (size_t)t0 * R * 16; kb.body += t0 * 16; kb.ms += (size_t)t0 * 16 * (n + 1);
+            if (kb.tap_ks) kb.tap_ks += (size_t)t0 * 16 * (n + 1);
+            kb.M = std::min<long long>(M - t0 * 16, tn * 16);
+            k_keyswitch<<<dim3(kgrid.x, (unsigned)tn), 128, 0, st>>>(kb);
+        }
+    } else {
+        k_keyswitch<<<kgrid, 128, 0, st>>>(ka);
+    }
+    CK(cudaGetLastError());
+    if (timed) CK(cudaEventRecord(c->ev[2], st));
+    BRArgs ba{};
+    ba.ms = c->d_ms; ba.bsk = c->d_bsk; ba.psi_rev = c->d_psi_rev; ba.psi_inv_rev = c->d_psi_inv_rev;
+    ba.bs_lc = g->d_bs_lc; ba.bs_slot = g->d_bs_slot; ba.bs_tab_ptr = g->d_bs_tab_ptr; ba.bs_mode = g->d_bs_mode; ba.bs_tab = g->d_tab;
+    ba.wires = wires; ba.tap_acc = tap_acc; ba.B = B; ba.node_begin = node0; ba.lc_begin = lc0; ba.n = n; ba.p = g->p; ba.beta = P.bsk_beta;
+    const long long jobs = (long long)(node1 - node0) * B;
+    CK(c->br->launch(ba, jobs, c->br_smem, st));
+    if (timed) CK(cudaEventRecord(c->ev[3], st));
+    if (stats) { stats->n_pbs += jobs; stats->n_launches += 3; }
+    if (timed && stats) {
+        CK(cudaEventSynchronize(c->ev[3]));
+        float t;
+        CK(cudaEventElapsedTime(&t, c->ev[0], c->ev[1])); stats->ms_lincomb += t;
+        CK(cudaEventElapsedTime(&t, c->ev[1], c->ev[2])); stats->ms_keyswitch += t;
+        CK(cudaEventElapsedTime(&t, c->ev[2], c->ev[3])); stats->ms_blind_rotate += t;
+    }
+    return FBS_OK;
+}
+
+extern "C" int fbs_run_level(fbs_ctx *c, fbs_prog *g, int32_t level, int32_t node_begin, int32_t node_end, int64_t B,
+                             uint64_t *wires_dev, void *stream, fbs_run_stats *stats)
+{
+    if (!c || !g || !wires_dev || B < 1) return fail(FBS_ERR_ARG, "fbs_run_level: bad argument");
+    if (!c->have_keys) return fail(FBS_ERR_STATE, "fbs_run_level before fbs_keygen");
+    if (level < 0 || level >= g->n_levels) return fail(FBS_ERR_ARG, "fbs_run_level: no such level");
+    CK(cudaSetDevice(c->device));
+    return run_level_impl(c, g, level, node_begin, node_end, B, wires_dev, (cudaStream_t)stream, stats, nullptr, nullptr, stats != nullptr);
+}
+
+extern "C" int fbs_run(fbs_ctx *c, fbs_prog *g, int64_t B, uint64_t *wires_dev, void *stream, fbs_run_stats *stats)
+{
+    if (!c || !g || !wires_dev || B < 1) return fail(FBS_ERR_ARG, "fbs_run: bad argument");
+    if (!c->have_keys) return fail(FBS_ERR_STATE, "fbs_run before fbs_keygen");
+    CK(cudaSetDevice(c->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (stats) CK(cudaEventRecord(c->ev[4], st));
+    for (int lv = 0; lv < g->n_levels; lv++) CKR(run_level_impl(c, g, lv, -1, -1, B, wires_dev, st, stats, nullptr, nullptr, false));
+    if (stats) {
+        CK(cudaEventRecord(c->ev[5], st));
+        CK(cudaEventSynchronize(c->ev[5]));
+        float t; CK(cudaEventElapsedTime(&t, c->ev[4], c->ev[5])); stats->ms_total += t;
+    }
+    return FBS_OK;
+}
+
+extern "C" int fbs_decrypt_outputs(fbs_ctx *c, fbs_prog *g, int64_t B, const uint64_t *wires_dev, uint8_t *out_dev, void *stream)
+{
+    if (!c || !g || !wires_dev || !out_dev || B < 1) return fail(FBS_ERR_ARG, "fbs_decrypt_outputs: bad argument");
+    if (!c->have_keys) return fail(FBS_ERR_STATE, "fbs_decrypt_outputs before fbs_keygen");
+    CK(cudaSetDevice(c->device));
+    if (g->n_outputs == 0) return FBS_OK;
+    OutArgs a{};
+    a.wires = wires_dev; a.s_big = c->d_s_big; a.out_ptr = g->d_out_ptr; a.out_slot = g->d_out_slot; a.out_coef = g->d_out_coef;
+    a.out_const = g->d_out_const; a.out8 = out_dev; a.B = B; a.D = c->P.k * c->P.N; a.p = g->p;
+    k_decrypt<<<(unsigned)((long long)g->n_outputs * B), 256, 0, (cudaStream_t)stream>>>(a);
+    CK(cudaGetLastError());
+    return FBS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// host-buffer evaluation: the drop-in for LutExecEnv.eval
+// ------------------------------------------------------------------------------------------------------
+extern "C" int fbs_eval_bits(fbs_ctx *c, fbs_prog *g, const uint8_t *in, int64_t B, int64_t inst_offset, int64_t B_total,
+                             uint64_t enc_seed, size_t max_wire_bytes, uint8_t *out, fbs_run_stats *stats)
+{
+    if (!c || !g || (!in && g->n_inputs) || (!out && g->n_outputs) || B < 1) return fail(FBS_ERR_ARG, "fbs_eval_bits: bad argument");
+    if (!c->have_keys) return fail(FBS_ERR_STATE, "fbs_eval_bits before fbs_keygen");
+    CK(cudaSetDevice(c->device));
+    if (B_total < B) B_total = B;
+    const fbs_params &P = c->P;
+    const size_t CT = ct_words(c) * 8;
+    const size_t R = (size_t)P.k * P.N * P.ks_l;
+    const size_t per_inst = (size_t)g->n_slots * CT + (size_t)std::max(1, g->max_lc_per_level) * (R + 8 + 2 * (size_t)(P.n + 1));
+    if (max_wire_bytes == 0) {
+        size_t fr = 0, tot = 0;
+        CK(cudaMemGetInfo(&fr, &tot));
+        max_wire_bytes = std::min<size_t>((size_t)48 << 30, (fr + c->cap_wires * 8 + c->cap_digits) / 2);
+    }
+    int64_t Bc = (int64_t)std::max<size_t>(1, max_wire_bytes / per_inst);
+    if (Bc >= 16) Bc &= ~(int64_t)15;
+    Bc = std::min<int64_t>(Bc, B);
+    cudaStream_t st = c->stream;
+    CKR(grow(&c->d_wires, &c->cap_wires, (size_t)g->n_slots * Bc * ct_words(c)));
+    CKR(grow(&c->d_io, &c->cap_io, (size_t)(g->n_inputs + g->n_outputs + 1) * Bc));
+    u8 *d_in = c->d_io, *d_out = c->d_io + (size_t)g->n_inputs * Bc;
+    if (stats) CK(cudaEventRecord(c->ev[6], st));
+    for (int64_t off = 0; off < B; off += Bc) {
+        const int64_t bc = std::min<int64_t>(Bc, B - off);
+        if (g->n_inputs) {
+            CK(cudaMemcpy2DAsync(d_in, (size_t)bc, in + off, (size_t)B, (size_t)bc, (size_t)g->n_inputs, cudaMemcpyHostToDevice, st));
+            CKR(fbs_encrypt_inputs(c, g, d_in, bc, inst_offset + off, B_total, enc_seed, c->d_wires, st));
+            if (stats) stats->n_launches += 1;
+        }
+        for (int lv = 0; lv < g->n_levels; lv++) CKR(run_level_impl(c, g, lv, -1, -1, bc, c->d_wires, st, stats, nullptr, nullptr, false));
+        if (g->n_outputs) {
+            CKR(fbs_decrypt_outputs(c, g, bc, c->d_wires, d_out, st));
+            if (stats) stats->n_launches += 1;
+            CK(cudaMemcpy2DAsync(out + off, (size_t)B, d_out, (size_t)bc, (size_t)bc, (size_t)g->n_outputs, cudaMemcpyDeviceToHost, st));
+        }
+    }
+    if (stats) {
+        CK(cudaEventRecord(c->ev[7], st));
+        CK(cudaEventSynchronize(c->ev[7]));
+        float t; CK(cudaEventElapsedTime(&t, c->ev[6], c->ev[7])); stats->ms_total += t;
+    }
+    CK(cudaStreamSynchronize(st));
+    return FBS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// cleartext evaluation on the GPU
+// ------------------------------------------------------------------------------------------------------
+extern "C" int fbs_clear_eval(fbs_ctx *c, fbs_prog *g, const uint8_t *in, int64_t B, uint8_t *out, fbs_run_stats *stats)
+{
+    if (!c || !g || (!in && g->n_inputs) || (!out && g->n_outputs) || B < 1) return fail(FBS_ERR_ARG, "fbs_clear_eval: bad argument");
+    CK(cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    const size_t nio = (size_t)(g->n_inputs + g->n_outputs + g->n_slots + 1) * B;
+    u8 *d_io = nullptr; int32_t *d_lcv = nullptr; int *d_err = nullptr;
+    CKR(dev_alloc(&d_io, nio)); CKR(dev_alloc(&d_lcv, (size_t)std::max(1, g->max_lc_per_level) * B)); CKR(dev_alloc(&d_err, 1));
+    CK(cudaMemsetAsync(d_err, 0, 4, st));
+    u8 *d_in = d_io, *d_out = d_in + (size_t)g->n_inputs * B, *d_vals = d_out + (size_t)g->n_outputs * B;
+    if (g->n_inputs) CK(cudaMemcpyAsync(d_in, in, (size_t)g->n_inputs * B, cudaMemcpyHostToDevice, st));
+    if (stats) CK(cudaEventRecord(c->ev[6], st));
+    ClearArgs a{};
+    a.lc_level_ptr = g->d_lc_level_ptr; a.bs_level_ptr = g->d_bs_level_ptr; a.lc_ptr = g->d_lc_ptr; a.lc_slot = g->d_lc_slot; a.lc_coef = g->d_lc_coef;
+    a.lc_const = g->d_lc_const; a.bs_lc = g->d_bs_lc; a.bs_slot = g->d_bs_slot; a.bs_tab_ptr = g->d_bs_tab_ptr; a.in_slot = g->d_in_slot; a.bs_tab = g->d_tab;
+    a.out_ptr = g->d_out_ptr; a.out_slot = g->d_out_slot; a.out_coef = g->d_out_coef; a.out_const = g->d_out_const;
+    a.in = d_in; a.vals = d_vals; a.out = d_out; a.lcv = d_lcv; a.err = d_err; a.B = B; a.n_inputs = g->n_inputs; a.n_levels = g->n_levels; a.n_outputs = g->n_outputs;
+    k_clear_eval<<<(unsigned)((B + 255) / 256), 256, 0, st>>>(a);
+    CK(cudaGetLastError());
+    if (stats) CK(cudaEventRecord(c->ev[7], st));
+    int err = 0;
+    if (g->n_outputs) CK(cudaMemcpyAsync(out, d_out, (size_t)g->n_outputs * B, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(&err, d_err, 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (stats) { float t; CK(cudaEventElapsedTime(&t, c->ev[6], c->ev[7])); stats->ms_total += t; stats->n_launches += 1; stats->n_pbs += (int64_t)g->n_boots * B; }
+    cudaFree(d_io); cudaFree(d_lcv); cudaFree(d_err);
+    if (err) return fail(FBS_ERR_ARG, "cleartext evaluation: table index out of range at bootstrap #" + std::to_string(err - 1));
+    return FBS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// PBS batch + parity taps, built on a one-level program: count inputs, identity lincombs, one table each
+// ------------------------------------------------------------------------------------------------------
+static int make_pbs_prog(fbs_ctx *c, int p, const uint8_t *tables, int tab_stride, const uint8_t *tlen, const int32_t *modes, int64_t count, fbs_prog **out)
+{
+    const int n = (int)count;
+    std::vector<int32_t> lvl = {0, n}, lc_ptr(n + 1), lc_slot(n), lc_coef(n, 1), lc_const(n, 0), bs_lc(n), bs_slot(n), tab_ptr(n + 1), mode(n), in_slot(n),
+                         out_ptr(n + 1), out_slot(n), out_coef(n, 1), out_const(n, 0);
+    std::vector<u8> tab;
+    tab_ptr[0] = 0;
+    for (int i = 0; i < n; i++) {
+        lc_ptr[i] = i; lc_slot[i] = i; bs_lc[i] = i; bs_slot[i] = n + i; in_slot[i] = i; out_ptr[i] = i; out_slot[i] = n + i;
+        mode[i] = modes ? modes[i] : 1;
+        for (int t = 0; t < tlen[i]; t++) tab.push_back(tables[(size_t)i * tab_stride + t]);
+        tab_ptr[i + 1] = (int)tab.size();
+    }
+    lc_ptr[n] = n; out_ptr[n] = n;
+    fbs_prog_desc d{};
+    d.p = p; d.n_inputs = n; d.n_lincombs = n; d.n_boots = n; d.n_levels = 1; d.n_slots = 2 * n; d.n_outputs = n;
+    d.lc_level_ptr = lvl.data(); d.bs_level_ptr = lvl.data(); d.lc_ptr = lc_ptr.data(); d.lc_slot = lc_slot.data(); d.lc_coef = lc_coef.data();
+    d.lc_const = lc_const.data(); d.bs_lc = bs_lc.data(); d.bs_slot = bs_slot.data(); d.bs_tab_ptr = tab_ptr.data(); d.bs_tab = tab.data();
+    d.bs_mode = mode.data(); d.in_slot = in_slot.data(); d.out_ptr = out_ptr.data(); d.out_slot = out_slot.data(); d.out_coef = out_coef.data(); d.out_const = out_const.data();
+    return fbs_prog_load(c, &d, out);
+}
+
+extern "C" int fbs_pbs_batch(fbs_ctx *c, int32_t p, const uint8_t *msgs, const uint8_t *tables, const uint8_t *tlen, const int32_t *modes,
+                             int64_t count, uint64_t enc_seed, uint8_t *out, fbs_run_stats *stats)
+{
+    if (!c || !msgs || !tables || !tlen || !out || count < 1 || count > (1 << 24)) return fail(FBS_ERR_ARG, "fbs_pbs_batch: bad argument");
+    if (!c->have_keys) return fail(FBS_ERR_STATE, "fbs_pbs_batch before fbs_keygen");
+    CK(cudaSetDevice(c->device));
+    fbs_prog *g = nullptr;
+    CKR(make_pbs_prog(c, p, tables, 2 * p, tlen, modes, count, &g));
+    cudaStream_t st = c->stream;
+    int rc = FBS_OK;
+    do {
+        if ((rc = grow(&c->d_wires, &c->cap_wires, (size_t)g->n_slots * ct_words(c))) != FBS_OK) break;
+        if ((rc = grow(&c->d_io, &c->cap_io, (size_t)2 * count + 16)) != FBS_OK) break;
+        u8 *d_in = c->d_io, *d_out = c->d_io + count;
+        if (cudaMemcpyAsync(d_in, msgs, count, cudaMemcpyHostToDevice, st) != cudaSuccess) { rc = fail(FBS_ERR_CUDA, "pbs_batch H2D"); break; }
+        // B = 1 with one input per PBS: input i, instance 0 -> ciphertext id i
+        if ((rc = fbs_encrypt_inputs(c, g, d_in, 1, 0, 1, enc_seed, c->d_wires, st)) != FBS_OK) break;
+        if ((rc = run_level_impl(c, g, 0, -1, -1, 1, c->d_wires, st, stats, nullptr, nullptr, stats != nullptr)) != FBS_OK) break;
+        if ((rc = fbs_decrypt_outputs(c, g, 1, c->d_wires, d_out, st)) != FBS_OK) break;
+        if (cudaMemcpyAsync(out, d_out, count, cudaMemcpyDeviceToHost, st) != cudaSuccess) { rc = fail(FBS_ERR_CUDA, "pbs_batch D2H"); break; }
+        if (cudaStreamSynchronize(st) != cudaSuccess) { rc = fail(FBS_ERR_CUDA, std::string("pbs_batch sync: ") + cudaGetErrorString(cudaGetLastError())); break; }
+        if (stats) { stats->n_launches += 2; stats->ms_total += stats->ms_lincomb + stats->ms_keyswitch + stats->ms_blind_rotate; }
+    } while (0);
+    fbs_prog_free(g);
+    return rc;
+}
+
+extern "C" int fbs_debug_get_keys(fbs_ctx *c, uint8_t *s_lwe, uint8_t *s_big, uint64_t *ksk, uint64_t *bsk_coef)
+{
+    if (!c || !c->have_keys) return fail(FBS_ERR_STATE, "fbs_debug_get_keys before fbs_keygen");
+    CK(cudaSetDevice(c->device));
+    const fbs_params &P = c->P;
+    if (s_lwe) CK(cudaMemcpy(s_lwe, c->d_s_lwe, P.n, cudaMemcpyDeviceToHost));
+    if (s_big) CK(cudaMemcpy(s_big, c->d_s_big, (size_t)P.k * P.N, cudaMemcpyDeviceToHost));
+    if (ksk) CK(cudaMemcpy(ksk, c->d_ksk, (size_t)P.k * P.N * P.ks_l * (P.n + 1) * 8, cudaMemcpyDeviceToHost));
+    if (bsk_coef) {
+        if (!c->d_bsk_coef) return fail(FBS_ERR_STATE, "coefficient-domain BSK is only kept for key sizes <= 64 MiB");
+        CK(cudaMemcpy(bsk_coef, c->d_bsk_coef, (size_t)P.n * (P.k + 1) * P.bsk_l * (P.k + 1) * P.N * 8, cudaMemcpyDeviceToHost));
+    }
+    return FBS_OK;
+}
+extern "C" int fbs_debug_ntt(fbs_ctx *c, uint64_t *polys, int64_t count, int32_t inverse)
+{
+    if (!c || !polys || count < 1) return fail(FBS_ERR_ARG, "fbs_debug_ntt: bad argument");
+    CK(cudaSetDevice(c->device));
+    ntt_launch_fn nf = ntt_for(c->logN);
+    if (!nf) return fail(FBS_ERR_ARG, "no NTT kernel for this N");
+    u64 *d_a = nullptr, *d_b = nullptr; const size_t words = (size_t)count * c->P.N;
+    CKR(dev_alloc(&d_a, words)); CKR(dev_alloc(&d_b, words));
+    CK(cudaMemcpy(d_a, polys, words * 8, cudaMemcpyHostToDevice));
+    nf(d_a, d_b, inverse ? 1 : 0, c->d_psi_rev, c->d_psi_inv_rev, c->ninv, count, c->stream);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaMemcpy(polys, d_b, words * 8, cudaMemcpyDeviceToHost));
+    cudaFree(d_a); cudaFree(d_b);
+    return FBS_OK;
+}
+extern "C" int fbs_debug_encrypt(fbs_ctx *c, int32_t p, const int32_t *msgs, const uint64_t *ct_ids, int64_t count, uint64_t enc_seed, uint64_t *out_cts)
+{
+    if (!c || !msgs || !out_cts || count < 1) return fail(FBS_ERR_ARG, "fbs_debug_encrypt: bad argument");
+    if (!c->have_keys) return fail(FBS_ERR_STATE, "fbs_debug_encrypt before fbs_keygen");
+    CK(cudaSetDevice(c->device));
+    int32_t *d_m = nullptr; u64 *d_id = nullptr, *d_ct = nullptr; const size_t CT = ct_words(c);
+    CKR(dev_alloc(&d_m, count)); CKR(dev_alloc(&d_id, count)); CKR(dev_alloc(&d_ct, (size_t)count * CT));
+    CK(cudaMemcpy(d_m, msgs, count * 4, cudaMemcpyHostToDevice));
+    if (ct_ids) CK(cudaMemcpy(d_id, ct_ids, count * 8, cudaMemcpyHostToDevice));
+    EncArgs a{};
+    a.msgs32 = d_m; a.ct_ids = ct_ids ? d_id : nullptr; a.out = d_ct; a.s_big = c->d_s_big; a.D = c->P.k * c->P.N; a.p = p;
+    a.enc_seed = enc_seed; a.noise_scale = c->P.glwe_noise; a.B = 1; a.B_total = 1;
+    k_encrypt<<<(unsigned)count, 256, 0, c->stream>>>(a);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaMemcpy(out_cts, d_ct, (size_t)count * CT * 8, cudaMemcpyDeviceToHost));
+    cudaFree(d_m); cudaFree(d_id); cudaFree(d_ct);
+    return FBS_OK;
+}
+extern "C" int fbs_debug_decrypt(fbs_ctx *c, int32_t p, const uint64_t *cts, int64_t count, int32_t *out)
+{
+    if (!c || !cts || !out || count < 1) return fail(FBS_ERR_ARG, "fbs_debug_decrypt: bad argument");
+    if (!c->have_keys) return fail(FBS_ERR_STATE, "fbs_debug_decrypt before fbs_keygen");
+    CK(cudaSetDevice(c->device));
+    u64 *d_ct = nullptr; int32_t *d_o = nullptr; const size_t CT = ct_words(c);
+    CKR(dev_alloc(&d_ct, (size_t)count * CT)); CKR(dev_alloc(&d_o, count));
+    CK(cudaMemcpy(d_ct, cts, (size_t)count * CT * 8, cudaMemcpyHostToDevice));
+    OutArgs a{};
+    a.wires = d_ct; a.s_big = c->d_s_big; a.out32 = d_o; a.B = 1; a.D = c->P.k * c->P.N; a.p = p;
+    k_decrypt<<<(unsigned)count, 256, 0, c->stream>>>(a);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaMemcpy(out, d_o, count * 4, cudaMemcpyDeviceToHost));
+    cudaFree(d_ct); cudaFree(d_o);
+    return FBS_OK;
+}
+extern "C" int fbs_debug_pbs(fbs_ctx *c, int32_t p, const uint64_t *in_cts, const uint8_t *tables, const uint8_t *tlen, const int32_t *modes,
+                             int64_t count, uint64_t *out_cts, uint64_t *tap_ks, uint16_t *tap_ms, uint64_t *tap_acc)
+{
+    if (!c || !in_cts || !tables || !tlen || !out_cts || count < 1 || count > 65536) return fail(FBS_ERR_ARG, "fbs_debug_pbs: bad argument");
+    if (!c->have_keys) return fail(FBS_ERR_STATE, "fbs_debug_pbs before fbs_keygen");
+    CK(cudaSetDevice(c->device));
+    fbs_prog *g = nullptr;
+    CKR(make_pbs_prog(c, p, tables, 2 * p, tlen, modes, count, &g));
+    const size_t CT = ct_words(c); const fbs_params &P = c->P; cudaStream_t st = c->stream;
+    u64 *d_w = nullptr, *d_ks = nullptr, *d_acc = nullptr;
+    int rc = FBS_OK;
+    do {
+        if ((rc = dev_alloc(&d_w, (size_t)2 * count * CT)) != FBS_OK) break;
+        if ((rc = dev_alloc(&d_ks, (size_t)(count + 16) * (P.n + 1))) != FBS_OK) break;
+        if ((rc = dev_alloc(&d_acc, (size_t)count * (P.k + 1) * P.N)) != FBS_OK) break;
+        cudaMemcpy(d_w, in_cts, (size_t)count * CT * 8, cudaMemcpyHostToDevice);
+        if ((rc = run_level_impl(c, g, 0, -1, -1, 1, d_w, st, nullptr, d_ks, d_acc, false)) != FBS_OK) break;
+        if (cudaStreamSynchronize(st) != cudaSuccess) { rc = fail(FBS_ERR_CUDA, std::string("debug_pbs: ") + cudaGetErrorString(cudaGetLastError())); break; }
+        cudaMemcpy(out_cts, d_w + (size_t)count * CT, (size_t)count * CT * 8, cudaMemcpyDeviceToHost);
+        if (tap_ks) cudaMemcpy(tap_ks, d_ks, (size_t)count * (P.n + 1) * 8, cudaMemcpyDeviceToHost);
+        if (tap_ms) cudaMemcpy(tap_ms, c->d_ms, (size_t)count * (P.n + 1) * 2, cudaMemcpyDeviceToHost);
+        if (tap_acc) cudaMemcpy(tap_acc, d_acc, (size_t)count * (P.k + 1) * P.N * 8, cudaMemcpyDeviceToHost);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) rc = fail(FBS_ERR_CUDA, std::string("debug_pbs copies: ") + cudaGetErrorString(e));
+    } while (0);
+    if (d_w) cudaFree(d_w); if (d_ks) cudaFree(d_ks); if (d_acc) cudaFree(d_acc);
+    fbs_prog_free(g);
+    return rc;
+}

@@ -1,0 +1,579 @@
+// kernels.cuh -- sm_100a kernels of the encrypted FBS executor.
+//   K1a k_lincomb_decomp : LWE linear combination (weighted sum mod P) + key-switch gadget decomposition
+//   K1b k_keyswitch      : digit x KSK accumulation (2 IMAD.WIDE per MAC), fused modulus switch to 2N
+//   K2  k_blind_rotate   : test polynomial, n CMUX steps (decompose, NTT, BSK MAC, inverse NTT), accumulator in
+//                          shared memory, BSK rows streamed with cp.async.bulk (TMA) + mbarrier; K3 sample
+//                          extraction (+ table-mode offset) as epilogue
+//   K4  encrypt / decrypt / keygen, K5 stand-alone NTT (tests + BSK preprocessing), cleartext evaluator
+#pragma once
+#include <cuda_runtime.h>
+#include "common.cuh"
+#include "ntt.cuh"
+
+typedef uint8_t u8;
+typedef uint16_t u16;
+
+// ------------------------------------------------------------------------------------------------------
+// small device helpers
+// ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ u32 smem_u32(const void *p) { return (u32)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(u64 *bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(u64 *bar, u32 bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(u64 *bar, u32 parity)
+{
+    u32 ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(u64 *bar, u32 parity) { while (!mbar_try_wait(bar, parity)) { } }
+// 1-D bulk tensor-memory-accelerator copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void tma_load_1d(void *dst, const void *src, u32 bytes, u64 *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void bar_sync_named(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+
+// block-wide sum in Z_P (addition mod P is associative, so the tree order does not matter)
+template <int THREADS>
+__device__ __forceinline__ u64 block_sum_gl(u64 v, u64 *sh /* [THREADS/32] */)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        u64 w = __shfl_xor_sync(0xffffffffu, v, o);
+        v = gl_add(v, w);
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    __syncthreads();
+    if (lane == 0) sh[warp] = v;
+    __syncthreads();
+    u64 r = 0;
+#pragma unroll
+    for (int w = 0; w < THREADS / 32; w++) r = gl_add(r, sh[w]);
+    return r;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// K4: key generation, all seeded and deterministic
+// ------------------------------------------------------------------------------------------------------
+__global__ void k_gen_bits(u8 *out, int count, u64 seed, u64 dom)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) out[i] = (u8)(fbs_rnd64(seed, dom, (u64)i) & 1);
+}
+// KSK row r = i*lk + j : LWE_{s_lwe}( s_big[i] * g_j ), body last
+__global__ void __launch_bounds__(256) k_gen_ksk(u64 *ksk, int n, int lk, u64 seed, const u8 *__restrict__ s_lwe,
+                                                const u8 *__restrict__ s_big, u64 noise_scale, const u64 *__restrict__ gadgets)
+{
+    __shared__ u64 sh[8];
+    const size_t r = blockIdx.x;
+    u64 *row = ksk + r * (size_t)(n + 1);
+    u64 part = 0;
+    for (int q = threadIdx.x; q < n; q += 256) {
+        u64 a = fbs_rnd_uniform(seed, DOM_KSK_MASK, r * (u64)n + q);
+        row[q] = a;
+        if (s_lwe[q]) part = gl_add(part, a);
+    }
+    u64 body = block_sum_gl<256>(part, sh);
+    if (threadIdx.x == 0) {
+        body = gl_add(body, fbs_rnd_noise(seed, DOM_KSK_NOISE, r, noise_scale));
+        if (s_big[r / lk]) body = gl_add(body, gadgets[r % lk]);
+        row[n] = body;
+    }
+}
+__global__ void k_ksk_colsum(const u64 *__restrict__ ksk, int R, int cols, u64 *colsum)
+{
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= cols) return;
+    u64 s = 0;
+    for (int r = 0; r < R; r++) s = gl_add(s, ksk[(size_t)r * cols + c]);
+    colsum[c] = s;
+}
+// BSK in coefficient domain: masks uniform, body = noise (the key product is added by k_bsk_body)
+__global__ void k_gen_bsk_fill(u64 *bsk, int k, int N, u64 seed, u64 noise_scale, size_t total /* n*rows*(k+1)*N */)
+{
+    size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= total) return;
+    int q = (int)(g % N);
+    size_t poly = g / N;
+    int v = (int)(poly % (k + 1));
+    size_t ir = poly / (k + 1);
+    bsk[g] = (v < k) ? fbs_rnd_uniform(seed, DOM_BSK_MASK, (ir * k + v) * (u64)N + q)
+                     : fbs_rnd_noise(seed, DOM_BSK_NOISE, ir * (u64)N + q, noise_scale);
+}
+// body += sum_v A_v * S_v (negacyclic, S binary), then add s_lwe[i]*g_j to coefficient 0 of poly u
+__global__ void __launch_bounds__(256) k_bsk_body(u64 *bsk, int k, int N, int l, const u8 *__restrict__ s_lwe,
+                                                 const u8 *__restrict__ s_big, const u64 *__restrict__ gadgets)
+{
+    extern __shared__ u64 sh_a[];                 // [N] mask poly, then [N] key bits as bytes
+    u8 *sh_s = (u8 *)(sh_a + N);
+    const int ir = blockIdx.x, rows = (k + 1) * l;
+    const int i = ir / rows, r = ir % rows, u = r / l, j = r % l;
+    u64 *row = bsk + (size_t)ir * (k + 1) * N;
+    for (int v = 0; v < k; v++) {
+        __syncthreads();
+        for (int q = threadIdx.x; q < N; q += 256) { sh_a[q] = row[(size_t)v * N + q]; sh_s[q] = s_big[v * N + q]; }
+        __syncthreads();
+        for (int c = threadIdx.x; c < N; c += 256) {
+            u64 acc = row[(size_t)k * N + c];
+            for (int jj = 0; jj < N; jj++) {
+                if (!sh_s[jj]) continue;
+                int idx = c - jj;
+                acc = (idx >= 0) ? gl_add(acc, sh_a[idx]) : gl_sub(acc, sh_a[idx + N]);
+            }
+            row[(size_t)k * N + c] = acc;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && s_lwe[i]) row[(size_t)u * N] = gl_add(row[(size_t)u * N], gadgets[j]);
+}
+
+// ------------------------------------------------------------------------------------------------------
+// K5: stand-alone NTT.  mode 0: forward (natural in, bit-reversed out, array order as oracle/tfhe_ref.c)
+//                       mode 1: inverse incl. 1/N (for tests)
+//                       mode 2: BSK preprocessing: forward, times 1/N, stored SWIZZLED for the blind-rotate kernel
+// ------------------------------------------------------------------------------------------------------
+template <int LOGN>
+__global__ void __launch_bounds__(NttPlan<LOGN>::T) k_ntt(const u64 *__restrict__ in, u64 *__restrict__ out, int mode,
+                                                         const u64 *__restrict__ psi_rev, const u64 *__restrict__ psi_inv_rev, u64 ninv)
+{
+    using P = NttPlan<LOGN>;
+    __shared__ u64 bufA[P::N];
+    __shared__ u64 bufB[P::N];
+    const int tau = threadIdx.x;
+    const u64 *src = in + (size_t)blockIdx.x * P::N;
+    u64 *dst = out + (size_t)blockIdx.x * P::N;
+    u64 x[8];
+    auto sync = [] { __syncthreads(); };
+    if (mode == 1) {
+#pragma unroll
+        for (int e = 0; e < 8; e++) x[e] = src[P::idx(tau, e, P::inv_lb(0))];
+        ntt_inv_from<LOGN, 0>(x, tau, bufA, bufB, psi_inv_rev, sync, sync);
+#pragma unroll
+        for (int e = 0; e < 8; e++) dst[P::idx(tau, e, P::inv_lb(P::NPASS - 1))] = gl_mul(x[e], ninv);
+    } else {
+#pragma unroll
+        for (int e = 0; e < 8; e++) x[e] = src[P::idx(tau, e, P::fwd_lb(0))];
+        ntt_forward<LOGN>(x, tau, bufA, bufB, psi_rev, sync);
+#pragma unroll
+        for (int e = 0; e < 8; e++) {
+            const int id = P::idx(tau, e, P::fwd_lb(P::NPASS - 1));
+            if (mode == 0) dst[id] = x[e]; else dst[P::swz(id)] = gl_mul(x[e], ninv);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// K4: encrypt / decrypt
+// ------------------------------------------------------------------------------------------------------
+struct EncArgs {
+    const u8 *msgs;          // program inputs: [n_inputs][B] ; explicit: [count]
+    const int32_t *msgs32;   // explicit int32 messages (debug), used when != nullptr
+    const u64 *ct_ids;       // explicit ids or nullptr
+    const int32_t *in_slot;  // program inputs -> slot, or nullptr (explicit: ciphertext e goes to out + e*CT)
+    u64 *out;
+    const u8 *s_big;
+    long long B, inst_offset, B_total;
+    int D, p;
+    u64 enc_seed, noise_scale;
+};
+__global__ void __launch_bounds__(256) k_encrypt(EncArgs a)
+{
+    __shared__ u64 sh[8];
+    const long long e = blockIdx.x;
+    long long m;
+    u64 id;
+    u64 *ct;
+    if (a.in_slot) {
+        const long long i = e / a.B, b = e % a.B;
+        m = a.msgs[e];
+        id = (u64)i * (u64)a.B_total + (u64)(a.inst_offset + b);
+        ct = a.out + ((size_t)a.in_slot[i] * a.B + b) * (size_t)(a.D + 1);
+    } else {
+        m = a.msgs32 ? a.msgs32[e] : a.msgs[e];
+        id = a.ct_ids ? a.ct_ids[e] : (u64)e;
+        ct = a.out + (size_t)e * (a.D + 1);
+    }
+    u64 part = 0;
+    for (int q = threadIdx.x; q < a.D; q += 256) {
+        u64 x = fbs_rnd_uniform(a.enc_seed, DOM_ENC_MASK, id * (u64)a.D + q);
+        ct[q] = x;
+        if (a.s_big[q]) part = gl_add(part, x);
+    }
+    u64 body = block_sum_gl<256>(part, sh);
+    if (threadIdx.x == 0) {
+        body = gl_add(body, fbs_rnd_noise(a.enc_seed, DOM_ENC_NOISE, id, a.noise_scale));
+        const int p2 = 2 * a.p;
+        int mm = (int)(((m % p2) + p2) % p2);
+        ct[a.D] = gl_add(body, gl_mul((u64)mm, fbs_delta(a.p)));
+    }
+}
+// outputs are lincombs of wires: phase(sum c_o ct_o) + const*Delta, decoded to Z_2p
+struct OutArgs {
+    const u64 *wires; const u8 *s_big;
+    const int32_t *out_ptr, *out_slot, *out_coef, *out_const;   // nullptr out_ptr: plain decrypt of cts [count]
+    u8 *out8; int32_t *out32;
+    long long B; int D, p;
+};
+__global__ void __launch_bounds__(256) k_decrypt(OutArgs a)
+{
+    __shared__ u64 sh[8];
+    const long long e = blockIdx.x;
+    const size_t CT = (size_t)a.D + 1;
+    u64 part = 0, body = 0;
+    if (a.out_ptr) {
+        const long long q = e / a.B, b = e % a.B;
+        const int o0 = a.out_ptr[q], o1 = a.out_ptr[q + 1];
+        for (int o = o0; o < o1; o++) {
+            const u64 *ct = a.wires + ((size_t)a.out_slot[o] * a.B + b) * CT;
+            const u64 cf = gl_from_i64(a.out_coef[o]);
+            u64 acc = 0;
+            for (int w = threadIdx.x; w < a.D; w += 256) if (a.s_big[w]) acc = gl_add(acc, ct[w]);
+            part = gl_add(part, gl_mul(acc, cf));
+            body = gl_add(body, gl_mul(ct[a.D], cf));
+        }
+        body = gl_add(body, gl_mul(gl_from_i64(a.out_const[q]), fbs_delta(a.p)));
+    } else {
+        const u64 *ct = a.wires + (size_t)e * CT;
+        for (int w = threadIdx.x; w < a.D; w += 256) if (a.s_big[w]) part = gl_add(part, ct[w]);
+        body = ct[a.D];
+    }
+    u64 mask = block_sum_gl<256>(part, sh);
+    if (threadIdx.x == 0) {
+        int m = fbs_decode(gl_sub(body, mask), a.p);
+        if (a.out8) a.out8[e] = (u8)m;
+        if (a.out32) a.out32[e] = m;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// K1a: linear combination + key-switch decomposition.  One CTA = a tile of 16 (lincomb, instance) pairs, so
+// that the 16 digits of one (word, level) form one coalesced 16-byte store in the layout K1b consumes:
+//   digits[tile][r = i*lk + j][16]  (uint8, offset form d + B/2 in [0, B))
+// ------------------------------------------------------------------------------------------------------
+struct LCArgs {
+    const u64 *wires;
+    const int32_t *lc_ptr, *lc_slot, *lc_coef, *lc_const;
+    u8 *digits; u64 *body;
+    long long B, M;          // M = (#lincombs in range) * B
+    int lc_begin, D, p, ks_beta;
+};
+template <int LK>
+__global__ void __launch_bounds__(256) k_lincomb_decomp(LCArgs a)
+{
+    __shared__ int s_lc[16];
+    __shared__ long long s_inst[16];
+    const long long tile = blockIdx.x;
+    if (threadIdx.x < 16) {
+        long long m = tile * 16 + threadIdx.x;
+        s_lc[threadIdx.x] = (m < a.M) ? a.lc_begin + (int)(m / a.B) : -1;
+        s_inst[threadIdx.x] = (m < a.M) ? (m % a.B) : 0;
+    }
+    __syncthreads();
+    const size_t CT = (size_t)a.D + 1;
+    const size_t R = (size_t)a.D * LK;
+    const u32 halfB = 1u << (a.ks_beta - 1);
+    for (int i = threadIdx.x; i <= a.D; i += 256) {
+        u32 pk[LK][4];
+#pragma unroll
+        for (int j = 0; j < LK; j++) { pk[j][0] = pk[j][1] = pk[j][2] = pk[j][3] = 0; }
+#pragma unroll
+        for (int mm = 0; mm < 16; mm++) {
+            const int lc = s_lc[mm];
+            if (lc < 0) continue;
+            const long long inst = s_inst[mm];
+            u64 acc = 0;
+            for (int o = a.lc_ptr[lc]; o < a.lc_ptr[lc + 1]; o++) {
+                const u64 x = a.wires[((size_t)a.lc_slot[o] * a.B + inst) * CT + i];
+                acc = gl_add(acc, gl_mul(x, gl_from_i64(a.lc_coef[o])));
+            }
+            if (i == a.D) {
+                acc = gl_add(acc, gl_mul(gl_from_i64(a.lc_const[lc]), fbs_delta(a.p)));
+                a.body[tile * 16 + mm] = acc;
+            } else {
+                int d[LK];
+                fbs_balanced_digits<LK>(fbs_round_top(acc, a.ks_beta * LK), a.ks_beta, d);
+#pragma unroll
+                for (int j = 0; j < LK; j++) pk[j][mm >> 2] |= ((u32)(d[j] + (int)halfB)) << (8 * (mm & 3));
+            }
+        }
+        if (i < a.D) {
+            uint4 *dst = (uint4 *)(a.digits + ((size_t)tile * R + (size_t)i * LK) * 16);
+#pragma unroll
+            for (int j = 0; j < LK; j++) dst[j] = make_uint4(pk[j][0], pk[j][1], pk[j][2], pk[j][3]);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// K1b: key switch.  out[m][c] = [c==n]*body[m] - sum_r d[m][r] * KSK[r][c]  (mod P), then modulus switch to 2N.
+// Offset digits du = d + B/2 >= 0 make every product unsigned: sum du*x = two IMAD.WIDE per MAC into 64-bit
+// accumulators (low and high half of x), no carries; the offset is removed with (B/2)*colsum[c].
+// ------------------------------------------------------------------------------------------------------
+struct KSArgs {
+    const u8 *digits; const u64 *body; const u64 *ksk; const u64 *colsum;
+    u16 *ms; u64 *tap_ks;
+    long long M; int R, n, ks_beta, log2_2N;
+};
+__global__ void __launch_bounds__(128) k_keyswitch(KSArgs a)
+{
+    const int cols = a.n + 1;
+    int c = blockIdx.x * 128 + threadIdx.x;
+    const bool live = c < cols;
+    if (!live) c = cols - 1;
+    const long long tile = blockIdx.y;
+    const uint4 *dg = (const uint4 *)(a.digits + (size_t)tile * a.R * 16);
+    const u64 *kc = a.ksk + c;
+    u64 acc0[16], acc1[16];
+#pragma unroll
+    for (int mm = 0; mm < 16; mm++) { acc0[mm] = 0; acc1[mm] = 0; }
+    for (int r = 0; r < a.R; r += 4) {
+        u64 x[4]; uint4 d4[4];
+#pragma unroll
+        for (int t = 0; t < 4; t++) {
+            const int rr = (r + t < a.R) ? r + t : a.R - 1;
+            x[t] = kc[(size_t)rr * cols];
+            d4[t] = __ldg(dg + rr);
+            if (r + t >= a.R) d4[t] = make_uint4(0, 0, 0, 0), x[t] = 0;
+        }
+#pragma unroll
+        for (int t = 0; t < 4; t++) {
+            const u32 xl = (u32)x[t], xh = (u32)(x[t] >> 32);
+            const u32 w[4] = {d4[t].x, d4[t].y, d4[t].z, d4[t].w};
+#pragma unroll
+            for (int mm = 0; mm < 16; mm++) {
+                const u32 du = (w[mm >> 2] >> (8 * (mm & 3))) & 0xffu;
+                acc0[mm] += (u64)du * (u64)xl;
+                acc1[mm] += (u64)du * (u64)xh;
+            }
+        }
+    }
+    if (!live) return;
+    const u64 corr = gl_mul(a.colsum[c], (u64)(1u << (a.ks_beta - 1)));
+#pragma unroll
+    for (int mm = 0; mm < 16; mm++) {
+        const long long m = tile * 16 + mm;
+        if (m >= a.M) continue;
+        const u64 lo = acc0[mm] + (acc1[mm] << 32);
+        const u64 hi = (acc1[mm] >> 32) + (lo < acc0[mm] ? 1 : 0);
+        u64 v = gl_sub(corr, gl_reduce128(lo, hi));
+        if (c == a.n) v = gl_add(v, a.body[m]);
+        a.ms[(size_t)m * cols + c] = (u16)fbs_modswitch(v, a.log2_2N);
+        if (a.tap_ks) a.tap_ks[(size_t)m * cols + c] = v;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// K2 + K3: blind rotation + sample extraction.  One CTA per PBS; (K+1) thread groups of N/8 threads, group g
+// owns accumulator polynomial g: it decomposes/forward-transforms input polynomial g and produces/inverse-
+// transforms output polynomial g.  Shared memory (u64 words):
+//   ACC[(K+1)][N] natural order | SA[(K+1)][N], SB[(K+1)][N] transposes (swizzled) | DH[(K+1)L][N] digit
+//   spectra (aliases SB when L == 1) | BS[(K+1)L][(K+1)][N] current BSK row (TMA target, when BSK_SMEM)
+// ------------------------------------------------------------------------------------------------------
+struct BRArgs {
+    const u16 *ms;                      // [(lincomb - lc_begin) * B + inst][n+1]
+    const u64 *bsk, *psi_rev, *psi_inv_rev;
+    const int32_t *bs_lc, *bs_slot, *bs_tab_ptr, *bs_mode;
+    const u8 *bs_tab;
+    u64 *wires; u64 *tap_acc;
+    long long B;
+    int node_begin, lc_begin, n, p, beta;
+};
+template <int LOGN, int K, int L, bool BSK_SMEM>
+struct BRCfg {
+    static constexpr int N = 1 << LOGN, G = K + 1, T = N / 8, THREADS = G * T;
+    static constexpr size_t acc_w = (size_t)G * N, tr_w = (size_t)G * N;
+    static constexpr size_t dh_w = (L == 1) ? 0 : (size_t)G * L * N;
+    static constexpr size_t bs_w = BSK_SMEM ? (size_t)G * L * G * N : 0;
+    static constexpr size_t row_w = (size_t)G * L * G * N;       // BSK words per CMUX step
+    __host__ __device__ static constexpr size_t smem_bytes(int n)
+    {
+        return 8 * (acc_w + 2 * tr_w + dh_w + bs_w) + 16 /* mbarrier */ + (((size_t)(n + 1) * 2 + 15) / 16) * 16 + 64 /* table */;
+    }
+};
+
+template <int LOGN, int K, int L, bool BSK_SMEM>
+__global__ void __launch_bounds__((K + 1) * (1 << LOGN) / 8, 1) k_blind_rotate(BRArgs a)
+{
+    using C = BRCfg<LOGN, K, L, BSK_SMEM>;
+    using P = NttPlan<LOGN>;
+    constexpr int N = C::N, G = C::G, T = C::T;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    u64 *ACC = (u64 *)smem_raw;
+    u64 *SA = ACC + C::acc_w;
+    u64 *SB = SA + C::tr_w;
+    u64 *DH = (L == 1) ? SB : SB + C::tr_w;
+    u64 *BS = SB + C::tr_w + C::dh_w;
+    u64 *mbar = BS + C::bs_w;
+    u16 *s_ms = (u16 *)(mbar + 2);
+    u8 *s_tab = (u8 *)s_ms + (((size_t)(a.n + 1) * 2 + 15) / 16) * 16;
+
+    const int tid = threadIdx.x, g = tid / T, tau = tid % T;
+    const long long job = blockIdx.x;
+    const int node = a.node_begin + (int)(job / a.B);
+    const long long inst = job % a.B;
+    const int n = a.n, p = a.p;
+    const u16 *ms = a.ms + ((size_t)(a.bs_lc[node] - a.lc_begin) * a.B + inst) * (size_t)(n + 1);
+    const int tab0 = a.bs_tab_ptr[node], tabL = a.bs_tab_ptr[node + 1] - tab0, mode = a.bs_mode[node];
+
+    for (int i = tid; i <= n; i += C::THREADS) s_ms[i] = ms[i];
+    if (tid < 64) s_tab[tid] = (tid < tabL) ? a.bs_tab[tab0 + tid] : 0;
+    if (BSK_SMEM && tid == 0) mbar_init(mbar, 1);
+    __syncthreads();
+    if (BSK_SMEM && tid == 0) {
+        fence_proxy_async();
+        mbar_expect_tx(mbar, (u32)(C::row_w * 8));
+#pragma unroll 1
+        for (int q = 0; q < G * L * G; q++) tma_load_1d(BS + (size_t)q * N, a.bsk + (size_t)q * N, N * 8, mbar);
+    }
+    // ---- accumulator init: ACC = (0, .., 0, X^{-b~} * TV) ; TV[j] = F(round(j*p/N)), F(x) = tv[x]*Delta - s*Delta/2
+    {
+        const u64 delta = fbs_delta(p), off = gl_mul((u64)mode, delta >> 1);
+        const int bt = s_ms[n];
+        u64 *acc = ACC + (size_t)g * N;
+#pragma unroll
+        for (int e = 0; e < 8; e++) {
+            const int j = tau + e * T;
+            u64 val = 0;
+            if (g == K) {
+                int src = j + bt;                       // (X^{-bt} TV)[j] = +-TV[(j + bt) mod N]
+                bool neg = false;
+                if (src >= 2 * N) src -= 2 * N;
+                if (src >= N) { src -= N; neg = true; }
+                int x = (int)((2LL * src * p + N) / (2LL * N));
+                if (x >= p) { x -= p; neg = !neg; }
+                const u64 tvx = (x < tabL) ? (u64)s_tab[x] : 0;
+                const u64 F = gl_sub(gl_mul(tvx, delta), off);
+                val = neg ? gl_neg(F) : F;
+            }
+            acc[j] = val;
+        }
+    }
+    __syncthreads();
+
+    auto gsync = [g] { bar_sync_named(1 + g, T); };
+    u64 *sA = SA + (size_t)g * N, *sB = SB + (size_t)g * N;
+    u64 *acc = ACC + (size_t)g * N;
+    const int beta = a.beta;
+
+    for (int i = 0; i < n; i++) {
+        const int ai = s_ms[i];
+        // ---- rotate, subtract, decompose: digits of (X^{ai} ACC_g - ACC_g) in the first forward layout
+        u64 dg[L][8];
+#pragma unroll
+        for (int e = 0; e < 8; e++) {
+            const int j = tau + e * T;
+            int src = j - ai;
+            if (src < 0) src += 2 * N;
+            const u64 rot = (src < N) ? acc[src] : gl_neg(acc[src - N]);
+            const u64 diff = gl_sub(rot, acc[j]);
+            int d[L];
+            fbs_balanced_digits<L>(fbs_round_top(diff, beta * L), beta, d);
+#pragma unroll
+            for (int jj = 0; jj < L; jj++) dg[jj][e] = gl_from_i64(d[jj]);
+        }
+        // ---- forward NTTs, spectra to DH (swizzled, layout lb = 0)
+#pragma unroll
+        for (int jj = 0; jj < L; jj++) {
+            if (jj > 0) gsync();                     // previous transform's reads of sA/sB are complete
+            ntt_forward<LOGN>(dg[jj], tau, sA, sB, a.psi_rev, gsync);
+            u64 *dh = DH + (size_t)(g * L + jj) * N;
+            if (L == 1 && (P::NPASS & 1) == 1) gsync();   // DH aliases SB: the last transpose (pass NPASS-2) used SB iff NPASS is odd
+#pragma unroll
+            for (int e = 0; e < 8; e++) dh[P::swz(P::idx(tau, e, 0))] = dg[jj][e];
+        }
+        __syncthreads();
+        // ---- pointwise: out_g = sum_r DH[r] * BSK[r][g]
+        if (BSK_SMEM) mbar_wait(mbar, (u32)(i & 1));
+        u64 x[8];
+        {
+            const u64 *brow = BSK_SMEM ? BS : a.bsk + (size_t)i * C::row_w;
+#pragma unroll
+            for (int e = 0; e < 8; e++) {
+                const int id = P::swz(P::idx(tau, e, 0));
+                u64 s = 0;
+#pragma unroll
+                for (int r = 0; r < G * L; r++) s = gl_add(s, gl_mul(DH[(size_t)r * N + id], brow[((size_t)r * G + g) * N + id]));
+                x[e] = s;
+            }
+        }
+        // ---- inverse NTT; the first transpose barrier is CTA-wide: after it nobody reads DH/BS of this step
+        auto csync_prefetch = [&] {
+            __syncthreads();
+            if (BSK_SMEM && tid == 0 && i + 1 < n) {          // stream the next GGSW row while this step finishes
+                fence_proxy_async();
+                mbar_expect_tx(mbar, (u32)(C::row_w * 8));
+                const u64 *src = a.bsk + (size_t)(i + 1) * C::row_w;
+#pragma unroll 1
+                for (int q = 0; q < G * L * G; q++) tma_load_1d(BS + (size_t)q * N, src + (size_t)q * N, N * 8, mbar);
+            }
+        };
+        ntt_inv_from<LOGN, 0>(x, tau, sA, sB, a.psi_inv_rev, csync_prefetch, gsync);
+#pragma unroll
+        for (int e = 0; e < 8; e++) {
+            const int j = P::idx(tau, e, P::inv_lb(P::NPASS - 1));
+            acc[j] = gl_add(acc[j], x[e]);
+        }
+        __syncthreads();
+    }
+    // ---- K3: sample extraction of coefficient 0 (+ table-mode offset s*Delta/2 on the body)
+    const size_t CT = (size_t)K * N + 1;
+    u64 *out = a.wires + ((size_t)a.bs_slot[node] * a.B + inst) * CT;
+    for (int w = tid; w < K * N; w += C::THREADS) {
+        const int u = w / N, j = w % N;
+        out[w] = (j == 0) ? ACC[(size_t)u * N] : gl_neg(ACC[(size_t)u * N + N - j]);
+    }
+    if (tid == 0) out[(size_t)K * N] = gl_add(ACC[(size_t)K * N], gl_mul((u64)mode, fbs_delta(p) >> 1));
+    if (a.tap_acc) {
+        u64 *t = a.tap_acc + (size_t)job * G * N;
+        for (int w = tid; w < G * N; w += C::THREADS) t[w] = ACC[w];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// cleartext evaluator: the reference's hot loop (fbs_exec_env.py:215-220) as one thread per instance
+// wire values live in vals[slot][B] (uint8) so that neighbouring threads touch neighbouring bytes
+// ------------------------------------------------------------------------------------------------------
+struct ClearArgs {
+    const int32_t *lc_level_ptr, *bs_level_ptr, *lc_ptr, *lc_slot, *lc_coef, *lc_const, *bs_lc, *bs_slot, *bs_tab_ptr, *in_slot;
+    const u8 *bs_tab;
+    const int32_t *out_ptr, *out_slot, *out_coef, *out_const;
+    const u8 *in; u8 *vals; u8 *out; int32_t *lcv;     // lcv[n_lincombs_max_per_level][B] scratch
+    int *err;
+    long long B; int n_inputs, n_levels, n_outputs, lc_stride;
+};
+__global__ void __launch_bounds__(256) k_clear_eval(ClearArgs a)
+{
+    const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= a.B) return;
+    for (int i = 0; i < a.n_inputs; i++) a.vals[(size_t)a.in_slot[i] * a.B + b] = a.in[(size_t)i * a.B + b];
+    for (int lv = 0; lv < a.n_levels; lv++) {
+        const int l0 = a.lc_level_ptr[lv], l1 = a.lc_level_ptr[lv + 1];
+        for (int q = l0; q < l1; q++) {
+            int acc = a.lc_const[q];
+            for (int o = a.lc_ptr[q]; o < a.lc_ptr[q + 1]; o++) acc += a.lc_coef[o] * (int)a.vals[(size_t)a.lc_slot[o] * a.B + b];
+            a.lcv[(size_t)(q - l0) * a.B + b] = acc;
+        }
+        for (int q = a.bs_level_ptr[lv]; q < a.bs_level_ptr[lv + 1]; q++) {
+            const int idx = a.lcv[(size_t)(a.bs_lc[q] - l0) * a.B + b];
+            const int t0 = a.bs_tab_ptr[q], len = a.bs_tab_ptr[q + 1] - t0;
+            u8 v = 0;
+            if (idx < 0 || idx >= len) atomicExch(a.err, 1 + q); else v = a.bs_tab[t0 + idx];
+            a.vals[(size_t)a.bs_slot[q] * a.B + b] = v;
+        }
+    }
+    for (int q = 0; q < a.n_outputs; q++) {
+        int acc = a.out_const[q];
+        for (int o = a.out_ptr[q]; o < a.out_ptr[q + 1]; o++) acc += a.out_coef[o] * (int)a.vals[(size_t)a.out_slot[o] * a.B + b];
+        a.out[(size_t)q * a.B + b] = (u8)acc;
+    }
+}
