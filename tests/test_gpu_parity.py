@@ -1,0 +1,169 @@
+"""GPU parity: the CUDA path (through the C ABI) against the CPU oracle, bit for bit at every ciphertext tap, and
+against the reference's cleartext semantics after decryption.  Run on the B200 box: pytest -m gpu."""
+import numpy as np
+import pytest
+
+from conftest import (load_lbf_index, load_ref_mapped, out_hash, read_golden_blif, read_golden_lbf, selfcheck_inputs,
+                      unpack_outputs)
+from oracle import cleartext
+from oracle.tfhe_ref import RefTFHE, GOLDILOCKS_P
+from tfhe_fbs_map_b200 import levelize, params
+from tfhe_fbs_map_b200.formats import read_lbf
+
+pytestmark = pytest.mark.gpu
+TOYS = ["toy1", "toy2", "toy3", "toy4", "toy5", "toy6"]
+SEED = 777
+
+
+@pytest.fixture(scope="module")
+def ctxs():
+    from tfhe_fbs_map_b200.backend import B200Backend
+    cache = {}
+
+    def get(name):
+        if name not in cache:
+            ps = params.get(name)
+            cache[name] = (B200Backend(name, device=0, seed=SEED), RefTFHE(ps, seed=SEED))
+        return cache[name]
+    yield get
+    for be, _ in cache.values():
+        be.close()
+
+
+def tables_for(p, rng):
+    low = [int(x) for x in rng.integers(0, 2, p)]
+    tabs = [(low, 1), (low + [1 - x for x in low], 1), ([0] + low[1:] + [0], 0), ([1] + low[1:] + [1], 2)]
+    if p >= 3:
+        tabs.append(([0, 2, 1], 1))
+    return tabs
+
+
+@pytest.mark.parametrize("name", TOYS)
+def test_ntt_matches_oracle(ctxs, name):
+    be, ref = ctxs(name)
+    N = be.params.N
+    rng = np.random.default_rng(1)
+    polys = rng.integers(0, GOLDILOCKS_P, (5, N), dtype=np.uint64)
+    polys[0] = 0; polys[0, 1] = 1
+    fwd = be.debug_ntt(polys)
+    for i in range(len(polys)):
+        assert np.array_equal(fwd[i], ref.ntt(polys[i])), f"forward NTT poly {i}"
+    inv = be.debug_ntt(fwd, inverse=True)
+    assert np.array_equal(inv, polys)
+
+
+@pytest.mark.parametrize("name", TOYS)
+def test_keys_bit_exact(ctxs, name):
+    be, ref = ctxs(name)
+    g, r = be.debug_keys(), ref.keys()
+    for what, a, b in zip(("s_lwe", "s_big", "ksk", "bsk_coef"), g, r):
+        assert np.array_equal(a, b), what
+
+
+@pytest.mark.parametrize("name", TOYS)
+def test_encrypt_decrypt_bit_exact(ctxs, name):
+    be, ref = ctxs(name)
+    p = 7
+    msgs = np.arange(-3, 2 * p + 3, dtype=np.int32)
+    ids = np.arange(len(msgs), dtype=np.uint64) * 3 + 11
+    g = be.debug_encrypt(p, msgs, ids, enc_seed=99)
+    r = ref.encrypt(p, msgs, ids, 99)
+    assert np.array_equal(g, r)
+    assert np.array_equal(be.debug_decrypt(p, g), msgs % (2 * p))
+    assert np.array_equal(be.debug_decrypt(p, g), ref.decrypt(p, r))
+
+
+@pytest.mark.parametrize("name", TOYS)
+@pytest.mark.parametrize("p", [2, 3, 5, 7])
+def test_pbs_every_stage_bit_exact(ctxs, name, p):
+    be, ref = ctxs(name)
+    rng = np.random.default_rng(100 + p)
+    for tab, mode in tables_for(p, rng):
+        L = len(tab)
+        msgs = np.arange(L, dtype=np.int32)
+        cts = ref.encrypt(p, msgs, np.arange(L) + 5, 42)
+        tables = np.zeros((L, 2 * p), np.uint8); tables[:, :L] = tab
+        out, ks, ms, acc = be.debug_pbs(p, cts, tables, np.full(L, L, np.uint8), np.full(L, mode, np.int32))
+        for m in range(L):
+            ro, rks, rms, racc = ref.pbs(p, cts[m], tab, mode)
+            assert np.array_equal(ks[m], rks), f"key switch m={m}"
+            assert np.array_equal(ms[m], rms), f"modulus switch m={m}"
+            assert np.array_equal(acc[m], racc), f"blind rotation m={m}"
+            assert np.array_equal(out[m], ro), f"sample extract m={m}"
+        assert np.array_equal(be.debug_decrypt(p, out), np.array(tab)), (tab, mode)
+
+
+@pytest.mark.parametrize("circuit,p,toy", [("half_adder", 15, "toy3"), ("full_adder", 11, "toy3"), ("_2_input_gates", 15, "toy5"),
+                                           ("ascon_lut", 11, "toy3"), ("aes_sbox", 11, "toy5"), ("trivium_iter_v1", 15, "toy5")])
+def test_program_equals_oracle_and_cleartext(ctxs, circuit, p, toy):
+    be, ref = ctxs(toy)
+    e = next(x for x in load_ref_mapped() if x["circuit"] == circuit and x["p"] == p and x["mapper"] == "search" and not x.get("strict"))
+    env = read_lbf(e["lbf"])
+    prog = levelize(env, p)
+    cp = be.load(prog)
+    B = 40
+    inputs = selfcheck_inputs(e["input_names"])
+    bits = np.array([inputs[nm][:B] for nm in prog.input_names], dtype=np.uint8)
+    got = be.eval_bits(cp, bits)
+    want = unpack_outputs(e, batch=B)
+    for nm in prog.output_names:
+        assert np.array_equal(got[prog.out_index[nm]], want[str(nm)]), nm
+    # ragged chunking (chunk of 16 + 16 + 8) must give the same answer
+    CT = be.params.ct_words * 8
+    got2 = be.eval_bits(cp, bits, max_wire_bytes=16 * (prog.n_slots * CT + 64 * 1024))
+    assert np.array_equal(got, got2)
+    if B * prog.n_boots <= 400:
+        r = ref.eval_prog(prog, bits[:, :6].copy(), enc_seed=be.enc_seed, total=B)
+        assert np.array_equal(r, got[:, :6])
+
+
+def test_drop_in_eval_contract(ctxs):
+    """LutExecEnv.eval keeps the reference's return contract (fbs_exec_env.py:208-229): dict name -> int64[B], Python
+    scalar for Const outputs, outputs that are lincombs / inputs."""
+    be, _ = ctxs("toy3")
+    from tfhe_fbs_map_b200 import LutExecEnv
+    env = LutExecEnv()
+    a, b = env.input("a"), env.input("b")
+    d = env.linear([1, 2], [a, b]); e = env.linear([1, 1], [env.const(1), d]); f = env.bootstrap(e, [1, 0, 1, 1, 0])
+    g = env.linear([2, 1], [a, f]); h = env.bootstrap(g, [1, 1, 0, 2])
+    env.output("f", f); env.output("g", g); env.output("h", h); env.output("one", env.const(1)); env.output("a", a)
+    iv = {"a": [1, 0, 1, 0], "b": [1, 0, 0, 1]}
+    got = env.eval(iv, backend=be)
+    want = cleartext.lut_eval(env, iv)
+    assert got["one"] == 1 and isinstance(got["one"], int)
+    for k in ("f", "g", "h", "a"):
+        assert got[k].dtype == np.int64 and np.array_equal(got[k], want[k]), k
+    clear = env.eval_clear(iv, backend=be)
+    for k in ("f", "g", "h", "a"):
+        assert np.array_equal(clear[k], want[k])
+
+
+@pytest.mark.parametrize("name", sorted({e["circuit"] for e in load_ref_mapped()}))
+def test_bit_env_eval_on_gpu_matches_reference_outputs(ctxs, name):
+    be, _ = ctxs("toy1")
+    entry = next(e for e in load_ref_mapped() if e["circuit"] == name)
+    env = read_golden_blif(name)
+    got = env.eval(selfcheck_inputs(entry["input_names"]), backend=be)
+    want = unpack_outputs(entry)
+    for k in got:
+        assert np.array_equal(np.asarray(got[k]), want[str(k)]), k
+
+
+@pytest.mark.parametrize("item", load_lbf_index(), ids=lambda e: e["file"])
+def test_clear_kernel_reproduces_reference_hashes(ctxs, item):
+    be, _ = ctxs("toy1")
+    env = read_golden_lbf(item["file"])
+    got = env.eval_clear(selfcheck_inputs(item["input_names"]), backend=be)
+    assert out_hash(got) == item["out_sha256"]
+
+
+def test_error_paths(ctxs):
+    from tfhe_fbs_map_b200.backend import B200Backend, FbsError
+    be, _ = ctxs("toy1")
+    nk = B200Backend("toy1", device=0, keygen=False)
+    env = read_golden_lbf("adder8_p15.lbf")
+    with pytest.raises(FbsError):
+        nk.eval_bits(nk.load(levelize(env, 15)), np.zeros((16, 4), np.uint8))
+    with pytest.raises(AssertionError):
+        levelize(env, 5)                       # tables of 13 entries do not fit p=5
+    nk.close()

@@ -115,7 +115,10 @@ def levelize(env, p: int | None = None, reuse_slots: bool = True, shard_pad: int
     level's outputs can be all-gathered in place across ``shard_pad`` ranks (node-sharded mode)."""
     instrs = env.instructions
     if p is None:
-        p = 2 if clear else min_fbs_size(env)
+        if clear:   # cleartext look-ups have no modulus; pick one that passes the loader's table-length check
+            p = max([2] + [len(i.table) for i in env.instructions if isinstance(i, Bootstrap)])
+        else:
+            p = min_fbs_size(env)
     inputs = [i for i in instrs if isinstance(i, Input)]
     boots = [i for i in instrs if isinstance(i, Bootstrap)]
     by_name = {i.name: i for i in instrs}

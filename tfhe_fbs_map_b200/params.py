@@ -127,7 +127,10 @@ TOY_4 = ParamSet("toy4", n=12, k=1, N=1024, bsk_l=3, bsk_beta=8, ks_l=2, ks_beta
 TOY_5 = ParamSet("toy5", n=10, k=1, N=2048, bsk_l=1, bsk_beta=23, ks_l=5, ks_beta=3,
                  lwe_sigma=2.0 ** -30, glwe_sigma=2.0 ** -52, secure=False)
 
-PARAM_SETS = {ps.name: ps for ps in (SET_A, SET_C, SET_S, TOY_1, TOY_2, TOY_3, TOY_4, TOY_5)}
+TOY_6 = ParamSet("toy6", n=8, k=1, N=2048, bsk_l=2, bsk_beta=15, ks_l=6, ks_beta=3,
+                 lwe_sigma=2.0 ** -30, glwe_sigma=2.0 ** -52, secure=False)
+
+PARAM_SETS = {ps.name: ps for ps in (SET_A, SET_C, SET_S, TOY_1, TOY_2, TOY_3, TOY_4, TOY_5, TOY_6)}
 DEFAULT_SET = "A"
 
 
