@@ -123,6 +123,10 @@ int fbs_pbs_batch(fbs_ctx *ctx, int32_t p, const uint8_t *msgs, const uint8_t *t
  * integer lincomb + table look-up per (node, instance).  Needs no keys. */
 int fbs_clear_eval(fbs_ctx *ctx, fbs_prog *prog, const uint8_t *in, int64_t B, uint8_t *out, fbs_run_stats *stats);
 
+/* ---- integer roofline probe: sustained mad.wide.u32 (IMAD.WIDE) rate of the device, 32x32->64 multiplies/s.
+ * MEASURED_PEAKS.json holds only HBM and bf16 peaks; BASELINE.json asks for the integer-multiply roofline. */
+int fbs_measure_int_peak(fbs_ctx *ctx, double *mul32_per_s);
+
 /* ---- parity taps (used by tests/ only; product code never calls them) ------------------------------- */
 int fbs_debug_get_keys(fbs_ctx *ctx, uint8_t *s_lwe, uint8_t *s_big, uint64_t *ksk, uint64_t *bsk_coef);
 int fbs_debug_ntt(fbs_ctx *ctx, uint64_t *polys_host, int64_t count, int32_t inverse);

@@ -22,7 +22,7 @@ def lut_eval(env, input_values):
     for instr in env.instructions:                                    # :211 build order is topological
         k = _kind(instr)
         if k == "Input":
-            val = np.array(input_values[instr.name]).reshape(-1)      # :213-214
+            val = np.array(input_values[instr.name]).reshape(-1).astype(np.int64)   # :213-214 (int64 like randint's output)
         elif k == "LinearProd":
             val = np.sum([c * wire[v.name] for c, v in instr.coef_vals], axis=0) + instr.const_coef   # :215-217
         elif k == "Bootstrap":
@@ -40,7 +40,7 @@ def bit_eval(env, input_values):
         if k in ("Const", "BConst"):
             continue
         if k in ("Input", "BInput"):
-            val = np.array(input_values[instr.name]).reshape(-1)      # :180-181
+            val = np.array(input_values[instr.name]).reshape(-1).astype(np.int64)   # :180-181
         else:                                                         # any LUT subclass, :182-185
             idx = sum(wire[inp.name] * 2 ** e for e, inp in enumerate(instr.inputs[::-1]))   # first input = MSB
             val = np.asarray(instr.truth_table, dtype=int)[np.asarray(idx)]

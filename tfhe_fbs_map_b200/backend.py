@@ -21,7 +21,7 @@ EXPORTS = [
     "fbs_last_error", "fbs_abi_version", "fbs_ctx_create", "fbs_keygen", "fbs_ctx_destroy", "fbs_ctx_info",
     "fbs_prog_load", "fbs_prog_free", "fbs_eval_bits", "fbs_wires_bytes", "fbs_encrypt_inputs", "fbs_run_level",
     "fbs_run", "fbs_decrypt_outputs", "fbs_pbs_batch", "fbs_clear_eval", "fbs_debug_get_keys", "fbs_debug_ntt",
-    "fbs_debug_pbs", "fbs_debug_encrypt", "fbs_debug_decrypt",
+    "fbs_debug_pbs", "fbs_debug_encrypt", "fbs_debug_decrypt", "fbs_measure_int_peak",
 ]
 
 
@@ -71,6 +71,7 @@ def load_library(path: str | None = None):
         lib.fbs_debug_pbs.argtypes = [vp, i32, vp, vp, vp, vp, i64, vp, vp, vp, vp]
         lib.fbs_debug_encrypt.argtypes = [vp, i32, vp, vp, i64, u64, vp]
         lib.fbs_debug_decrypt.argtypes = [vp, i32, vp, i64, vp]
+        lib.fbs_measure_int_peak.argtypes = [vp, ctypes.POINTER(ctypes.c_double)]
         for name in EXPORTS:
             if name != "fbs_last_error":
                 getattr(lib, name).restype = ctypes.c_int
@@ -144,6 +145,12 @@ class B200Backend:
         sm, bsk, ksk, sme = ctypes.c_int32(), ctypes.c_int64(), ctypes.c_int64(), ctypes.c_int32()
         self._check(self.lib.fbs_ctx_info(self.ctx, ctypes.byref(sm), ctypes.byref(bsk), ctypes.byref(ksk), ctypes.byref(sme)))
         return dict(sm_count=sm.value, bsk_bytes=bsk.value, ksk_bytes=ksk.value, br_smem_bytes=sme.value)
+
+    def measure_int_peak(self) -> float:
+        """Sustained IMAD.WIDE rate of this device in 32x32->64 multiplies per second."""
+        v = ctypes.c_double()
+        self._check(self.lib.fbs_measure_int_peak(self.ctx, ctypes.byref(v)))
+        return v.value
 
     def close(self):
         if self.ctx:

@@ -73,6 +73,7 @@ struct fbs_ctx {
     u64 ninv = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[8] = {};
+    std::vector<cudaEvent_t> ev_pool;          // 4 per level, for per-phase timing inside fbs_run / fbs_eval_bits
     // grow-only level scratch
     u8 *d_digits = nullptr; size_t cap_digits = 0;
     u64 *d_body = nullptr; size_t cap_body = 0;
@@ -195,6 +196,7 @@ extern "C" int fbs_ctx_destroy(fbs_ctx *c)
                     c->d_gad_bsk, c->d_gad_ks, c->d_digits, c->d_body, c->d_ms, c->d_io, c->d_wires};
     for (void *p : ptrs) if (p) cudaFree(p);
     for (auto &e : c->ev) if (e) cudaEventDestroy(e);
+    for (auto &e : c->ev_pool) if (e) cudaEventDestroy(e);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
     return FBS_OK;
@@ -309,8 +311,10 @@ extern "C" int fbs_encrypt_inputs(fbs_ctx *c, fbs_prog *g, const uint8_t *in_dev
 template <int LK> static void launch_lc(const LCArgs &a, long long tiles, cudaStream_t st) { k_lincomb_decomp<LK><<<(unsigned)tiles, 256, 0, st>>>(a); }
 
 static int run_level_impl(fbs_ctx *c, fbs_prog *g, int level, int nb, int ne, int64_t B, u64 *wires, cudaStream_t st,
-                          fbs_run_stats *stats, u64 *tap_ks, u64 *tap_acc, bool timed)
+                          fbs_run_stats *stats, u64 *tap_ks, u64 *tap_acc, bool timed, cudaEvent_t *evq = nullptr)
 {
+    cudaEvent_t *E = evq ? evq : c->ev;
+    const bool rec = timed || evq;
     const int b0 = g->bs_level_ptr[level], b1 = g->bs_level_ptr[level + 1];
     if (nb < 0 && ne < 0) { nb = 0; ne = b1 - b0; }
     if (nb < 0 || ne > b1 - b0 || nb > ne) return fail(FBS_ERR_ARG, "fbs_run_level: node range outside the level");
@@ -324,7 +328,7 @@ static int run_level_impl(fbs_ctx *c, fbs_prog *g, int level, int nb, int ne, in
     CKR(grow(&c->d_digits, &c->cap_digits, (size_t)tiles * R * 16));
     CKR(grow(&c->d_body, &c->cap_body, (size_t)tiles * 16));
     CKR(grow(&c->d_ms, &c->cap_ms, (size_t)tiles * 16 * (n + 1)));
-    if (timed) CK(cudaEventRecord(c->ev[0], st));
+    if (rec) CK(cudaEventRecord(E[0], st));
     LCArgs la{};
     la.wires = wires; la.lc_ptr = g->d_lc_ptr; la.lc_slot = g->d_lc_slot; la.lc_coef = g->d_lc_coef; la.lc_const = g->d_lc_const;
     la.digits = c->d_digits; la.body = c->d_body; la.B = B; la.M = M; la.lc_begin = lc0; la.D = D; la.p = g->p; la.ks_beta = P.ks_beta;
@@ -334,7 +338,7 @@ static int run_level_impl(fbs_ctx *c, fbs_prog *g, int level, int nb, int ne, in
     case 7: launch_lc<7>(la, tiles, st); break; default: launch_lc<8>(la, tiles, st); break;
     }
     CK(cudaGetLastError());
-    if (timed) CK(cudaEventRecord(c->ev[1], st));
+    if (rec) CK(cudaEventRecord(E[1], st));
     KSArgs ka{};
     ka.digits = c->d_digits; ka.body = c->d_body; ka.ksk = c->d_ksk; ka.colsum = c->d_colsum; ka.ms = c->d_ms; ka.tap_ks = tap_ks;
     ka.M = M; ka.R = (int)R; ka.n = n; ka.ks_beta = P.ks_beta; ka.log2_2N = c->logN + 1;
@@ -351,14 +355,14 @@ static int run_level_impl(fbs_ctx *c, fbs_prog *g, int level, int nb, int ne, in
         k_keyswitch<<<kgrid, 128, 0, st>>>(ka);
     }
     CK(cudaGetLastError());
-    if (timed) CK(cudaEventRecord(c->ev[2], st));
+    if (rec) CK(cudaEventRecord(E[2], st));
     BRArgs ba{};
     ba.ms = c->d_ms; ba.bsk = c->d_bsk; ba.psi_rev = c->d_psi_rev; ba.psi_inv_rev = c->d_psi_inv_rev;
     ba.bs_lc = g->d_bs_lc; ba.bs_slot = g->d_bs_slot; ba.bs_tab_ptr = g->d_bs_tab_ptr; ba.bs_mode = g->d_bs_mode; ba.bs_tab = g->d_tab;
     ba.wires = wires; ba.tap_acc = tap_acc; ba.B = B; ba.node_begin = node0; ba.lc_begin = lc0; ba.n = n; ba.p = g->p; ba.beta = P.bsk_beta;
     const long long jobs = (long long)(node1 - node0) * B;
     CK(c->br->launch(ba, jobs, c->br_smem, st));
-    if (timed) CK(cudaEventRecord(c->ev[3], st));
+    if (rec) CK(cudaEventRecord(E[3], st));
     if (stats) { stats->n_pbs += jobs; stats->n_launches += 3; }
     if (timed && stats) {
         CK(cudaEventSynchronize(c->ev[3]));
@@ -380,18 +384,38 @@ extern "C" int fbs_run_level(fbs_ctx *c, fbs_prog *g, int32_t level, int32_t nod
     return run_level_impl(c, g, level, node_begin, node_end, B, wires_dev, (cudaStream_t)stream, stats, nullptr, nullptr, stats != nullptr);
 }
 
+static int ensure_pool(fbs_ctx *c, size_t need)
+{
+    while (c->ev_pool.size() < need) { cudaEvent_t e; CK(cudaEventCreate(&e)); c->ev_pool.push_back(e); }
+    return FBS_OK;
+}
+static int collect_phase_times(fbs_ctx *c, int n_levels, fbs_run_stats *stats)
+{
+    for (int lv = 0; lv < n_levels; lv++) {
+        cudaEvent_t *E = &c->ev_pool[4 * (size_t)lv];
+        float t;
+        if (cudaEventQuery(E[3]) != cudaSuccess) CK(cudaEventSynchronize(E[3]));
+        CK(cudaEventElapsedTime(&t, E[0], E[1])); stats->ms_lincomb += t;
+        CK(cudaEventElapsedTime(&t, E[1], E[2])); stats->ms_keyswitch += t;
+        CK(cudaEventElapsedTime(&t, E[2], E[3])); stats->ms_blind_rotate += t;
+    }
+    return FBS_OK;
+}
+
 extern "C" int fbs_run(fbs_ctx *c, fbs_prog *g, int64_t B, uint64_t *wires_dev, void *stream, fbs_run_stats *stats)
 {
     if (!c || !g || !wires_dev || B < 1) return fail(FBS_ERR_ARG, "fbs_run: bad argument");
     if (!c->have_keys) return fail(FBS_ERR_STATE, "fbs_run before fbs_keygen");
     CK(cudaSetDevice(c->device));
     cudaStream_t st = (cudaStream_t)stream;
-    if (stats) CK(cudaEventRecord(c->ev[4], st));
-    for (int lv = 0; lv < g->n_levels; lv++) CKR(run_level_impl(c, g, lv, -1, -1, B, wires_dev, st, stats, nullptr, nullptr, false));
+    if (stats) { CKR(ensure_pool(c, 4 * (size_t)g->n_levels)); CK(cudaEventRecord(c->ev[4], st)); }
+    for (int lv = 0; lv < g->n_levels; lv++)
+        CKR(run_level_impl(c, g, lv, -1, -1, B, wires_dev, st, stats, nullptr, nullptr, false, stats ? &c->ev_pool[4 * (size_t)lv] : nullptr));
     if (stats) {
         CK(cudaEventRecord(c->ev[5], st));
         CK(cudaEventSynchronize(c->ev[5]));
         float t; CK(cudaEventElapsedTime(&t, c->ev[4], c->ev[5])); stats->ms_total += t;
+        CKR(collect_phase_times(c, g->n_levels, stats));
     }
     return FBS_OK;
 }
@@ -444,12 +468,15 @@ extern "C" int fbs_eval_bits(fbs_ctx *c, fbs_prog *g, const uint8_t *in, int64_t
             CKR(fbs_encrypt_inputs(c, g, d_in, bc, inst_offset + off, B_total, enc_seed, c->d_wires, st));
             if (stats) stats->n_launches += 1;
         }
-        for (int lv = 0; lv < g->n_levels; lv++) CKR(run_level_impl(c, g, lv, -1, -1, bc, c->d_wires, st, stats, nullptr, nullptr, false));
+        if (stats) CKR(ensure_pool(c, 4 * (size_t)g->n_levels));
+        for (int lv = 0; lv < g->n_levels; lv++)
+            CKR(run_level_impl(c, g, lv, -1, -1, bc, c->d_wires, st, stats, nullptr, nullptr, false, stats ? &c->ev_pool[4 * (size_t)lv] : nullptr));
         if (g->n_outputs) {
             CKR(fbs_decrypt_outputs(c, g, bc, c->d_wires, d_out, st));
             if (stats) stats->n_launches += 1;
             CK(cudaMemcpy2DAsync(out + off, (size_t)B, d_out, (size_t)bc, (size_t)bc, (size_t)g->n_outputs, cudaMemcpyDeviceToHost, st));
         }
+        if (stats) CKR(collect_phase_times(c, g->n_levels, stats));
     }
     if (stats) {
         CK(cudaEventRecord(c->ev[7], st));
@@ -639,4 +666,43 @@ extern "C" int fbs_debug_pbs(fbs_ctx *c, int32_t p, const uint64_t *in_cts, cons
     if (d_w) cudaFree(d_w); if (d_ks) cudaFree(d_ks); if (d_acc) cudaFree(d_acc);
     fbs_prog_free(g);
     return rc;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// integer-multiply roofline probe: independent mad.wide.u32 chains, reports 32x32->64 multiplies per second
+// ------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_imad_peak(u64 *sink, int iters, u32 a0, u32 b0)
+{
+    u64 acc[8];
+    u32 a = a0 + threadIdx.x, b = b0 + blockIdx.x;
+#pragma unroll
+    for (int i = 0; i < 8; i++) acc[i] = i;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[i]) : "r"(a), "r"(b));
+    }
+    u64 s = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) s += acc[i];
+    if (s == 0x1234567ULL) sink[0] = s;
+}
+extern "C" int fbs_measure_int_peak(fbs_ctx *c, double *mul32_per_s)
+{
+    if (!c || !mul32_per_s) return fail(FBS_ERR_ARG, "fbs_measure_int_peak: bad argument");
+    CK(cudaSetDevice(c->device));
+    u64 *d = nullptr; CKR(dev_alloc(&d, 1));
+    const int iters = 1 << 14, blocks = c->sm_count * 8;
+    double best = 0;
+    for (int rep = 0; rep < 4; rep++) {
+        CK(cudaEventRecord(c->ev[0], c->stream));
+        k_imad_peak<<<blocks, 256, 0, c->stream>>>(d, iters, 12345u, 6789u);
+        CK(cudaEventRecord(c->ev[1], c->stream));
+        CK(cudaEventSynchronize(c->ev[1]));
+        float ms; CK(cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]));
+        double rate = (double)blocks * 256 * 8 * iters / (ms * 1e-3);
+        if (rep > 0 && rate > best) best = rate;
+    }
+    cudaFree(d);
+    *mul32_per_s = best;
+    return FBS_OK;
 }

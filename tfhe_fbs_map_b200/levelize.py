@@ -109,10 +109,12 @@ def _flatten(node, scale, acc, const):
     return const
 
 
-def levelize(env, p: int | None = None, reuse_slots: bool = True, shard_pad: int = 1, clear: bool = False) -> Program:
+def levelize(env, p: int | None = None, reuse_slots: bool = True, shard_pad: int = 1, clear: bool = False,
+             preserve_inputs: bool = False) -> Program:
     """Build the program.  ``reuse_slots``: liveness-based slot reuse (instance-sharded / single GPU);
     ``shard_pad`` > 1: level-contiguous slots padded to a multiple of ``shard_pad`` nodes per level so a
-    level's outputs can be all-gathered in place across ``shard_pad`` ranks (node-sharded mode)."""
+    level's outputs can be all-gathered in place across ``shard_pad`` ranks (node-sharded mode);
+    ``preserve_inputs``: never recycle the input slots, so the same encrypted inputs can be run repeatedly."""
     instrs = env.instructions
     if p is None:
         if clear:   # cleartext look-ups have no modulus; pick one that passes the loader's table-length check
@@ -180,6 +182,9 @@ def levelize(env, p: int | None = None, reuse_slots: bool = True, shard_pad: int
     for ops, _ in out_rows:
         for w in ops:
             last_use[w] = INF
+    if preserve_inputs:
+        for i in inputs:
+            last_use[i.name] = INF
 
     slot = {}
     if shard_pad > 1 or not reuse_slots:
