@@ -27,7 +27,7 @@ extern "C" {
 #define FBS_ERR_STATE (-3)    /* call order violated (e.g. eval before keygen) */
 #define FBS_ERR_NOMEM (-4)
 
-/* TFHE parameter set.  Ciphertext modulus is P = 2^64 - 2^32 + 1. */
+/* TFHE parameter set.  Ciphertext modulus is Q = 2^62 - 2^16 + 1. */
 typedef struct fbs_params {
     int32_t n;          /* small LWE dimension                         */
     int32_t k;          /* GLWE dimension                              */
@@ -37,8 +37,8 @@ typedef struct fbs_params {
     int32_t ks_l;       /* key-switch levels                           */
     int32_t ks_beta;    /* log2 key-switch base (<= 8)                 */
     int32_t reserved;
-    uint64_t lwe_noise; /* round(sigma_lwe  * P)                       */
-    uint64_t glwe_noise;/* round(sigma_glwe * P)                       */
+    uint64_t lwe_noise; /* round(sigma_lwe  * Q)                       */
+    uint64_t glwe_noise;/* round(sigma_glwe * Q)                       */
 } fbs_params;
 
 /*

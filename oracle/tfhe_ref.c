@@ -18,8 +18,7 @@
  * pattern (the pattern experiments/concrete.patch:62-74 edits) with the message encoding of
  * experiments/concrete.patch:21-27 (absolute number of message values p, one negacyclic padding
  * "bit": Delta = q/(2p), decision half-interval q/(4p)) and the table modes of
- * fbs_mapper/map_to_fbs.py:81-98, over the Goldilocks prime P = 2^64 - 2^32 + 1 as ciphertext
- * modulus.  It is deliberately written with plain loops and unsigned __int128 so that it shares no
+ * fbs_mapper/map_to_fbs.py:81-98, over the prime Q = 2^62 - 2^16 + 1 as ciphertext modulus.  It is deliberately written with plain loops and unsigned __int128 so that it shares no
  * code (and no bugs) with the CUDA product; both follow the written spec in DESIGN.md section 3, so
  * with identical seeds they must agree BIT FOR BIT at every ciphertext tap.
  */
@@ -38,22 +37,13 @@ typedef uint8_t u8;
 typedef unsigned __int128 u128;
 typedef __int128 i128;
 
-#define GLP 0xFFFFFFFF00000001ULL
+#define GLP 0x3FFFFFFFFFFF0001ULL   /* ciphertext modulus Q = 2^62 - 2^16 + 1 */
 
 /* ---------------- field arithmetic (slow-and-obvious on purpose) ---------------- */
 static inline u64 f_add(u64 a, u64 b) { u128 s = (u128)a + b; if (s >= GLP) s -= GLP; return (u64)s; }
 static inline u64 f_sub(u64 a, u64 b) { return a >= b ? a - b : (u64)((u128)a + GLP - b); }
 static inline u64 f_neg(u64 a) { return a ? GLP - a : 0; }
-static inline u64 f_mul(u64 a, u64 b)
-{
-    /* 2^64 = 2^32 - 1, 2^96 = -1 (mod P): x = lo + 2^64*(hl + 2^32*hh) = lo + hl*(2^32-1) - hh */
-    u128 x = (u128)a * b;
-    u64 lo = (u64)x, hi = (u64)(x >> 64);
-    u64 hl = hi & 0xFFFFFFFFULL, hh = hi >> 32;
-    u128 t = (u128)lo + (u128)hl * 0xFFFFFFFFULL + GLP - hh;
-    while (t >= GLP) t -= GLP;
-    return (u64)t;
-}
+static inline u64 f_mul(u64 a, u64 b) { return (u64)(((u128)a * b) % GLP); }   /* slow and obvious on purpose */
 static u64 f_pow(u64 b, u64 e) { u64 r = 1; while (e) { if (e & 1) r = f_mul(r, b); b = f_mul(b, b); e >>= 1; } return r; }
 static inline u64 f_from_i64(i64 v) { return v >= 0 ? (u64)v % GLP : GLP - ((u64)(-v) % GLP); }
 
@@ -69,8 +59,8 @@ static inline u64 rnd64(u64 seed, u64 dom, u64 idx)
     u64 h = mix64(seed ^ (dom * 0xD1B54A32D192ED03ULL));
     return mix64(h + (idx + 1) * 0x9E3779B97F4A7C15ULL);
 }
-static inline u64 rnd_uniform(u64 seed, u64 dom, u64 idx) { u64 u = rnd64(seed, dom, idx); return u >= GLP ? u - GLP : u; }
-/* Irwin-Hall(12) over 32-bit uniforms, std = scale (in units of 1/P of the torus) */
+static inline u64 rnd_uniform(u64 seed, u64 dom, u64 idx) { u64 u = rnd64(seed, dom, idx) >> 2; return u >= GLP ? u - GLP : u; }
+/* Irwin-Hall(12) over 32-bit uniforms, std = scale (in units of 1/Q of the torus) */
 static inline u64 rnd_noise(u64 seed, u64 dom, u64 idx, u64 scale)
 {
     u64 S = 0;
@@ -102,15 +92,14 @@ typedef struct {
 static int ilog2(int v) { int l = 0; while ((1 << l) < v) l++; return l; }
 static u32 bitrev(u32 x, int bits) { u32 r = 0; for (int i = 0; i < bits; i++) { r = (r << 1) | (x & 1); x >>= 1; } return r; }
 
-/* gadget element g_j = round(P / B^(j+1)), j = 0..l-1 */
+/* gadget element g_j = round(Q / B^(j+1)), j = 0..l-1 */
 static u64 gadget(int beta, int j) { u128 B = (u128)1 << (beta * (j + 1)); return (u64)(((u128)GLP + B / 2) / B); }
 
-/* decomposition: closest multiple of P/B^l, balanced digits in [-B/2, B/2) */
+/* decomposition: closest multiple of Q/B^l, balanced digits in [-B/2, B/2) */
 static void decompose(u64 x, int beta, int l, int32_t *d /* [l], d[0] is the most significant level */)
 {
     int bl = beta * l;
-    u64 t = x + (x >> 32) + (1ULL << (63 - bl));   /* wraps mod 2^64 on purpose */
-    u64 y = t >> (64 - bl);
+    u64 y = ((x + (1ULL << (61 - bl))) >> (62 - bl)) & ((1ULL << bl) - 1);   /* round(x*2^bl/2^62), wraps to 0 */
     u64 Bm = (1ULL << beta) - 1, half = 1ULL << (beta - 1);
     for (int j = l - 1; j >= 0; j--) {
         u64 dig = y & Bm; y >>= beta;
@@ -119,8 +108,7 @@ static void decompose(u64 x, int beta, int l, int32_t *d /* [l], d[0] is the mos
 }
 static inline u32 modswitch(u64 x, int log2N /* log2(2N) */)
 {
-    u64 t = x + (x >> 32) + (1ULL << (63 - log2N));
-    return (u32)(t >> (64 - log2N));
+    return (u32)(((x + (1ULL << (61 - log2N))) >> (62 - log2N)) & ((1ULL << log2N) - 1));
 }
 static inline u64 delta_of(int p) { return (GLP + (u64)p) / (2ULL * (u64)p); }
 
@@ -186,7 +174,7 @@ ref_ctx *ref_ctx_create(const ref_params *P, u64 seed)
     ref_ctx *c = calloc(1, sizeof(ref_ctx));
     c->P = *P; c->seed = seed; c->logN = ilog2(P->N);
     int N = P->N;
-    /* primitive 2N-th root of unity: 7 generates Z_P^* */
+    /* primitive 2N-th root of unity: 7 is a quadratic non-residue mod Q, so 7^((Q-1)/2N) has order exactly 2N */
     u64 psi = f_pow(7, (GLP - 1) / (2ULL * N)), psi_inv = f_pow(psi, GLP - 2);
     c->psi_rev = malloc(8 * N); c->psi_inv_rev = malloc(8 * N);
     for (int i = 0; i < N; i++) {

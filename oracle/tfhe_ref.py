@@ -92,7 +92,8 @@ def lib():
     return _lib
 
 
-GOLDILOCKS_P = 0xFFFFFFFF00000001
+FBS_Q = 0x3FFFFFFFFFFF0001          # ciphertext modulus 2^62 - 2^16 + 1
+GOLDILOCKS_P = FBS_Q   # old name kept for the tests' imports
 
 
 class RefTFHE:

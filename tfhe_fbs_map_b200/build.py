@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "csrc", "api.cu")
 OUT = os.path.join(HERE, "libfbs_b200.so")
-DEPS = [os.path.join(HERE, "csrc", f) for f in ("api.cu", "kernels.cuh", "ntt.cuh", "common.cuh", "gl64.cuh")] + \
+DEPS = [os.path.join(HERE, "csrc", f) for f in ("api.cu", "kernels.cuh", "ntt.cuh", "common.cuh", "fq.cuh")] + \
        [os.path.join(HERE, "..", "include", "fbs_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-shared",
               "-Xcompiler", "-fPIC"]

@@ -50,11 +50,11 @@ static const BRVariant g_br_variants[] = {
     BRV(8, 1, 2, true), BRV(8, 2, 1, true), BRV(9, 1, 1, true), BRV(10, 1, 3, true),   // toy sets (tests)
 };
 
-typedef void (*ntt_launch_fn)(const u64 *, u64 *, int, const u64 *, const u64 *, u64, long long, cudaStream_t);
+typedef void (*ntt_launch_fn)(const u64 *, u64 *, int, const fq_tw *, const fq_tw *, u64, long long, cudaStream_t);
 template <int LOGN>
-static void ntt_launch(const u64 *in, u64 *out, int mode, const u64 *pr, const u64 *pir, u64 ninv, long long count, cudaStream_t st)
+static void ntt_launch(const u64 *in, u64 *out, int mode, const fq_tw *pr, const fq_tw *pir, u64 scale, long long count, cudaStream_t st)
 {
-    k_ntt<LOGN><<<(unsigned)count, NttPlan<LOGN>::T, 0, st>>>(in, out, mode, pr, pir, ninv);
+    k_ntt<LOGN><<<(unsigned)count, NttPlan<LOGN>::T, 0, st>>>(in, out, mode, pr, pir, scale);
 }
 static ntt_launch_fn ntt_for(int logN)
 {
@@ -69,8 +69,9 @@ struct fbs_ctx {
     const BRVariant *br = nullptr; size_t br_smem = 0;
     u8 *d_s_lwe = nullptr, *d_s_big = nullptr;
     u64 *d_ksk = nullptr, *d_colsum = nullptr, *d_bsk = nullptr, *d_bsk_coef = nullptr;
-    u64 *d_psi_rev = nullptr, *d_psi_inv_rev = nullptr, *d_gad_bsk = nullptr, *d_gad_ks = nullptr;
-    u64 ninv = 0;
+    fq_tw *d_psi_rev = nullptr, *d_psi_inv_rev = nullptr;
+    u64 *d_gad_bsk = nullptr, *d_gad_ks = nullptr;
+    u64 ninv = 0, mont_ninv = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[8] = {};
     std::vector<cudaEvent_t> ev_pool;          // 4 per level, for per-phase timing inside fbs_run / fbs_eval_bits
@@ -142,13 +143,18 @@ extern "C" int fbs_ctx_create(const fbs_params *params, int device, uint64_t see
     for (auto &e : c->ev) CK(cudaEventCreate(&e));
     // twiddles psi^bitrev(i): 7 generates Z_P^*
     const int N = P.N;
-    std::vector<u64> pr(N), pir(N);
-    const u64 psi = gl_pow_host(7, (GL_P - 1) / (2ULL * N)), psi_inv = gl_pow_host(psi, GL_P - 2);
-    for (int i = 0; i < N; i++) { u32 r = bitrev32((u32)i, logN); pr[i] = gl_pow_host(psi, r); pir[i] = gl_pow_host(psi_inv, r); }
-    c->ninv = gl_pow_host((u64)N, GL_P - 2);
+    std::vector<fq_tw> pr(N), pir(N);
+    const u64 psi = fq_pow_host(7, (FQ_Q - 1) / (2ULL * N)), psi_inv = fq_pow_host(psi, FQ_Q - 2);
+    for (int i = 0; i < N; i++) {
+        u32 r = bitrev32((u32)i, logN);
+        const u64 w = fq_pow_host(psi, r), wi = fq_pow_host(psi_inv, r);
+        pr[i] = fq_tw{w, fq_shoup_host(w)}; pir[i] = fq_tw{wi, fq_shoup_host(wi)};
+    }
+    c->ninv = fq_pow_host((u64)N, FQ_Q - 2);
+    c->mont_ninv = fq_mul(FQ_R, c->ninv);                 // 2^64 / N mod Q
     CKR(dev_alloc(&c->d_psi_rev, N)); CKR(dev_alloc(&c->d_psi_inv_rev, N));
-    CK(cudaMemcpy(c->d_psi_rev, pr.data(), 8 * N, cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(c->d_psi_inv_rev, pir.data(), 8 * N, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(c->d_psi_rev, pr.data(), sizeof(fq_tw) * N, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(c->d_psi_inv_rev, pir.data(), sizeof(fq_tw) * N, cudaMemcpyHostToDevice));
     std::vector<u64> gb(8, 0), gk(8, 0);
     for (int j = 0; j < P.bsk_l; j++) gb[j] = fbs_gadget_host(P.bsk_beta, j);
     for (int j = 0; j < P.ks_l; j++) gk[j] = fbs_gadget_host(P.ks_beta, j);
@@ -179,7 +185,7 @@ extern "C" int fbs_keygen(fbs_ctx *c)
     k_bsk_body<<<n * rows, 256, (size_t)N * 9, st>>>(c->d_bsk_coef, k, N, l, c->d_s_lwe, c->d_s_big, c->d_gad_bsk);
     ntt_launch_fn nf = ntt_for(c->logN);
     if (!nf) return fail(FBS_ERR_ARG, "no NTT kernel for this N");
-    nf(c->d_bsk_coef, c->d_bsk, 2, c->d_psi_rev, c->d_psi_inv_rev, c->ninv, (long long)(total / N), st);
+    nf(c->d_bsk_coef, c->d_bsk, 2, c->d_psi_rev, c->d_psi_inv_rev, c->mont_ninv, (long long)(total / N), st);
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(st));
     // the coefficient-domain copy is only a parity tap: keep it for toy sizes, drop it for real key sizes

@@ -43,14 +43,14 @@ __device__ __forceinline__ void tma_load_1d(void *dst, const void *src, u32 byte
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void bar_sync_named(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 
-// block-wide sum in Z_P (addition mod P is associative, so the tree order does not matter)
+// block-wide sum in Z_Q (addition mod Q is associative, so the tree order does not matter)
 template <int THREADS>
 __device__ __forceinline__ u64 block_sum_gl(u64 v, u64 *sh /* [THREADS/32] */)
 {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         u64 w = __shfl_xor_sync(0xffffffffu, v, o);
-        v = gl_add(v, w);
+        v = fq_add(v, w);
     }
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     __syncthreads();
@@ -58,7 +58,7 @@ __device__ __forceinline__ u64 block_sum_gl(u64 v, u64 *sh /* [THREADS/32] */)
     __syncthreads();
     u64 r = 0;
 #pragma unroll
-    for (int w = 0; w < THREADS / 32; w++) r = gl_add(r, sh[w]);
+    for (int w = 0; w < THREADS / 32; w++) r = fq_add(r, sh[w]);
     return r;
 }
 
@@ -81,12 +81,12 @@ __global__ void __launch_bounds__(256) k_gen_ksk(u64 *ksk, int n, int lk, u64 se
     for (int q = threadIdx.x; q < n; q += 256) {
         u64 a = fbs_rnd_uniform(seed, DOM_KSK_MASK, r * (u64)n + q);
         row[q] = a;
-        if (s_lwe[q]) part = gl_add(part, a);
+        if (s_lwe[q]) part = fq_add(part, a);
     }
     u64 body = block_sum_gl<256>(part, sh);
     if (threadIdx.x == 0) {
-        body = gl_add(body, fbs_rnd_noise(seed, DOM_KSK_NOISE, r, noise_scale));
-        if (s_big[r / lk]) body = gl_add(body, gadgets[r % lk]);
+        body = fq_add(body, fbs_rnd_noise(seed, DOM_KSK_NOISE, r, noise_scale));
+        if (s_big[r / lk]) body = fq_add(body, gadgets[r % lk]);
         row[n] = body;
     }
 }
@@ -95,7 +95,7 @@ __global__ void k_ksk_colsum(const u64 *__restrict__ ksk, int R, int cols, u64 *
     int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= cols) return;
     u64 s = 0;
-    for (int r = 0; r < R; r++) s = gl_add(s, ksk[(size_t)r * cols + c]);
+    for (int r = 0; r < R; r++) s = fq_add(s, ksk[(size_t)r * cols + c]);
     colsum[c] = s;
 }
 // BSK in coefficient domain: masks uniform, body = noise (the key product is added by k_bsk_body)
@@ -128,23 +128,24 @@ __global__ void __launch_bounds__(256) k_bsk_body(u64 *bsk, int k, int N, int l,
             for (int jj = 0; jj < N; jj++) {
                 if (!sh_s[jj]) continue;
                 int idx = c - jj;
-                acc = (idx >= 0) ? gl_add(acc, sh_a[idx]) : gl_sub(acc, sh_a[idx + N]);
+                acc = (idx >= 0) ? fq_add(acc, sh_a[idx]) : fq_sub(acc, sh_a[idx + N]);
             }
             row[(size_t)k * N + c] = acc;
         }
     }
     __syncthreads();
-    if (threadIdx.x == 0 && s_lwe[i]) row[(size_t)u * N] = gl_add(row[(size_t)u * N], gadgets[j]);
+    if (threadIdx.x == 0 && s_lwe[i]) row[(size_t)u * N] = fq_add(row[(size_t)u * N], gadgets[j]);
 }
 
 // ------------------------------------------------------------------------------------------------------
 // K5: stand-alone NTT.  mode 0: forward (natural in, bit-reversed out, array order as oracle/tfhe_ref.c)
 //                       mode 1: inverse incl. 1/N (for tests)
-//                       mode 2: BSK preprocessing: forward, times 1/N, stored SWIZZLED for the blind-rotate kernel
+//                       mode 2: BSK preprocessing: forward, times 2^64/N (Montgomery form with the inverse
+//                               transform's 1/N folded in), stored SWIZZLED for the blind-rotate kernel
 // ------------------------------------------------------------------------------------------------------
 template <int LOGN>
 __global__ void __launch_bounds__(NttPlan<LOGN>::T) k_ntt(const u64 *__restrict__ in, u64 *__restrict__ out, int mode,
-                                                         const u64 *__restrict__ psi_rev, const u64 *__restrict__ psi_inv_rev, u64 ninv)
+                                                         const fq_tw *__restrict__ psi_rev, const fq_tw *__restrict__ psi_inv_rev, u64 scale)
 {
     using P = NttPlan<LOGN>;
     __shared__ u64 bufA[P::N];
@@ -154,12 +155,12 @@ __global__ void __launch_bounds__(NttPlan<LOGN>::T) k_ntt(const u64 *__restrict_
     u64 *dst = out + (size_t)blockIdx.x * P::N;
     u64 x[8];
     auto sync = [] { __syncthreads(); };
-    if (mode == 1) {
+    if (mode == 1) {                                   // inverse, scale = 1/N
 #pragma unroll
         for (int e = 0; e < 8; e++) x[e] = src[P::idx(tau, e, P::inv_lb(0))];
         ntt_inv_from<LOGN, 0>(x, tau, bufA, bufB, psi_inv_rev, sync, sync);
 #pragma unroll
-        for (int e = 0; e < 8; e++) dst[P::idx(tau, e, P::inv_lb(P::NPASS - 1))] = gl_mul(x[e], ninv);
+        for (int e = 0; e < 8; e++) dst[P::idx(tau, e, P::inv_lb(P::NPASS - 1))] = fq_mul(fq_csub(x[e], FQ_Q), scale);
     } else {
 #pragma unroll
         for (int e = 0; e < 8; e++) x[e] = src[P::idx(tau, e, P::fwd_lb(0))];
@@ -167,7 +168,9 @@ __global__ void __launch_bounds__(NttPlan<LOGN>::T) k_ntt(const u64 *__restrict_
 #pragma unroll
         for (int e = 0; e < 8; e++) {
             const int id = P::idx(tau, e, P::fwd_lb(P::NPASS - 1));
-            if (mode == 0) dst[id] = x[e]; else dst[P::swz(id)] = gl_mul(x[e], ninv);
+            const u64 v = fq_csub(fq_csub(x[e], FQ_2Q), FQ_Q);            // lazy [0,4Q) -> canonical
+            if (mode == 0) dst[id] = v;
+            else dst[P::swz(id)] = fq_mul(v, scale);                     // mode 2: scale = 2^64 / N (Montgomery form, 1/N folded)
         }
     }
 }
@@ -207,14 +210,14 @@ __global__ void __launch_bounds__(256) k_encrypt(EncArgs a)
     for (int q = threadIdx.x; q < a.D; q += 256) {
         u64 x = fbs_rnd_uniform(a.enc_seed, DOM_ENC_MASK, id * (u64)a.D + q);
         ct[q] = x;
-        if (a.s_big[q]) part = gl_add(part, x);
+        if (a.s_big[q]) part = fq_add(part, x);
     }
     u64 body = block_sum_gl<256>(part, sh);
     if (threadIdx.x == 0) {
-        body = gl_add(body, fbs_rnd_noise(a.enc_seed, DOM_ENC_NOISE, id, a.noise_scale));
+        body = fq_add(body, fbs_rnd_noise(a.enc_seed, DOM_ENC_NOISE, id, a.noise_scale));
         const int p2 = 2 * a.p;
         int mm = (int)(((m % p2) + p2) % p2);
-        ct[a.D] = gl_add(body, gl_mul((u64)mm, fbs_delta(a.p)));
+        ct[a.D] = fq_add(body, fq_mul((u64)mm, fbs_delta(a.p)));
     }
 }
 // outputs are lincombs of wires: phase(sum c_o ct_o) + const*Delta, decoded to Z_2p
@@ -235,21 +238,21 @@ __global__ void __launch_bounds__(256) k_decrypt(OutArgs a)
         const int o0 = a.out_ptr[q], o1 = a.out_ptr[q + 1];
         for (int o = o0; o < o1; o++) {
             const u64 *ct = a.wires + ((size_t)a.out_slot[o] * a.B + b) * CT;
-            const u64 cf = gl_from_i64(a.out_coef[o]);
+            const u64 cf = fq_from_i64(a.out_coef[o]);
             u64 acc = 0;
-            for (int w = threadIdx.x; w < a.D; w += 256) if (a.s_big[w]) acc = gl_add(acc, ct[w]);
-            part = gl_add(part, gl_mul(acc, cf));
-            body = gl_add(body, gl_mul(ct[a.D], cf));
+            for (int w = threadIdx.x; w < a.D; w += 256) if (a.s_big[w]) acc = fq_add(acc, ct[w]);
+            part = fq_add(part, fq_mul(acc, cf));
+            body = fq_add(body, fq_mul(ct[a.D], cf));
         }
-        body = gl_add(body, gl_mul(gl_from_i64(a.out_const[q]), fbs_delta(a.p)));
+        body = fq_add(body, fq_mul(fq_from_i64(a.out_const[q]), fbs_delta(a.p)));
     } else {
         const u64 *ct = a.wires + (size_t)e * CT;
-        for (int w = threadIdx.x; w < a.D; w += 256) if (a.s_big[w]) part = gl_add(part, ct[w]);
+        for (int w = threadIdx.x; w < a.D; w += 256) if (a.s_big[w]) part = fq_add(part, ct[w]);
         body = ct[a.D];
     }
     u64 mask = block_sum_gl<256>(part, sh);
     if (threadIdx.x == 0) {
-        int m = fbs_decode(gl_sub(body, mask), a.p);
+        int m = fbs_decode(fq_sub(body, mask), a.p);
         if (a.out8) a.out8[e] = (u8)m;
         if (a.out32) a.out32[e] = m;
     }
@@ -294,10 +297,10 @@ __global__ void __launch_bounds__(256) k_lincomb_decomp(LCArgs a)
             u64 acc = 0;
             for (int o = a.lc_ptr[lc]; o < a.lc_ptr[lc + 1]; o++) {
                 const u64 x = a.wires[((size_t)a.lc_slot[o] * a.B + inst) * CT + i];
-                acc = gl_add(acc, gl_mul(x, gl_from_i64(a.lc_coef[o])));
+                acc = fq_add(acc, fq_mul(x, fq_from_i64(a.lc_coef[o])));
             }
             if (i == a.D) {
-                acc = gl_add(acc, gl_mul(gl_from_i64(a.lc_const[lc]), fbs_delta(a.p)));
+                acc = fq_add(acc, fq_mul(fq_from_i64(a.lc_const[lc]), fbs_delta(a.p)));
                 a.body[tile * 16 + mm] = acc;
             } else {
                 int d[LK];
@@ -358,15 +361,15 @@ __global__ void __launch_bounds__(128) k_keyswitch(KSArgs a)
         }
     }
     if (!live) return;
-    const u64 corr = gl_mul(a.colsum[c], (u64)(1u << (a.ks_beta - 1)));
+    const u64 corr = fq_mul(a.colsum[c], (u64)(1u << (a.ks_beta - 1)));
 #pragma unroll
     for (int mm = 0; mm < 16; mm++) {
         const long long m = tile * 16 + mm;
         if (m >= a.M) continue;
         const u64 lo = acc0[mm] + (acc1[mm] << 32);
         const u64 hi = (acc1[mm] >> 32) + (lo < acc0[mm] ? 1 : 0);
-        u64 v = gl_sub(corr, gl_reduce128(lo, hi));
-        if (c == a.n) v = gl_add(v, a.body[m]);
+        u64 v = fq_sub(corr, fq_reduce128(lo, hi));
+        if (c == a.n) v = fq_add(v, a.body[m]);
         a.ms[(size_t)m * cols + c] = (u16)fbs_modswitch(v, a.log2_2N);
         if (a.tap_ks) a.tap_ks[(size_t)m * cols + c] = v;
     }
@@ -381,7 +384,8 @@ __global__ void __launch_bounds__(128) k_keyswitch(KSArgs a)
 // ------------------------------------------------------------------------------------------------------
 struct BRArgs {
     const u16 *ms;                      // [(lincomb - lc_begin) * B + inst][n+1]
-    const u64 *bsk, *psi_rev, *psi_inv_rev;
+    const u64 *bsk;
+    const fq_tw *psi_rev, *psi_inv_rev;
     const int32_t *bs_lc, *bs_slot, *bs_tab_ptr, *bs_mode;
     const u8 *bs_tab;
     u64 *wires; u64 *tap_acc;
@@ -437,7 +441,7 @@ __global__ void __launch_bounds__((K + 1) * (1 << LOGN) / 8, 1) k_blind_rotate(B
     }
     // ---- accumulator init: ACC = (0, .., 0, X^{-b~} * TV) ; TV[j] = F(round(j*p/N)), F(x) = tv[x]*Delta - s*Delta/2
     {
-        const u64 delta = fbs_delta(p), off = gl_mul((u64)mode, delta >> 1);
+        const u64 delta = fbs_delta(p), off = fq_mul((u64)mode, delta >> 1);
         const int bt = s_ms[n];
         u64 *acc = ACC + (size_t)g * N;
 #pragma unroll
@@ -452,8 +456,8 @@ __global__ void __launch_bounds__((K + 1) * (1 << LOGN) / 8, 1) k_blind_rotate(B
                 int x = (int)((2LL * src * p + N) / (2LL * N));
                 if (x >= p) { x -= p; neg = !neg; }
                 const u64 tvx = (x < tabL) ? (u64)s_tab[x] : 0;
-                const u64 F = gl_sub(gl_mul(tvx, delta), off);
-                val = neg ? gl_neg(F) : F;
+                const u64 F = fq_sub(fq_mul(tvx, delta), off);
+                val = neg ? fq_neg(F) : F;
             }
             acc[j] = val;
         }
@@ -474,12 +478,12 @@ __global__ void __launch_bounds__((K + 1) * (1 << LOGN) / 8, 1) k_blind_rotate(B
             const int j = tau + e * T;
             int src = j - ai;
             if (src < 0) src += 2 * N;
-            const u64 rot = (src < N) ? acc[src] : gl_neg(acc[src - N]);
-            const u64 diff = gl_sub(rot, acc[j]);
+            const u64 rot = (src < N) ? acc[src] : fq_neg(acc[src - N]);
+            const u64 diff = fq_sub(rot, acc[j]);
             int d[L];
             fbs_balanced_digits<L>(fbs_round_top(diff, beta * L), beta, d);
 #pragma unroll
-            for (int jj = 0; jj < L; jj++) dg[jj][e] = gl_from_i64(d[jj]);
+            for (int jj = 0; jj < L; jj++) dg[jj][e] = fq_from_i64(d[jj]);
         }
         // ---- forward NTTs, spectra to DH (swizzled, layout lb = 0)
 #pragma unroll
@@ -492,7 +496,8 @@ __global__ void __launch_bounds__((K + 1) * (1 << LOGN) / 8, 1) k_blind_rotate(B
             for (int e = 0; e < 8; e++) dh[P::swz(P::idx(tau, e, 0))] = dg[jj][e];
         }
         __syncthreads();
-        // ---- pointwise: out_g = sum_r DH[r] * BSK[r][g]
+        // ---- pointwise: out_g = sum_r DH[r] * BSK[r][g].  DH is lazy (< 4Q), the key is canonical and in Montgomery
+        // form, so a PAIR of 128-bit products (< 8Q^2 < 2^127) is reduced by one REDC to < 3Q, then folded to < 2Q.
         if (BSK_SMEM) mbar_wait(mbar, (u32)(i & 1));
         u64 x[8];
         {
@@ -502,8 +507,19 @@ __global__ void __launch_bounds__((K + 1) * (1 << LOGN) / 8, 1) k_blind_rotate(B
                 const int id = P::swz(P::idx(tau, e, 0));
                 u64 s = 0;
 #pragma unroll
-                for (int r = 0; r < G * L; r++) s = gl_add(s, gl_mul(DH[(size_t)r * N + id], brow[((size_t)r * G + g) * N + id]));
-                x[e] = s;
+                for (int r = 0; r < G * L; r += 2) {
+                    u64 lo, hi;
+                    fq_mul_wide(DH[(size_t)r * N + id], brow[((size_t)r * G + g) * N + id], lo, hi);
+                    if (r + 1 < G * L) {
+                        u64 lo2, hi2;
+                        fq_mul_wide(DH[(size_t)(r + 1) * N + id], brow[((size_t)(r + 1) * G + g) * N + id], lo2, hi2);
+                        lo += lo2;
+                        hi += hi2 + (lo < lo2 ? 1 : 0);
+                    }
+                    const u64 t = fq_csub(fq_redc(lo, hi), FQ_2Q);
+                    s = (r == 0) ? t : fq_csub(s + t, FQ_2Q);
+                }
+                x[e] = s;                                  // < 2Q: what the inverse butterflies expect
             }
         }
         // ---- inverse NTT; the first transpose barrier is CTA-wide: after it nobody reads DH/BS of this step
@@ -521,7 +537,7 @@ __global__ void __launch_bounds__((K + 1) * (1 << LOGN) / 8, 1) k_blind_rotate(B
 #pragma unroll
         for (int e = 0; e < 8; e++) {
             const int j = P::idx(tau, e, P::inv_lb(P::NPASS - 1));
-            acc[j] = gl_add(acc[j], x[e]);
+            acc[j] = fq_add(acc[j], fq_csub(x[e], FQ_Q));
         }
         __syncthreads();
     }
@@ -530,9 +546,9 @@ __global__ void __launch_bounds__((K + 1) * (1 << LOGN) / 8, 1) k_blind_rotate(B
     u64 *out = a.wires + ((size_t)a.bs_slot[node] * a.B + inst) * CT;
     for (int w = tid; w < K * N; w += C::THREADS) {
         const int u = w / N, j = w % N;
-        out[w] = (j == 0) ? ACC[(size_t)u * N] : gl_neg(ACC[(size_t)u * N + N - j]);
+        out[w] = (j == 0) ? ACC[(size_t)u * N] : fq_neg(ACC[(size_t)u * N + N - j]);
     }
-    if (tid == 0) out[(size_t)K * N] = gl_add(ACC[(size_t)K * N], gl_mul((u64)mode, fbs_delta(p) >> 1));
+    if (tid == 0) out[(size_t)K * N] = fq_add(ACC[(size_t)K * N], fq_mul((u64)mode, fbs_delta(p) >> 1));
     if (a.tap_acc) {
         u64 *t = a.tap_acc + (size_t)job * G * N;
         for (int w = tid; w < G * N; w += C::THREADS) t[w] = ACC[w];

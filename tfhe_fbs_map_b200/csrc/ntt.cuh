@@ -4,13 +4,15 @@
 // holds) separated by shared-memory transposes.  Forward = Cooley-Tukey, natural order in, bit-reversed
 // out, negacyclic twist merged into the twiddles psi_rev[m+i] = psi^bitrev(m+i); inverse = Gentleman-
 // Sande, bit-reversed in, natural out, WITHOUT the 1/N scale (it is folded into the bootstrapping key).
+// Butterflies are Harvey's lazy ones with Shoup twiddles (w, ws = floor(w*2^64/Q)):
+//   forward: inputs in [0,4Q), outputs in [0,4Q);   inverse: inputs in [0,2Q), outputs in [0,2Q).
 //
 // A pass is described by `lb`, the lowest of its three in-thread index bits:
 //     idx(tau, e) = ((tau >> lb) << (lb+3)) | (e << lb) | (tau & ((1<<lb)-1)),   e = 0..7
 // Everything here is __host__ __device__ so tests/host_emul.cu can run the exact index / twiddle logic on
 // the CPU (this container has no GPU) by looping over tau and treating a transpose as an array copy.
 #pragma once
-#include "gl64.cuh"
+#include "fq.cuh"
 
 template <int LOGN>
 struct NttPlan {
@@ -18,29 +20,40 @@ struct NttPlan {
     static constexpr int T = N / 8;                 // threads per polynomial
     static constexpr int NPASS = (LOGN + 2) / 3;
     // forward pass p covers index bits hi = LOGN-1-3p down to max(hi-2, 0)
-    GL_HDM static constexpr int fwd_hi(int p) { return LOGN - 1 - 3 * p; }
-    GL_HDM static constexpr int fwd_lb(int p) { return fwd_hi(p) - 2 > 0 ? fwd_hi(p) - 2 : 0; }
+    FQ_HDM static constexpr int fwd_hi(int p) { return LOGN - 1 - 3 * p; }
+    FQ_HDM static constexpr int fwd_lb(int p) { return fwd_hi(p) - 2 > 0 ? fwd_hi(p) - 2 : 0; }
     // inverse pass p covers index bits lo = 3p up to min(lo+2, LOGN-1)
-    GL_HDM static constexpr int inv_lo(int p) { return 3 * p; }
-    GL_HDM static constexpr int inv_lb(int p) { return 3 * p < LOGN - 3 ? 3 * p : LOGN - 3; }
+    FQ_HDM static constexpr int inv_lo(int p) { return 3 * p; }
+    FQ_HDM static constexpr int inv_lb(int p) { return 3 * p < LOGN - 3 ? 3 * p : LOGN - 3; }
     // bank-conflict-free XOR swizzle of the low 4 index bits (tools/swizzle_search.py):
     // 4-bit columns added for index bits 4, 5, 6
-    GL_HDM static constexpr int sw_c0() { return (LOGN % 3 == 2) ? 1 : (LOGN % 3 == 0) ? 1 : 2; }
-    GL_HDM static constexpr int sw_c1() { return (LOGN % 3 == 2) ? 4 : (LOGN % 3 == 0) ? 2 : 4; }
-    GL_HDM static constexpr int sw_c2() { return (LOGN % 3 == 2) ? 10 : (LOGN % 3 == 0) ? 12 : 9; }
-    GL_HDM static constexpr int swz(int i)
+    FQ_HDM static constexpr int sw_c0() { return (LOGN % 3 == 2) ? 1 : (LOGN % 3 == 0) ? 1 : 2; }
+    FQ_HDM static constexpr int sw_c1() { return (LOGN % 3 == 2) ? 4 : (LOGN % 3 == 0) ? 2 : 4; }
+    FQ_HDM static constexpr int sw_c2() { return (LOGN % 3 == 2) ? 10 : (LOGN % 3 == 0) ? 12 : 9; }
+    FQ_HDM static constexpr int swz(int i)
     {
         return i ^ (((i >> 4) & 1) * sw_c0()) ^ (((i >> 5) & 1) * sw_c1()) ^ (((i >> 6) & 1) * sw_c2());
     }
-    GL_HDM static constexpr int idx(int tau, int e, int lb)
+    FQ_HDM static constexpr int idx(int tau, int e, int lb)
     {
         return ((tau >> lb) << (lb + 3)) | (e << lb) | (tau & ((1 << lb) - 1));
     }
 };
 
 // ---- one forward pass on registers -------------------------------------------------------------------
+struct alignas(16) fq_tw { u64 w, ws; };      // twiddle and its Shoup companion, one 128-bit load
+FQ_HD fq_tw fq_tw_load(const fq_tw *p)
+{
+#if defined(__CUDA_ARCH__)
+    const ulonglong2 v = __ldg(reinterpret_cast<const ulonglong2 *>(p));
+    return fq_tw{v.x, v.y};
+#else
+    return *p;
+#endif
+}
+
 template <int LOGN, int PASS>
-GL_HD void ntt_fwd_pass(u64 (&x)[8], int tau, const u64 *__restrict__ psi_rev)
+FQ_HD void ntt_fwd_pass(u64 (&x)[8], int tau, const fq_tw *__restrict__ psi_rev)
 {
     using P = NttPlan<LOGN>;
     constexpr int hi = P::fwd_hi(PASS), lb = P::fwd_lb(PASS);
@@ -53,16 +66,16 @@ GL_HD void ntt_fwd_pass(u64 (&x)[8], int tau, const u64 *__restrict__ psi_rev)
         for (int e0 = 0; e0 < 8; e0++) {
             if (e0 & (1 << q)) continue;
             const int e1 = e0 | (1 << q);
-            const u64 w = psi_rev[m + ((th << (2 - q)) | (e0 >> (q + 1)))];
-            const u64 v = gl_mul(x[e1], w), u = x[e0];
-            x[e0] = gl_add(u, v);
-            x[e1] = gl_sub(u, v);
+            const fq_tw w = fq_tw_load(psi_rev + m + ((th << (2 - q)) | (e0 >> (q + 1))));
+            const u64 u = fq_csub(x[e0], FQ_2Q), v = fq_mul_shoup(x[e1], w.w, w.ws);
+            x[e0] = u + v;
+            x[e1] = u - v + FQ_2Q;
         }
     }
 }
 // ---- one inverse pass on registers ---------------------------------------------------------------------
 template <int LOGN, int PASS>
-GL_HD void ntt_inv_pass(u64 (&x)[8], int tau, const u64 *__restrict__ psi_inv_rev)
+FQ_HD void ntt_inv_pass(u64 (&x)[8], int tau, const fq_tw *__restrict__ psi_inv_rev)
 {
     using P = NttPlan<LOGN>;
     constexpr int lo = P::inv_lo(PASS), lb = P::inv_lb(PASS);
@@ -75,10 +88,10 @@ GL_HD void ntt_inv_pass(u64 (&x)[8], int tau, const u64 *__restrict__ psi_inv_re
         for (int e0 = 0; e0 < 8; e0++) {
             if (e0 & (1 << q)) continue;
             const int e1 = e0 | (1 << q);
-            const u64 w = psi_inv_rev[m + ((th << (2 - q)) | (e0 >> (q + 1)))];
+            const fq_tw w = fq_tw_load(psi_inv_rev + m + ((th << (2 - q)) | (e0 >> (q + 1))));
             const u64 u = x[e0], v = x[e1];
-            x[e0] = gl_add(u, v);
-            x[e1] = gl_mul(gl_sub(u, v), w);
+            x[e0] = fq_csub(u + v, FQ_2Q);
+            x[e1] = fq_mul_shoup(u - v + FQ_2Q, w.w, w.ws);
         }
     }
 }
@@ -87,7 +100,7 @@ GL_HD void ntt_inv_pass(u64 (&x)[8], int tau, const u64 *__restrict__ psi_inv_re
 // ---- device drivers: transposes through two alternating swizzled buffers -------------------------------
 // `sync` is a callable that synchronises the T threads working on this polynomial.
 template <int LOGN, int PASS, class Sync>
-__device__ __forceinline__ void ntt_fwd_from(u64 (&x)[8], int tau, u64 *bufA, u64 *bufB, const u64 *psi_rev, Sync sync)
+__device__ __forceinline__ void ntt_fwd_from(u64 (&x)[8], int tau, u64 *bufA, u64 *bufB, const fq_tw *psi_rev, Sync sync)
 {
     using P = NttPlan<LOGN>;
     ntt_fwd_pass<LOGN, PASS>(x, tau, psi_rev);
@@ -105,13 +118,13 @@ __device__ __forceinline__ void ntt_fwd_from(u64 (&x)[8], int tau, u64 *bufA, u6
 // forward NTT: x enters in layout fwd_lb(0) (idx = tau + e*T), leaves in layout fwd_lb(NPASS-1) = 0 (idx = 8*tau+e),
 // values at bit-reversed positions.
 template <int LOGN, class Sync>
-__device__ __forceinline__ void ntt_forward(u64 (&x)[8], int tau, u64 *bufA, u64 *bufB, const u64 *psi_rev, Sync sync)
+__device__ __forceinline__ void ntt_forward(u64 (&x)[8], int tau, u64 *bufA, u64 *bufB, const fq_tw *psi_rev, Sync sync)
 {
     ntt_fwd_from<LOGN, 0>(x, tau, bufA, bufB, psi_rev, sync);
 }
 // inverse NTT passes PASS.. ; the caller supplies x in layout inv_lb(PASS)
 template <int LOGN, int PASS, class Sync0, class Sync>
-__device__ __forceinline__ void ntt_inv_from(u64 (&x)[8], int tau, u64 *bufA, u64 *bufB, const u64 *psi_inv_rev, Sync0 sync_first, Sync sync)
+__device__ __forceinline__ void ntt_inv_from(u64 (&x)[8], int tau, u64 *bufA, u64 *bufB, const fq_tw *psi_inv_rev, Sync0 sync_first, Sync sync)
 {
     using P = NttPlan<LOGN>;
     ntt_inv_pass<LOGN, PASS>(x, tau, psi_inv_rev);

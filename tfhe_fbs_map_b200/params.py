@@ -7,8 +7,8 @@ noise bound to the *absolute* number of message values p (reference experiments/
 noise by ``sqrt(sq_norm2)`` (concrete.patch:133-134).  ``estimate()`` below applies exactly that bound to the
 parameter sets this executor ships, so every benchmark line can state its PBS failure probability.
 
-Ciphertext modulus is the Goldilocks prime P = 2^64 - 2^32 + 1; all standard
-deviations are relative to the torus (i.e. in units of P).
+Ciphertext modulus is the prime Q = 2^62 - 2^16 + 1; all standard deviations are
+relative to the torus (i.e. in units of Q).
 """
 from __future__ import annotations
 
@@ -16,7 +16,8 @@ import ctypes
 import math
 from dataclasses import dataclass, asdict
 
-GOLDILOCKS_P = 0xFFFFFFFF00000001
+FBS_Q = 0x3FFFFFFFFFFF0001          # ciphertext modulus 2^62 - 2^16 + 1
+GOLDILOCKS_P = FBS_Q   # old name kept for the tests' imports
 
 
 @dataclass(frozen=True)
