@@ -27,27 +27,29 @@ extern "C" int fbs_abi_version(void) { return 1; }
 // ------------------------------------------------------------------------------------------------------
 // blind-rotate kernel variants
 // ------------------------------------------------------------------------------------------------------
-typedef cudaError_t (*br_launch_fn)(const BRArgs &, long long grid, size_t smem, cudaStream_t);
-struct BRVariant { int logN, k, l; bool bsk_smem; int threads; size_t (*smem)(int n); br_launch_fn launch; cudaError_t (*prepare)(size_t smem); };
+typedef cudaError_t (*br_launch_fn)(const BRArgs &, long long jobs, size_t smem, cudaStream_t);
+struct BRVariant { int logN, k, l; bool bsk_smem; int pb, threads; size_t (*smem)(int n); br_launch_fn launch; cudaError_t (*prepare)(size_t smem); };
 
-template <int LOGN, int K, int L, bool SM>
-static cudaError_t br_launch(const BRArgs &a, long long grid, size_t smem, cudaStream_t st)
+template <int LOGN, int K, int L, bool SM, int PB>
+static cudaError_t br_launch(const BRArgs &a, long long jobs, size_t smem, cudaStream_t st)
 {
-    k_blind_rotate<LOGN, K, L, SM><<<(unsigned)grid, BRCfg<LOGN, K, L, SM>::THREADS, smem, st>>>(a);
+    const long long grid = (jobs + PB - 1) / PB;
+    k_blind_rotate<LOGN, K, L, SM, PB><<<(unsigned)grid, BRCfg<LOGN, K, L, SM, PB>::THREADS, smem, st>>>(a);
     return cudaGetLastError();
 }
-template <int LOGN, int K, int L, bool SM>
+template <int LOGN, int K, int L, bool SM, int PB>
 static cudaError_t br_prepare(size_t smem)
 {
-    return cudaFuncSetAttribute(k_blind_rotate<LOGN, K, L, SM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    return cudaFuncSetAttribute(k_blind_rotate<LOGN, K, L, SM, PB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 }
-template <int LOGN, int K, int L, bool SM> static size_t br_smem(int n) { return BRCfg<LOGN, K, L, SM>::smem_bytes(n); }
-#define BRV(LOGN, K, L, SM) { LOGN, K, L, SM, BRCfg<LOGN, K, L, SM>::THREADS, br_smem<LOGN, K, L, SM>, br_launch<LOGN, K, L, SM>, br_prepare<LOGN, K, L, SM> }
+template <int LOGN, int K, int L, bool SM, int PB> static size_t br_smem(int n) { return BRCfg<LOGN, K, L, SM, PB>::smem_bytes(n); }
+#define BRV(LOGN, K, L, SM, PB) { LOGN, K, L, SM, PB, BRCfg<LOGN, K, L, SM, PB>::THREADS, br_smem<LOGN, K, L, SM, PB>, br_launch<LOGN, K, L, SM, PB>, br_prepare<LOGN, K, L, SM, PB> }
 static const BRVariant g_br_variants[] = {
-    BRV(11, 1, 1, true),    // set A
-    BRV(11, 1, 2, false),   // set C (row does not fit shared memory next to the accumulator: BSK read from L2)
-    BRV(10, 2, 1, true),    // set S
-    BRV(8, 1, 2, true), BRV(8, 2, 1, true), BRV(9, 1, 1, true), BRV(10, 1, 3, true),   // toy sets (tests)
+    BRV(11, 1, 1, true, 2),    // set A: two bootstraps per CTA share the TMA-streamed BSK row (192 KB shared memory)
+    BRV(11, 1, 1, true, 1),    // set A, one bootstrap per CTA: used when a launch has no more jobs than SMs
+    BRV(11, 1, 2, false, 1),   // set C (row does not fit shared memory next to the accumulator: BSK read from L2)
+    BRV(10, 2, 1, true, 1),    // set S
+    BRV(8, 1, 2, true, 2), BRV(8, 2, 1, true, 2), BRV(9, 1, 1, true, 2), BRV(10, 1, 3, true, 1),   // toy sets (tests)
 };
 
 typedef void (*ntt_launch_fn)(const u64 *, u64 *, int, const fq_tw *, const fq_tw *, u64, long long, cudaStream_t);
@@ -66,7 +68,8 @@ static ntt_launch_fn ntt_for(int logN)
 struct fbs_ctx {
     fbs_params P; int device = 0; u64 seed = 0; int logN = 0, sm_count = 0;
     bool have_keys = false;
-    const BRVariant *br = nullptr; size_t br_smem = 0;
+    const BRVariant *br = nullptr; size_t br_smem = 0;        // widest variant (most bootstraps per CTA)
+    const BRVariant *br1 = nullptr; size_t br1_smem = 0;      // one bootstrap per CTA, for launches with <= sm_count jobs
     u8 *d_s_lwe = nullptr, *d_s_big = nullptr;
     u64 *d_ksk = nullptr, *d_colsum = nullptr, *d_bsk = nullptr, *d_bsk_coef = nullptr;
     fq_tw *d_psi_rev = nullptr, *d_psi_inv_rev = nullptr;
@@ -123,15 +126,18 @@ extern "C" int fbs_ctx_create(const fbs_params *params, int device, uint64_t see
         return fail(FBS_ERR_ARG, "unsupported key-switch decomposition (need 1<=ks_beta<=8, 1<=ks_l<=8)");
     if (P.bsk_beta * P.bsk_l > 48 || P.bsk_beta < 2) return fail(FBS_ERR_ARG, "unsupported blind-rotate decomposition");
     if (P.n < 1 || P.n > 4095) return fail(FBS_ERR_ARG, "n out of range");
-    const BRVariant *br = nullptr;
-    for (const BRVariant &v : g_br_variants) if (v.logN == logN && v.k == P.k && v.l == P.bsk_l) { br = &v; break; }
+    const BRVariant *br = nullptr, *br1 = nullptr;
+    for (const BRVariant &v : g_br_variants) if (v.logN == logN && v.k == P.k && v.l == P.bsk_l) {
+        if (!br || v.pb > br->pb) br = &v;
+        if (v.pb == 1) br1 = &v;
+    }
     if (!br) return fail(FBS_ERR_ARG, "no blind-rotate kernel compiled for (N=" + std::to_string(P.N) + ", k=" + std::to_string(P.k) + ", l=" + std::to_string(P.bsk_l) + ")");
     int ndev = 0;
     CK(cudaGetDeviceCount(&ndev));
     if (device < 0 || device >= ndev) return fail(FBS_ERR_ARG, "no such CUDA device");
     CK(cudaSetDevice(device));
     fbs_ctx *c = new fbs_ctx();
-    c->P = P; c->device = device; c->seed = seed; c->logN = logN; c->br = br;
+    c->P = P; c->device = device; c->seed = seed; c->logN = logN; c->br = br; c->br1 = br1 ? br1 : br;
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, device));
     c->sm_count = prop.multiProcessorCount;
@@ -139,6 +145,8 @@ extern "C" int fbs_ctx_create(const fbs_params *params, int device, uint64_t see
     if (c->br_smem > (size_t)prop.sharedMemPerBlockOptin)
         return fail(FBS_ERR_ARG, "blind-rotate kernel needs " + std::to_string(c->br_smem) + " B shared memory, device offers " + std::to_string(prop.sharedMemPerBlockOptin));
     CK(br->prepare(c->br_smem));
+    c->br1_smem = c->br1->smem(P.n);
+    if (c->br1 != c->br) CK(c->br1->prepare(c->br1_smem));
     CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     for (auto &e : c->ev) CK(cudaEventCreate(&e));
     // twiddles psi^bitrev(i): 7 generates Z_P^*
@@ -365,9 +373,10 @@ static int run_level_impl(fbs_ctx *c, fbs_prog *g, int level, int nb, int ne, in
     BRArgs ba{};
     ba.ms = c->d_ms; ba.bsk = c->d_bsk; ba.psi_rev = c->d_psi_rev; ba.psi_inv_rev = c->d_psi_inv_rev;
     ba.bs_lc = g->d_bs_lc; ba.bs_slot = g->d_bs_slot; ba.bs_tab_ptr = g->d_bs_tab_ptr; ba.bs_mode = g->d_bs_mode; ba.bs_tab = g->d_tab;
-    ba.wires = wires; ba.tap_acc = tap_acc; ba.B = B; ba.node_begin = node0; ba.lc_begin = lc0; ba.n = n; ba.p = g->p; ba.beta = P.bsk_beta;
+    ba.wires = wires; ba.tap_acc = tap_acc; ba.B = B; ba.jobs = (long long)(node1 - node0) * B; ba.node_begin = node0; ba.lc_begin = lc0; ba.n = n; ba.p = g->p; ba.beta = P.bsk_beta;
     const long long jobs = (long long)(node1 - node0) * B;
-    CK(c->br->launch(ba, jobs, c->br_smem, st));
+    if (jobs <= c->sm_count) CK(c->br1->launch(ba, jobs, c->br1_smem, st));   // fill SMs first, pair bootstraps after
+    else CK(c->br->launch(ba, jobs, c->br_smem, st));
     if (rec) CK(cudaEventRecord(E[3], st));
     if (stats) { stats->n_pbs += jobs; stats->n_launches += 3; }
     if (timed && stats) {

@@ -29,6 +29,8 @@ typedef int64_t i64;
 #endif
 
 FQ_HD u64 fq_csub(u64 x, u64 m) { return x >= m ? x - m : x; }          // conditional subtract
+// lazy fold used by the forward butterflies: subtract 2Q iff bit 63 is set (a single test on the high word)
+FQ_HD u64 fq_lazy_fold(u64 x) { return ((i64)x < 0) ? x - FQ_2Q : x; }
 FQ_HD u64 fq_add(u64 a, u64 b) { return fq_csub(a + b, FQ_Q); }          // canonical in, canonical out
 FQ_HD u64 fq_sub(u64 a, u64 b) { return a >= b ? a - b : a + FQ_Q - b; }
 FQ_HD u64 fq_neg(u64 a) { return a ? FQ_Q - a : 0; }
@@ -74,7 +76,7 @@ FQ_HD u64 fq_mul(u64 a, u64 b)                         // canonical in, canonica
 }
 // Shoup / Harvey lazy multiplication by a constant w with ws = floor(w * 2^64 / Q):
 // returns w*y mod Q + {0, Q}, i.e. a value in [0, 2Q), for ANY 64-bit y.
-FQ_HD u64 fq_mul_shoup(u64 y, u64 w, u64 ws) { return w * y - fq_mulhi(ws, y) * FQ_Q; }
+FQ_HD u64 fq_mul_shoup(u64 y, u64 w, u64 ws) { return w * y + fq_mulhi(ws, y) * (0ULL - FQ_Q); }   // all IMAD, no subtract
 // Montgomery reduction: (hi:lo) * 2^-64 mod Q, lazy: result < hi + Q + 1
 FQ_HD u64 fq_redc(u64 lo, u64 hi)
 {

@@ -168,7 +168,7 @@ __global__ void __launch_bounds__(NttPlan<LOGN>::T) k_ntt(const u64 *__restrict_
 #pragma unroll
         for (int e = 0; e < 8; e++) {
             const int id = P::idx(tau, e, P::fwd_lb(P::NPASS - 1));
-            const u64 v = fq_csub(fq_csub(x[e], FQ_2Q), FQ_Q);            // lazy [0,4Q) -> canonical
+            const u64 v = fq_csub(fq_csub(fq_csub(x[e], FQ_2Q), FQ_2Q), FQ_Q);   // lazy (< 2^64 - 2^17) -> canonical
             if (mode == 0) dst[id] = v;
             else dst[P::swz(id)] = fq_mul(v, scale);                     // mode 2: scale = 2^64 / N (Montgomery form, 1/N folded)
         }
@@ -376,11 +376,15 @@ __global__ void __launch_bounds__(128) k_keyswitch(KSArgs a)
 }
 
 // ------------------------------------------------------------------------------------------------------
-// K2 + K3: blind rotation + sample extraction.  One CTA per PBS; (K+1) thread groups of N/8 threads, group g
-// owns accumulator polynomial g: it decomposes/forward-transforms input polynomial g and produces/inverse-
-// transforms output polynomial g.  Shared memory (u64 words):
-//   ACC[(K+1)][N] natural order | SA[(K+1)][N], SB[(K+1)][N] transposes (swizzled) | DH[(K+1)L][N] digit
-//   spectra (aliases SB when L == 1) | BS[(K+1)L][(K+1)][N] current BSK row (TMA target, when BSK_SMEM)
+// K2 + K3: blind rotation + sample extraction.  One CTA runs PB bootstraps in lock-step (they share the BSK row in
+// shared memory); each bootstrap has (K+1) thread groups of N/8 threads, group g owns accumulator polynomial g: it
+// decomposes / forward-transforms input polynomial g and produces / inverse-transforms output polynomial g.
+// Shared memory (u64 words):
+//   per bootstrap: ACC[(K+1)][N] natural order | S[(K+1)][N] transpose scratch (swizzled) | DH[(K+1)L][N] digit spectra
+//                  (aliases S when L == 1)
+//   per CTA      : BS[(K+1)L][(K+1)][N] current BSK row (TMA target, when BSK_SMEM)
+// PB = 2 doubles the resident warps per SM (8 per scheduler at 64 registers per thread): the first version of this
+// kernel ran 4 warps per scheduler and was issue-latency bound (profiles/r1_v2_*).
 // ------------------------------------------------------------------------------------------------------
 struct BRArgs {
     const u16 *ms;                      // [(lincomb - lc_begin) * B + inst][n+1]
@@ -389,48 +393,57 @@ struct BRArgs {
     const int32_t *bs_lc, *bs_slot, *bs_tab_ptr, *bs_mode;
     const u8 *bs_tab;
     u64 *wires; u64 *tap_acc;
-    long long B;
+    long long B, jobs;
     int node_begin, lc_begin, n, p, beta;
 };
-template <int LOGN, int K, int L, bool BSK_SMEM>
+template <int LOGN, int K, int L, bool BSK_SMEM, int PB>
 struct BRCfg {
-    static constexpr int N = 1 << LOGN, G = K + 1, T = N / 8, THREADS = G * T;
-    static constexpr size_t acc_w = (size_t)G * N, tr_w = (size_t)G * N;
+    static constexpr int N = 1 << LOGN, G = K + 1, T = N / 8, PT = G * T, THREADS = PB * PT;
+    static constexpr size_t acc_w = (size_t)G * N, s_w = (size_t)G * N;
     static constexpr size_t dh_w = (L == 1) ? 0 : (size_t)G * L * N;
+    static constexpr size_t per_pbs_w = acc_w + s_w + dh_w;
     static constexpr size_t bs_w = BSK_SMEM ? (size_t)G * L * G * N : 0;
     static constexpr size_t row_w = (size_t)G * L * G * N;       // BSK words per CMUX step
+    __host__ __device__ static constexpr size_t ms_stride(int n) { return (((size_t)(n + 1) * 2 + 15) / 16) * 16; }
     __host__ __device__ static constexpr size_t smem_bytes(int n)
     {
-        return 8 * (acc_w + 2 * tr_w + dh_w + bs_w) + 16 /* mbarrier */ + (((size_t)(n + 1) * 2 + 15) / 16) * 16 + 64 /* table */;
+        return 8 * (PB * per_pbs_w + bs_w) + 16 /* mbarrier */ + PB * ((((size_t)(n + 1) * 2 + 15) / 16) * 16 + 64 /* table */);
     }
 };
 
-template <int LOGN, int K, int L, bool BSK_SMEM>
-__global__ void __launch_bounds__((K + 1) * (1 << LOGN) / 8, 1) k_blind_rotate(BRArgs a)
+#ifndef BR_LB_MULT
+#define BR_LB_MULT 1      /* experiment knob: pretend the CTA is this many times larger to cap registers */
+#endif
+template <int LOGN, int K, int L, bool BSK_SMEM, int PB>
+__global__ void __launch_bounds__(PB * (K + 1) * (1 << LOGN) / 8 * BR_LB_MULT, 1) k_blind_rotate(BRArgs a)
 {
-    using C = BRCfg<LOGN, K, L, BSK_SMEM>;
+    using C = BRCfg<LOGN, K, L, BSK_SMEM, PB>;
     using P = NttPlan<LOGN>;
     constexpr int N = C::N, G = C::G, T = C::T;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    u64 *ACC = (u64 *)smem_raw;
-    u64 *SA = ACC + C::acc_w;
-    u64 *SB = SA + C::tr_w;
-    u64 *DH = (L == 1) ? SB : SB + C::tr_w;
-    u64 *BS = SB + C::tr_w + C::dh_w;
+    const int tid = threadIdx.x, pb = tid / C::PT, ptid = tid % C::PT, g = ptid / T, tau = ptid % T;
+    u64 *base = (u64 *)smem_raw + (size_t)pb * C::per_pbs_w;
+    u64 *ACC = base;
+    u64 *S = ACC + C::acc_w;
+    u64 *DH = (L == 1) ? S : S + C::s_w;
+    u64 *BS = (u64 *)smem_raw + (size_t)PB * C::per_pbs_w;
     u64 *mbar = BS + C::bs_w;
-    u16 *s_ms = (u16 *)(mbar + 2);
-    u8 *s_tab = (u8 *)s_ms + (((size_t)(a.n + 1) * 2 + 15) / 16) * 16;
+    const size_t ms_stride = C::ms_stride(a.n);
+    u16 *s_ms = (u16 *)((unsigned char *)(mbar + 2) + (size_t)pb * (ms_stride + 64));
+    u8 *s_tab = (u8 *)s_ms + ms_stride;
 
-    const int tid = threadIdx.x, g = tid / T, tau = tid % T;
-    const long long job = blockIdx.x;
+    // the second bootstrap of the last CTA may not exist: it recomputes the previous job and skips the store
+    long long job = (long long)blockIdx.x * PB + pb;
+    const bool live = job < a.jobs;
+    if (!live) job = a.jobs - 1;
     const int node = a.node_begin + (int)(job / a.B);
     const long long inst = job % a.B;
     const int n = a.n, p = a.p;
     const u16 *ms = a.ms + ((size_t)(a.bs_lc[node] - a.lc_begin) * a.B + inst) * (size_t)(n + 1);
     const int tab0 = a.bs_tab_ptr[node], tabL = a.bs_tab_ptr[node + 1] - tab0, mode = a.bs_mode[node];
 
-    for (int i = tid; i <= n; i += C::THREADS) s_ms[i] = ms[i];
-    if (tid < 64) s_tab[tid] = (tid < tabL) ? a.bs_tab[tab0 + tid] : 0;
+    for (int i = ptid; i <= n; i += C::PT) s_ms[i] = ms[i];
+    if (ptid < 64) s_tab[ptid] = (ptid < tabL) ? a.bs_tab[tab0 + ptid] : 0;
     if (BSK_SMEM && tid == 0) mbar_init(mbar, 1);
     __syncthreads();
     if (BSK_SMEM && tid == 0) {
@@ -440,10 +453,10 @@ __global__ void __launch_bounds__((K + 1) * (1 << LOGN) / 8, 1) k_blind_rotate(B
         for (int q = 0; q < G * L * G; q++) tma_load_1d(BS + (size_t)q * N, a.bsk + (size_t)q * N, N * 8, mbar);
     }
     // ---- accumulator init: ACC = (0, .., 0, X^{-b~} * TV) ; TV[j] = F(round(j*p/N)), F(x) = tv[x]*Delta - s*Delta/2
+    u64 *acc = ACC + (size_t)g * N;
     {
         const u64 delta = fbs_delta(p), off = fq_mul((u64)mode, delta >> 1);
         const int bt = s_ms[n];
-        u64 *acc = ACC + (size_t)g * N;
 #pragma unroll
         for (int e = 0; e < 8; e++) {
             const int j = tau + e * T;
@@ -464,9 +477,10 @@ __global__ void __launch_bounds__((K + 1) * (1 << LOGN) / 8, 1) k_blind_rotate(B
     }
     __syncthreads();
 
-    auto gsync = [g] { bar_sync_named(1 + g, T); };
-    u64 *sA = SA + (size_t)g * N, *sB = SB + (size_t)g * N;
-    u64 *acc = ACC + (size_t)g * N;
+    const int bar_g = 1 + pb * G + g, bar_p = 1 + PB * G + pb;      // named barriers: per group, per bootstrap
+    auto gsync = [bar_g] { bar_sync_named(bar_g, T); };
+    auto psync = [bar_p] { bar_sync_named(bar_p, C::PT); };
+    u64 *sg = S + (size_t)g * N;
     const int beta = a.beta;
 
     for (int i = 0; i < n; i++) {
@@ -485,19 +499,18 @@ __global__ void __launch_bounds__((K + 1) * (1 << LOGN) / 8, 1) k_blind_rotate(B
 #pragma unroll
             for (int jj = 0; jj < L; jj++) dg[jj][e] = fq_from_i64(d[jj]);
         }
-        // ---- forward NTTs, spectra to DH (swizzled, layout lb = 0)
+        // ---- forward NTTs through the group's scratch polynomial; spectra to DH (swizzled, layout lb = 0)
 #pragma unroll
         for (int jj = 0; jj < L; jj++) {
-            if (jj > 0) gsync();                     // previous transform's reads of sA/sB are complete
-            ntt_forward<LOGN>(dg[jj], tau, sA, sB, a.psi_rev, gsync);
+            ntt_fwd1_from<LOGN, 0>(dg[jj], tau, sg, a.psi_rev, gsync, jj == 0);
             u64 *dh = DH + (size_t)(g * L + jj) * N;
-            if (L == 1 && (P::NPASS & 1) == 1) gsync();   // DH aliases SB: the last transpose (pass NPASS-2) used SB iff NPASS is odd
+            if (L == 1 && P::NPASS > 1) gsync();            // DH aliases S: the last transpose's readers are done
 #pragma unroll
             for (int e = 0; e < 8; e++) dh[P::swz(P::idx(tau, e, 0))] = dg[jj][e];
         }
-        __syncthreads();
-        // ---- pointwise: out_g = sum_r DH[r] * BSK[r][g].  DH is lazy (< 4Q), the key is canonical and in Montgomery
-        // form, so a PAIR of 128-bit products (< 8Q^2 < 2^127) is reduced by one REDC to < 3Q, then folded to < 2Q.
+        psync();
+        // ---- pointwise: out_g = sum_r DH[r] * BSK[r][g].  DH is lazy (< 2^64), the key is canonical and in Montgomery
+        // form, so a PAIR of 128-bit products (< 2^127) is reduced by one REDC to < 3Q, then folded to < 2Q.
         if (BSK_SMEM) mbar_wait(mbar, (u32)(i & 1));
         u64 x[8];
         {
@@ -522,10 +535,11 @@ __global__ void __launch_bounds__((K + 1) * (1 << LOGN) / 8, 1) k_blind_rotate(B
                 x[e] = s;                                  // < 2Q: what the inverse butterflies expect
             }
         }
-        // ---- inverse NTT; the first transpose barrier is CTA-wide: after it nobody reads DH/BS of this step
-        auto csync_prefetch = [&] {
+        // ---- inverse NTT.  After its first register pass a CTA-wide barrier guarantees that nobody reads DH / BS of
+        // this step any more: the scratch may be overwritten and the next GGSW row is prefetched by TMA.
+        auto after_pass0 = [&] {
             __syncthreads();
-            if (BSK_SMEM && tid == 0 && i + 1 < n) {          // stream the next GGSW row while this step finishes
+            if (BSK_SMEM && tid == 0 && i + 1 < n) {
                 fence_proxy_async();
                 mbar_expect_tx(mbar, (u32)(C::row_w * 8));
                 const u64 *src = a.bsk + (size_t)(i + 1) * C::row_w;
@@ -533,25 +547,28 @@ __global__ void __launch_bounds__((K + 1) * (1 << LOGN) / 8, 1) k_blind_rotate(B
                 for (int q = 0; q < G * L * G; q++) tma_load_1d(BS + (size_t)q * N, src + (size_t)q * N, N * 8, mbar);
             }
         };
-        ntt_inv_from<LOGN, 0>(x, tau, sA, sB, a.psi_inv_rev, csync_prefetch, gsync);
+        ntt_inv1_from<LOGN, 0>(x, tau, sg, a.psi_inv_rev, after_pass0, gsync);
 #pragma unroll
         for (int e = 0; e < 8; e++) {
             const int j = P::idx(tau, e, P::inv_lb(P::NPASS - 1));
             acc[j] = fq_add(acc[j], fq_csub(x[e], FQ_Q));
         }
-        __syncthreads();
+        gsync();                                         // ACC_g is only read by group g (next step's rotation)
     }
     // ---- K3: sample extraction of coefficient 0 (+ table-mode offset s*Delta/2 on the body)
-    const size_t CT = (size_t)K * N + 1;
-    u64 *out = a.wires + ((size_t)a.bs_slot[node] * a.B + inst) * CT;
-    for (int w = tid; w < K * N; w += C::THREADS) {
-        const int u = w / N, j = w % N;
-        out[w] = (j == 0) ? ACC[(size_t)u * N] : fq_neg(ACC[(size_t)u * N + N - j]);
-    }
-    if (tid == 0) out[(size_t)K * N] = fq_add(ACC[(size_t)K * N], fq_mul((u64)mode, fbs_delta(p) >> 1));
-    if (a.tap_acc) {
-        u64 *t = a.tap_acc + (size_t)job * G * N;
-        for (int w = tid; w < G * N; w += C::THREADS) t[w] = ACC[w];
+    psync();
+    if (live) {
+        const size_t CT = (size_t)K * N + 1;
+        u64 *out = a.wires + ((size_t)a.bs_slot[node] * a.B + inst) * CT;
+        for (int w = ptid; w < K * N; w += C::PT) {
+            const int u = w / N, j = w % N;
+            out[w] = (j == 0) ? ACC[(size_t)u * N] : fq_neg(ACC[(size_t)u * N + N - j]);
+        }
+        if (ptid == 0) out[(size_t)K * N] = fq_add(ACC[(size_t)K * N], fq_mul((u64)mode, fbs_delta(p) >> 1));
+        if (a.tap_acc) {
+            u64 *t = a.tap_acc + (size_t)job * G * N;
+            for (int w = ptid; w < G * N; w += C::PT) t[w] = ACC[w];
+        }
     }
 }
 

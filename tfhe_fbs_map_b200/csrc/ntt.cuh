@@ -5,7 +5,7 @@
 // out, negacyclic twist merged into the twiddles psi_rev[m+i] = psi^bitrev(m+i); inverse = Gentleman-
 // Sande, bit-reversed in, natural out, WITHOUT the 1/N scale (it is folded into the bootstrapping key).
 // Butterflies are Harvey's lazy ones with Shoup twiddles (w, ws = floor(w*2^64/Q)):
-//   forward: inputs in [0,4Q), outputs in [0,4Q);   inverse: inputs in [0,2Q), outputs in [0,2Q).
+//   forward: inputs and outputs in [0, 2^64 - 2^17] (a little above 4Q);   inverse: inputs and outputs in [0,2Q).
 //
 // A pass is described by `lb`, the lowest of its three in-thread index bits:
 //     idx(tau, e) = ((tau >> lb) << (lb+3)) | (e << lb) | (tau & ((1<<lb)-1)),   e = 0..7
@@ -67,7 +67,9 @@ FQ_HD void ntt_fwd_pass(u64 (&x)[8], int tau, const fq_tw *__restrict__ psi_rev)
             if (e0 & (1 << q)) continue;
             const int e1 = e0 | (1 << q);
             const fq_tw w = fq_tw_load(psi_rev + m + ((th << (2 - q)) | (e0 >> (q + 1))));
-            const u64 u = fq_csub(x[e0], FQ_2Q), v = fq_mul_shoup(x[e1], w.w, w.ws);
+            // inputs < 2^64 - 2^17: subtracting 2Q when the top bit is set (one test on the high word) brings u below
+            // 2^63; with v < 2Q both outputs stay below 2^63 + 2Q = 2^64 - 2^17 + 2, so the invariant is closed.
+            const u64 u = fq_lazy_fold(x[e0]), v = fq_mul_shoup(x[e1], w.w, w.ws);
             x[e0] = u + v;
             x[e1] = u - v + FQ_2Q;
         }
@@ -122,6 +124,42 @@ __device__ __forceinline__ void ntt_forward(u64 (&x)[8], int tau, u64 *bufA, u64
 {
     ntt_fwd_from<LOGN, 0>(x, tau, bufA, bufB, psi_rev, sync);
 }
+// ---- single-buffer variants: one scratch polynomial per thread group, two barriers per transpose -----------
+// (used by the blind-rotate kernel, where shared memory rather than barrier count limits residency)
+template <int LOGN, int PASS, class Sync>
+__device__ __forceinline__ void ntt_fwd1_from(u64 (&x)[8], int tau, u64 *buf, const fq_tw *psi_rev, Sync sync, bool buf_free)
+{
+    using P = NttPlan<LOGN>;
+    ntt_fwd_pass<LOGN, PASS>(x, tau, psi_rev);
+    if constexpr (PASS + 1 < P::NPASS) {
+        constexpr int lb0 = P::fwd_lb(PASS), lb1 = P::fwd_lb(PASS + 1);
+        if (!buf_free) sync();                          // earlier readers of buf are done
+#pragma unroll
+        for (int e = 0; e < 8; e++) buf[P::swz(P::idx(tau, e, lb0))] = x[e];
+        sync();
+#pragma unroll
+        for (int e = 0; e < 8; e++) x[e] = buf[P::swz(P::idx(tau, e, lb1))];
+        ntt_fwd1_from<LOGN, PASS + 1>(x, tau, buf, psi_rev, sync, false);
+    }
+}
+// inverse: pass 0 is done by the caller's registers; `after_pass0` runs between pass 0 and the first write to buf
+template <int LOGN, int PASS, class Sync0, class Sync>
+__device__ __forceinline__ void ntt_inv1_from(u64 (&x)[8], int tau, u64 *buf, const fq_tw *psi_inv_rev, Sync0 after_pass0, Sync sync)
+{
+    using P = NttPlan<LOGN>;
+    ntt_inv_pass<LOGN, PASS>(x, tau, psi_inv_rev);
+    if constexpr (PASS == 0) after_pass0(); else if constexpr (PASS + 1 < P::NPASS) sync();
+    if constexpr (PASS + 1 < P::NPASS) {
+        constexpr int lb0 = P::inv_lb(PASS), lb1 = P::inv_lb(PASS + 1);
+#pragma unroll
+        for (int e = 0; e < 8; e++) buf[P::swz(P::idx(tau, e, lb0))] = x[e];
+        sync();
+#pragma unroll
+        for (int e = 0; e < 8; e++) x[e] = buf[P::swz(P::idx(tau, e, lb1))];
+        ntt_inv1_from<LOGN, PASS + 1>(x, tau, buf, psi_inv_rev, sync, sync);
+    }
+}
+
 // inverse NTT passes PASS.. ; the caller supplies x in layout inv_lb(PASS)
 template <int LOGN, int PASS, class Sync0, class Sync>
 __device__ __forceinline__ void ntt_inv_from(u64 (&x)[8], int tau, u64 *bufA, u64 *bufB, const fq_tw *psi_inv_rev, Sync0 sync_first, Sync sync)
