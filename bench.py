@@ -133,6 +133,62 @@ def run_reference(args, wl, ps, rank, world):
     print(json.dumps(line))
 
 
+def run_nodes(args, wl, ps, be, rank, world, local, torch, dist):
+    """BASELINE configs[3]: ONE circuit, node-sharded levels, NCCL all-gather of output LWEs per level."""
+    from tfhe_fbs_map_b200 import levelize
+    from tfhe_fbs_map_b200.dist import B200Engine, run_node_sharded
+    from oracle import cleartext
+    env = load_env(wl["lbf"])
+    prog = levelize(env, wl["p"], shard_pad=world, reuse_slots=False)
+    cp = be.load(prog)
+    B = args.batch
+    rng = np.random.default_rng(77)                      # every rank evaluates the SAME instances
+    bits = rng.integers(0, 2, (prog.n_inputs, B)).astype(np.uint8)
+    want = cleartext.lut_eval(env, {nm: bits[i] for i, nm in enumerate(prog.input_names)})
+    want_mat = np.array([np.asarray(want[nm]) for nm in prog.output_names], dtype=np.uint8)
+    eng = B200Engine(be, cp, B, torch)
+    eng.encrypt(bits)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    for _ in range(args.warmup):
+        run_node_sharded(eng, prog, dist, world, rank)
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    words = 0
+    for _ in range(args.steps):
+        words += run_node_sharded(eng, prog, dist, world, rank)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    sampler.stop_flag.set(); sampler.join(timeout=2)
+    out = eng.decrypt()
+    mism = int((out != want_mat).sum())
+    if rank == 0:
+        n_pbs = prog.n_boots * B * args.steps
+        print(json.dumps(dict(
+            metric="PBS/sec", value=n_pbs / (ms * 1e-3), unit="PBS/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
+            ms_per_step=ms / args.steps, higher_is_better=True, scaling="strong", vs_baseline=None, dtype="u64 (mod 2^62-2^16+1)",
+            data="synthetic", config=dict(workload=args.workload, desc=wl["desc"], param_set=ps.name, fbs_size=wl["p"], instances=B,
+                                          pbs_per_instance=prog.n_boots, levels=prog.n_levels, level_width_median=int(np.median(prog.level_widths)),
+                                          sharding="nodes of each level split across GPUs; NCCL all-gather of output LWE ciphertexts per level"),
+            evals_per_s=B * args.steps / (ms * 1e-3), mismatches=mism,
+            allgather_bytes_per_step=words * 8 // max(1, args.steps), gpu_launches=3 * prog.n_levels * args.steps, clocks=sampler.summary())))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -143,6 +199,9 @@ def main():
     ap.add_argument("--batch", type=int, default=296, help="encrypted instances per GPU per step")
     ap.add_argument("--param-set", default="A")
     ap.add_argument("--seed", type=int, default=20241018)
+    ap.add_argument("--shard", default="instances", choices=["instances", "nodes"],
+                    help="instances: batch split across GPUs, no collective (weak scaling); nodes: one circuit, each level's "
+                         "bootstraps split across GPUs + NCCL all-gather of the output LWE ciphertexts per level (strong scaling)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -168,6 +227,9 @@ def main():
     from tfhe_fbs_map_b200.backend import B200Backend, RunStats
 
     be = B200Backend(ps, device=local, seed=args.seed)          # identical seeded keys on every rank: no key broadcast
+    if args.shard == "nodes":
+        run_nodes(args, wl, ps, be, rank, world, local, torch, dist)
+        return
     env = load_env(wl["lbf"])
     prog = levelize(env, wl["p"], preserve_inputs=True)      # steps re-run the same resident encrypted inputs
     cp = be.load(prog)

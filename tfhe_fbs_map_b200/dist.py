@@ -1,0 +1,105 @@
+"""Multi-GPU partitioning of the encrypted evaluation: one process per GPU, ``torch.distributed`` for plumbing.
+
+Two ways the path shards (BASELINE.json configs[2] and configs[3]):
+
+* **instances** -- a batch of independent encrypted circuit instances is split contiguously across ranks; keys are
+  replicated by running the same *seeded* key generation on every device, so there is **no collective** on the data
+  path (outputs may be gathered at the end for convenience).
+* **nodes** -- ONE circuit (any batch size) whose levels are wide: the bootstraps of each level are split across ranks,
+  every rank keeps a full replica of the wire buffer, and after each level the new output ciphertexts are exchanged
+  with an in-place **all-gather** (NCCL over NVLink).  ``levelize(shard_pad=world)`` lays the slots of a level out
+  contiguously and padded to a multiple of ``world`` so every rank contributes an equal, contiguous chunk.
+
+The level loop is written against a small *engine* interface (``encrypt``, ``run_level``, ``decrypt``, ``wires``) so
+that the partitioning / exchange logic is exercised on CPU with the gloo backend (tests/test_dist_gloo.py, where the
+engine is backed by the CPU oracle) and on GPUs with NCCL (``B200Engine``).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def instance_shard(total: int, world: int, rank: int):
+    """Contiguous split of ``total`` instances: returns (offset, count) of this rank (sizes differ by at most 1)."""
+    base, rem = divmod(total, world)
+    count = base + (1 if rank < rem else 0)
+    offset = rank * base + min(rank, rem)
+    return offset, count
+
+
+def level_node_range(width: int, world: int, rank: int):
+    """Bootstraps [begin, end) of a level of ``width`` nodes handled by ``rank``; chunk = ceil(width/world) so that the
+    slot region of the level (padded to world*chunk) splits into equal contiguous pieces."""
+    chunk = -(-width // world)
+    begin = min(rank * chunk, width)
+    end = min(begin + chunk, width)
+    return begin, end, chunk
+
+
+class B200Engine:
+    """Engine over the CUDA library with the wire buffer held in a torch tensor (device memory + stream plumbing)."""
+
+    def __init__(self, backend, cprog, B, torch_mod):
+        self.be, self.cp, self.B, self.torch = backend, cprog, B, torch_mod
+        words = backend.wires_bytes(cprog, B) // 8
+        self.wires = torch_mod.empty(words, dtype=torch_mod.int64, device=f"cuda:{backend.device}")
+        self.ct_words = backend.params.ct_words
+        self.stream = torch_mod.cuda.current_stream().cuda_stream
+
+    def encrypt(self, bits: np.ndarray, inst_offset=0, total=None):
+        d_in = self.torch.from_numpy(np.ascontiguousarray(bits, dtype=np.uint8)).to(self.wires.device)
+        self.be.encrypt_inputs(self.cp, d_in.data_ptr(), self.B, self.wires.data_ptr(), stream=self.stream,
+                               inst_offset=inst_offset, total=total or self.B)
+        self.torch.cuda.current_stream().synchronize()
+
+    def run_level(self, level, node_begin, node_end):
+        self.be.run_level(self.cp, level, self.B, self.wires.data_ptr(), node_begin, node_end, stream=self.stream)
+
+    def decrypt(self) -> np.ndarray:
+        n_out = len(self.cp.program.output_names)
+        d_out = self.torch.empty((n_out, self.B), dtype=self.torch.uint8, device=self.wires.device)
+        self.be.decrypt_outputs(self.cp, self.B, self.wires.data_ptr(), d_out.data_ptr(), stream=self.stream)
+        self.torch.cuda.current_stream().synchronize()
+        return d_out.cpu().numpy()
+
+    def slot_view(self, slot_begin, n_slots):
+        per = self.B * self.ct_words
+        return self.wires[slot_begin * per:(slot_begin + n_slots) * per]
+
+
+def run_node_sharded(engine, program, dist, world: int, rank: int, in_place: bool = True):
+    """Evaluate all levels with the bootstraps of each level split over ``world`` ranks and an all-gather of the new
+    output ciphertexts after every level.  ``program`` must come from ``levelize(..., shard_pad=world)``.
+    Returns the number of words exchanged (for reporting)."""
+    assert program.contiguous_levels and (world == 1 or program.shard_pad == world), \
+        "program must be levelised with shard_pad=world (reuse_slots=False when world == 1)"
+    a = program.arrays
+    exchanged = 0
+    for lv in range(program.n_levels):
+        b0, b1 = int(a["bs_level_ptr"][lv]), int(a["bs_level_ptr"][lv + 1])
+        width = b1 - b0
+        nb, ne, chunk = level_node_range(width, world, rank)
+        if ne > nb:
+            engine.run_level(lv, nb, ne)
+        if world == 1:
+            continue
+        first_slot = int(a["bs_slot"][b0])
+        region = engine.slot_view(first_slot, chunk * world)
+        mine = engine.slot_view(first_slot + rank * chunk, chunk)
+        if in_place:
+            dist.all_gather_into_tensor(region, mine)
+        else:   # backends without an in-place path: gather into views of the region
+            parts = [engine.slot_view(first_slot + r * chunk, chunk) for r in range(world)]
+            dist.all_gather(parts, mine.clone())
+        exchanged += region.numel()
+    return exchanged
+
+
+def eval_instances_sharded(backend, cprog, bits: np.ndarray, world: int, rank: int):
+    """Instance-sharded evaluation through the host-buffer call: this rank evaluates its slice, no collective."""
+    total = bits.shape[1]
+    off, cnt = instance_shard(total, world, rank)
+    if cnt == 0:
+        return off, np.zeros((len(cprog.program.output_names), 0), np.uint8)
+    out = backend.eval_bits(cprog, np.ascontiguousarray(bits[:, off:off + cnt]), inst_offset=off, total=total)
+    return off, out
