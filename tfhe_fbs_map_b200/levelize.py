@@ -16,9 +16,14 @@ from dataclasses import dataclass, field
 
 import numpy as np
 
-from .lut_env import Bootstrap, Const, Input, LinearProd, Node
 
 MAX_FANIN = 64
+
+
+def _kind(node) -> str:
+    """Node classes are matched by NAME so that the reference's own LutExecEnv instances (fbs_exec_env.py:22-61) can be
+    levelised as well as this package's mirror classes."""
+    return type(node).__name__
 
 
 class CProgDesc(ctypes.Structure):
@@ -55,7 +60,7 @@ def table_mode(table, p):
 def min_fbs_size(env) -> int:
     """Smallest p for which every bootstrap table of the circuit is realisable."""
     need = 2
-    tables = [i.table for i in env.instructions if isinstance(i, Bootstrap)]
+    tables = [i.table for i in env.instructions if _kind(i) == "Bootstrap"]
     for tab in tables:
         need = max(need, (len(tab) + 1) // 2, max(tab) + 1)
     p = need
@@ -98,9 +103,9 @@ class Program:
 
 def _flatten(node, scale, acc, const):
     """Expand a node into {wire: coef} over wires (Input/Bootstrap) plus a constant."""
-    if isinstance(node, Const):
+    if _kind(node) == "Const":
         return const + scale * node.value
-    if isinstance(node, LinearProd):
+    if _kind(node) == "LinearProd":
         const += scale * node.const_coef
         for c, v in node.coef_vals:
             const = _flatten(v, scale * c, acc, const)
@@ -118,11 +123,11 @@ def levelize(env, p: int | None = None, reuse_slots: bool = True, shard_pad: int
     instrs = env.instructions
     if p is None:
         if clear:   # cleartext look-ups have no modulus; pick one that passes the loader's table-length check
-            p = max([2] + [len(i.table) for i in env.instructions if isinstance(i, Bootstrap)])
+            p = max([2] + [len(i.table) for i in env.instructions if _kind(i) == "Bootstrap"])
         else:
             p = min_fbs_size(env)
-    inputs = [i for i in instrs if isinstance(i, Input)]
-    boots = [i for i in instrs if isinstance(i, Bootstrap)]
+    inputs = [i for i in instrs if _kind(i) == "Input"]
+    boots = [i for i in instrs if _kind(i) == "Bootstrap"]
     by_name = {i.name: i for i in instrs}
 
     level = {i.name: 0 for i in inputs}
