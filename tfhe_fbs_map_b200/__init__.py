@@ -7,6 +7,7 @@ from .lut_env import LutExecEnv, FbsExecEnv, B200FbsExecEnv
 from .bit_env import BitExecEnv
 from .levelize import levelize, Program, table_mode, min_fbs_size
 from . import params
+from .mapper import MapToFBSBasic, MapToFBSHeur
 
 __all__ = ["LutExecEnv", "FbsExecEnv", "B200FbsExecEnv", "BitExecEnv", "levelize", "Program", "table_mode",
-           "min_fbs_size", "params"]
+           "min_fbs_size", "params", "MapToFBSBasic", "MapToFBSHeur"]
