@@ -27,7 +27,7 @@ extern "C" {
 #define FBS_ERR_STATE (-3)    /* call order violated (e.g. eval before keygen) */
 #define FBS_ERR_NOMEM (-4)
 
-/* TFHE parameter set.  Ciphertext modulus is Q = 2^62 - 2^16 + 1. */
+/* TFHE parameter set.  Ciphertext modulus is q = p1*p2 = 0x3FFE8001 * 0x3FFF4001 (60 bits). */
 typedef struct fbs_params {
     int32_t n;          /* small LWE dimension                         */
     int32_t k;          /* GLWE dimension                              */

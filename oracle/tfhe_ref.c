@@ -18,7 +18,7 @@
  * pattern (the pattern experiments/concrete.patch:62-74 edits) with the message encoding of
  * experiments/concrete.patch:21-27 (absolute number of message values p, one negacyclic padding
  * "bit": Delta = q/(2p), decision half-interval q/(4p)) and the table modes of
- * fbs_mapper/map_to_fbs.py:81-98, over the prime Q = 2^62 - 2^16 + 1 as ciphertext modulus.  It is deliberately written with plain loops and unsigned __int128 so that it shares no
+ * fbs_mapper/map_to_fbs.py:81-98, over q = p1*p2 (two 30-bit NTT primes, 60 bits) as ciphertext modulus.  It is deliberately written with plain loops and unsigned __int128 so that it shares no
  * code (and no bugs) with the CUDA product; both follow the written spec in DESIGN.md section 3, so
  * with identical seeds they must agree BIT FOR BIT at every ciphertext tap.
  */
@@ -37,13 +37,22 @@ typedef uint8_t u8;
 typedef unsigned __int128 u128;
 typedef __int128 i128;
 
-#define GLP 0x3FFFFFFFFFFF0001ULL   /* ciphertext modulus Q = 2^62 - 2^16 + 1 */
+#define RP1 1073643521ULL            /* p1 = 0x3FFE8001 */
+#define RP2 1073692673ULL            /* p2 = 0x3FFF4001 */
+#define GLP (RP1 * RP2)              /* ciphertext modulus q = p1*p2 = 0x0FFF70019FFDC001 */
 
 /* ---------------- field arithmetic (slow-and-obvious on purpose) ---------------- */
 static inline u64 f_add(u64 a, u64 b) { u128 s = (u128)a + b; if (s >= GLP) s -= GLP; return (u64)s; }
 static inline u64 f_sub(u64 a, u64 b) { return a >= b ? a - b : (u64)((u128)a + GLP - b); }
 static inline u64 f_neg(u64 a) { return a ? GLP - a : 0; }
 static inline u64 f_mul(u64 a, u64 b) { return (u64)(((u128)a * b) % GLP); }   /* slow and obvious on purpose */
+static u64 pmod(u64 b, u64 e, u64 m) { u128 r = 1, x = b % m; while (e) { if (e & 1) r = r * x % m; x = x * x % m; e >>= 1; } return (u64)r; }
+static u64 crt(u64 a, u64 b)       /* the x in [0,q) with x = a mod p1, x = b mod p2 */
+{
+    u64 p1inv = pmod(RP1, RP2 - 2, RP2);
+    u64 t = (u64)((u128)((b + RP2 - a % RP2) % RP2) * p1inv % RP2);
+    return a + RP1 * t;
+}
 static u64 f_pow(u64 b, u64 e) { u64 r = 1; while (e) { if (e & 1) r = f_mul(r, b); b = f_mul(b, b); e >>= 1; } return r; }
 static inline u64 f_from_i64(i64 v) { return v >= 0 ? (u64)v % GLP : GLP - ((u64)(-v) % GLP); }
 
@@ -59,7 +68,12 @@ static inline u64 rnd64(u64 seed, u64 dom, u64 idx)
     u64 h = mix64(seed ^ (dom * 0xD1B54A32D192ED03ULL));
     return mix64(h + (idx + 1) * 0x9E3779B97F4A7C15ULL);
 }
-static inline u64 rnd_uniform(u64 seed, u64 dom, u64 idx) { u64 u = rnd64(seed, dom, idx) >> 2; return u >= GLP ? u - GLP : u; }
+static inline u64 rnd_uniform(u64 seed, u64 dom, u64 idx)
+{
+    u64 u = rnd64(seed, dom, idx) >> 4;                       /* 60 bits */
+    if (u >= GLP) u = (u64)(((u128)rnd64(seed, dom + 64, idx) * GLP) >> 64);   /* rare second draw, scaled */
+    return u;
+}
 /* Irwin-Hall(12) over 32-bit uniforms, std = scale (in units of 1/Q of the torus) */
 static inline u64 rnd_noise(u64 seed, u64 dom, u64 idx, u64 scale)
 {
@@ -95,21 +109,31 @@ static u32 bitrev(u32 x, int bits) { u32 r = 0; for (int i = 0; i < bits; i++) {
 /* gadget element g_j = round(Q / B^(j+1)), j = 0..l-1 */
 static u64 gadget(int beta, int j) { u128 B = (u128)1 << (beta * (j + 1)); return (u64)(((u128)GLP + B / 2) / B); }
 
-/* decomposition: closest multiple of Q/B^l, balanced digits in [-B/2, B/2) */
-static void decompose(u64 x, int beta, int l, int32_t *d /* [l], d[0] is the most significant level */)
+/* y = round(x * 2^bits / q) mod 2^bits.  With x = r1 + p1*t: up to 24 bits
+ * y = (t*K63 + 8*r1 + 2^(s-1)) >> s, s = 63 - bits, K63 = floor(2^63 / p2); beyond, through floor(2^123 / q). */
+static u64 round_top(u64 x, int bits)
 {
-    int bl = beta * l;
-    u64 y = ((x + (1ULL << (61 - bl))) >> (62 - bl)) & ((1ULL << bl) - 1);   /* round(x*2^bl/2^62), wraps to 0 */
+    u64 mask = (1ULL << bits) - 1;
+    if (bits <= 24) {
+        u64 t = x / RP1, r1 = x % RP1, K63 = (1ULL << 63) / RP2;
+        int s = 63 - bits;
+        return ((t * K63 + (r1 << 3) + (1ULL << (s - 1))) >> s) & mask;
+    }
+    u64 RQ = (u64)((((u128)1) << 123) / GLP);
+    u64 sc = (u64)(((u128)x * RQ) >> 64);
+    return ((sc + (1ULL << (58 - bits))) >> (59 - bits)) & mask;
+}
+/* decomposition: closest multiple of q/B^l, balanced digits in [-B/2, B/2), d[0] = most significant level */
+static void decompose(u64 x, int beta, int l, int32_t *d)
+{
+    u64 y = round_top(x, beta * l);
     u64 Bm = (1ULL << beta) - 1, half = 1ULL << (beta - 1);
     for (int j = l - 1; j >= 0; j--) {
         u64 dig = y & Bm; y >>= beta;
         if (dig >= half) { d[j] = (int32_t)((i64)dig - (i64)(1LL << beta)); y += 1; } else d[j] = (int32_t)dig;
     }
 }
-static inline u32 modswitch(u64 x, int log2N /* log2(2N) */)
-{
-    return (u32)(((x + (1ULL << (61 - log2N))) >> (62 - log2N)) & ((1ULL << log2N) - 1));
-}
+static inline u32 modswitch(u64 x, int log2N /* log2(2N) */) { return (u32)round_top(x, log2N); }
 static inline u64 delta_of(int p) { return (GLP + (u64)p) / (2ULL * (u64)p); }
 
 /* ---------------- negacyclic NTT (Longa-Naehrig layout, natural in -> bit-reversed out) ---------------- */
@@ -174,14 +198,16 @@ ref_ctx *ref_ctx_create(const ref_params *P, u64 seed)
     ref_ctx *c = calloc(1, sizeof(ref_ctx));
     c->P = *P; c->seed = seed; c->logN = ilog2(P->N);
     int N = P->N;
-    /* primitive 2N-th root of unity: 7 is a quadratic non-residue mod Q, so 7^((Q-1)/2N) has order exactly 2N */
-    u64 psi = f_pow(7, (GLP - 1) / (2ULL * N)), psi_inv = f_pow(psi, GLP - 2);
+    /* primitive 2N-th root of unity mod q = CRT of roots mod each prime; 3 is a quadratic non-residue mod p1 and p2,
+     * so 3^((p-1)/2N) has order exactly 2N.  q is composite: inverses come from CRT, not from Fermat. */
+    u64 psi1 = pmod(3, (RP1 - 1) / (2ULL * N), RP1), psi2 = pmod(3, (RP2 - 1) / (2ULL * N), RP2);
+    u64 psi = crt(psi1, psi2), psi_inv = crt(pmod(psi1, RP1 - 2, RP1), pmod(psi2, RP2 - 2, RP2));
     c->psi_rev = malloc(8 * N); c->psi_inv_rev = malloc(8 * N);
     for (int i = 0; i < N; i++) {
         u32 r = bitrev((u32)i, c->logN);
         c->psi_rev[i] = f_pow(psi, r); c->psi_inv_rev[i] = f_pow(psi_inv, r);
     }
-    c->ninv = f_pow((u64)N, GLP - 2);
+    c->ninv = crt(pmod((u64)N, RP1 - 2, RP1), pmod((u64)N, RP2 - 2, RP2));
     return c;
 }
 void ref_ctx_destroy(ref_ctx *c)

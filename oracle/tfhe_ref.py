@@ -92,7 +92,8 @@ def lib():
     return _lib
 
 
-FBS_Q = 0x3FFFFFFFFFFF0001          # ciphertext modulus 2^62 - 2^16 + 1
+FBS_P1, FBS_P2 = 0x3FFE8001, 0x3FFF4001
+FBS_Q = FBS_P1 * FBS_P2             # ciphertext modulus: product of two 30-bit NTT primes (60 bits)
 GOLDILOCKS_P = FBS_Q   # old name kept for the tests' imports
 
 

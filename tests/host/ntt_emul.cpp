@@ -1,49 +1,56 @@
-// Host emulation of the device NTT pass/layout/twiddle logic (tfhe_fbs_map_b200/csrc/ntt.cuh).
-// Loops over tau play the threads, array copies play the shared-memory transposes.  Compared against the
-// textbook in-place negacyclic NTT loops and against a schoolbook product.  Exit code 0 = all good.
+// Host emulation of the device arithmetic and NTT pass/layout/twiddle logic (tfhe_fbs_map_b200/csrc/fq.cuh, ntt.cuh).
+// Loops over tau play the threads, array copies play the shared-memory transposes.  Compared against textbook
+// per-prime negacyclic NTT loops and against a schoolbook product over the integers mod q.  Exit code 0 = all good.
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
 #include "../../tfhe_fbs_map_b200/csrc/ntt.cuh"
 #include "../../tfhe_fbs_map_b200/csrc/common.cuh"
 
+typedef unsigned __int128 u128;
 static u32 bitrev(u32 x, int bits) { u32 r = 0; for (int i = 0; i < bits; i++) { r = (r << 1) | (x & 1); x >>= 1; } return r; }
+static const u32 PR[2] = {FQ_P1, FQ_P2};
 
 template <int LOGN> struct Tables {
     static constexpr int N = 1 << LOGN;
-    std::vector<fq_tw> psi_rev, psi_inv_rev; u64 ninv;
+    std::vector<fq_tw> psi_rev, psi_inv_rev; u32 ninv[2];
+    std::vector<u32> w[2], wi[2];
     Tables() : psi_rev(N), psi_inv_rev(N) {
-        u64 psi = fq_pow_host(7, (FQ_Q - 1) / (2ULL * N)), psi_inv = fq_pow_host(psi, FQ_Q - 2);
-        for (int i = 0; i < N; i++) {
-            u32 r = bitrev(i, LOGN);
-            u64 w = fq_pow_host(psi, r), wi = fq_pow_host(psi_inv, r);
-            psi_rev[i] = fq_tw{w, fq_shoup_host(w)}; psi_inv_rev[i] = fq_tw{wi, fq_shoup_host(wi)};
+        for (int l = 0; l < 2; l++) {
+            const u32 p = PR[l];
+            const u64 psi = pow_mod_host(3, (p - 1) / (2ULL * N), p), psi_inv = pow_mod_host(psi, p - 2, p);
+            w[l].resize(N); wi[l].resize(N);
+            for (int i = 0; i < N; i++) { u32 r = bitrev(i, LOGN); w[l][i] = (u32)pow_mod_host(psi, r, p); wi[l][i] = (u32)pow_mod_host(psi_inv, r, p); }
+            ninv[l] = (u32)pow_mod_host(N, p - 2, p);
         }
-        ninv = fq_pow_host(N, FQ_Q - 2);
+        for (int i = 0; i < N; i++) {
+            psi_rev[i] = fq_tw{w[0][i], shoup32_host(w[0][i], FQ_P1), w[1][i], shoup32_host(w[1][i], FQ_P2)};
+            psi_inv_rev[i] = fq_tw{wi[0][i], shoup32_host(wi[0][i], FQ_P1), wi[1][i], shoup32_host(wi[1][i], FQ_P2)};
+        }
     }
 };
-static u64 canon(u64 x) { return fq_csub(fq_csub(fq_csub(x, FQ_2Q), FQ_2Q), FQ_Q); }
-template <int LOGN> void ref_fwd(const Tables<LOGN> &t, std::vector<u64> &a) {
-    int N = 1 << LOGN, tt = N;
-    for (int m = 1; m < N; m <<= 1) { tt >>= 1; for (int i = 0; i < m; i++) { u64 S = t.psi_rev[m + i].w;
-        for (int j = 2 * i * tt; j < 2 * i * tt + tt; j++) { u64 U = a[j], V = fq_mul(a[j + tt], S); a[j] = fq_add(U, V); a[j + tt] = fq_sub(U, V); } } }
+static u32 mulp(u32 a, u32 b, u32 p) { return (u32)((u64)a * b % p); }
+template <int LOGN> void ref_fwd(const Tables<LOGN> &t, std::vector<u32> &a, int l) {
+    int N = 1 << LOGN, tt = N; u32 p = PR[l];
+    for (int m = 1; m < N; m <<= 1) { tt >>= 1; for (int i = 0; i < m; i++) { u32 S = t.w[l][m + i];
+        for (int j = 2 * i * tt; j < 2 * i * tt + tt; j++) { u32 U = a[j], V = mulp(a[j + tt], S, p); a[j] = (U + V) % p; a[j + tt] = (U + p - V) % p; } } }
 }
-template <int LOGN> void ref_inv(const Tables<LOGN> &t, std::vector<u64> &a) {
-    int N = 1 << LOGN, tt = 1;
-    for (int m = N >> 1; m >= 1; m >>= 1) { for (int i = 0; i < m; i++) { u64 S = t.psi_inv_rev[m + i].w;
-        for (int j = 2 * i * tt; j < 2 * i * tt + tt; j++) { u64 U = a[j], V = a[j + tt]; a[j] = fq_add(U, V); a[j + tt] = fq_mul(fq_sub(U, V), S); } } tt <<= 1; }
+template <int LOGN> void ref_inv(const Tables<LOGN> &t, std::vector<u32> &a, int l) {
+    int N = 1 << LOGN, tt = 1; u32 p = PR[l];
+    for (int m = N >> 1; m >= 1; m >>= 1) { for (int i = 0; i < m; i++) { u32 S = t.wi[l][m + i];
+        for (int j = 2 * i * tt; j < 2 * i * tt + tt; j++) { u32 U = a[j], V = a[j + tt]; a[j] = (U + V) % p; a[j + tt] = mulp((U + p - V) % p, S, p); } } tt <<= 1; }
 }
 template <int LOGN, int PASS> void emu_fwd(const Tables<LOGN> &t, std::vector<u64> &arr) {
     using P = NttPlan<LOGN>;
     if constexpr (PASS < P::NPASS) {
         std::vector<u64> sm(P::N);
         for (int tau = 0; tau < P::T; tau++) {
-            u64 x[8];
-            for (int e = 0; e < 8; e++) x[e] = arr[P::idx(tau, e, P::fwd_lb(PASS))];
+            rns2 x[8];
+            for (int e = 0; e < 8; e++) x[e] = rns_unpack(arr[P::idx(tau, e, P::fwd_lb(PASS))]);
             ntt_fwd_pass<LOGN, PASS>(x, tau, t.psi_rev.data());
-            for (int e = 0; e < 8; e++) sm[P::swz(P::idx(tau, e, P::fwd_lb(PASS)))] = x[e];   // swizzled store
+            for (int e = 0; e < 8; e++) sm[P::swz(P::idx(tau, e, P::fwd_lb(PASS)))] = rns_pack(x[e]);   // swizzled store
         }
-        for (int i = 0; i < P::N; i++) arr[i] = sm[P::swz(i)];                               // swizzled load
+        for (int i = 0; i < P::N; i++) arr[i] = sm[P::swz(i)];                                         // swizzled load
         emu_fwd<LOGN, PASS + 1>(t, arr);
     }
 }
@@ -52,75 +59,113 @@ template <int LOGN, int PASS> void emu_inv(const Tables<LOGN> &t, std::vector<u6
     if constexpr (PASS < P::NPASS) {
         std::vector<u64> sm(P::N);
         for (int tau = 0; tau < P::T; tau++) {
-            u64 x[8];
-            for (int e = 0; e < 8; e++) x[e] = arr[P::idx(tau, e, P::inv_lb(PASS))];
+            rns2 x[8];
+            for (int e = 0; e < 8; e++) x[e] = rns_unpack(arr[P::idx(tau, e, P::inv_lb(PASS))]);
             ntt_inv_pass<LOGN, PASS>(x, tau, t.psi_inv_rev.data());
-            for (int e = 0; e < 8; e++) sm[P::swz(P::idx(tau, e, P::inv_lb(PASS)))] = x[e];
+            for (int e = 0; e < 8; e++) sm[P::swz(P::idx(tau, e, P::inv_lb(PASS)))] = rns_pack(x[e]);
         }
         for (int i = 0; i < P::N; i++) arr[i] = sm[P::swz(i)];
         emu_inv<LOGN, PASS + 1>(t, arr);
     }
 }
+static rns2 canon4(rns2 v) { v.a %= FQ_P1; v.b %= FQ_P2; return v; }
 template <int LOGN> int run() {
     using P = NttPlan<LOGN>; Tables<LOGN> t; int N = P::N, bad = 0;
-    // swizzle is a permutation
     { std::vector<int> seen(N, 0); for (int i = 0; i < N; i++) seen[P::swz(i)]++; for (int i = 0; i < N; i++) if (seen[i] != 1) bad++; }
-    // every pass layout is a permutation of [0,N)
     for (int p = 0; p < P::NPASS; p++) for (int lb : {P::fwd_lb(p), P::inv_lb(p)}) {
         std::vector<int> seen(N, 0); for (int tau = 0; tau < P::T; tau++) for (int e = 0; e < 8; e++) seen[P::idx(tau, e, lb)]++;
         for (int i = 0; i < N; i++) if (seen[i] != 1) bad++;
     }
-    std::vector<u64> a(N), b(N);
+    std::vector<u64> a(N), b(N);                         // integers mod q
     for (int i = 0; i < N; i++) { a[i] = fbs_rnd_uniform(42 + LOGN, 99, i); b[i] = fbs_rnd_uniform(43 + LOGN, 98, i); }
-    std::vector<u64> r = a, e = a;
-    ref_fwd<LOGN>(t, r); emu_fwd<LOGN, 0>(t, e);
-    for (int i = 0; i < N; i++) { e[i] = canon(e[i]); if (r[i] != e[i]) bad++; }
-    std::vector<u64> r2 = r, e2 = e;
-    ref_inv<LOGN>(t, r2); emu_inv<LOGN, 0>(t, e2);
-    for (int i = 0; i < N; i++) { if (e2[i] >= FQ_2Q) bad++; e2[i] = canon(e2[i]); if (r2[i] != e2[i]) bad++; if (fq_mul(e2[i], t.ninv) != a[i]) bad++; }
-    // lazy inputs: the forward transform must accept anything in [0, 4Q)
-    { std::vector<u64> lz = a; for (int i = 0; i < N; i++) lz[i] += (i % 4) * FQ_Q; emu_fwd<LOGN, 0>(t, lz);
-      for (int i = 0; i < N; i++) if (canon(lz[i]) != r[i]) bad++; }
-    // negacyclic product through the emulated transforms vs schoolbook (only for small N: O(N^2))
+    std::vector<u64> e(N);
+    for (int i = 0; i < N; i++) { rns2 v = rns_from_int(a[i]); v.a += (i % 4) * FQ_P1; v.b += ((i + 1) % 4) * FQ_P2; e[i] = rns_pack(v); }  // lazy inputs < 4p
+    emu_fwd<LOGN, 0>(t, e);
+    for (int l = 0; l < 2; l++) {
+        std::vector<u32> r(N); for (int i = 0; i < N; i++) r[i] = (u32)(a[i] % PR[l]);
+        ref_fwd<LOGN>(t, r, l);
+        for (int i = 0; i < N; i++) { rns2 v = rns_unpack(e[i]); u32 g = l ? v.b : v.a; if (g >= 4ULL * PR[l] || g % PR[l] != r[i]) bad++; }
+        std::vector<u32> r2 = r; ref_inv<LOGN>(t, r2, l);
+        for (int i = 0; i < N; i++) if (mulp(r2[i], t.ninv[l], PR[l]) != a[i] % PR[l]) bad++;
+    }
+    // inverse on canonical-ish (<2p) inputs
+    std::vector<u64> e2(N);
+    for (int i = 0; i < N; i++) { rns2 v = canon4(rns_unpack(e[i])); v.a += (i & 1) * FQ_P1; v.b += ((i >> 1) & 1) * FQ_P2; e2[i] = rns_pack(v); }
+    emu_inv<LOGN, 0>(t, e2);
+    for (int i = 0; i < N; i++) { rns2 v = rns_unpack(e2[i]); if (v.a >= 2 * FQ_P1 || v.b >= 2 * FQ_P2) bad++;
+        if (mulp(v.a % FQ_P1, t.ninv[0], FQ_P1) != a[i] % FQ_P1 || mulp(v.b % FQ_P2, t.ninv[1], FQ_P2) != a[i] % FQ_P2) bad++; }
+    // negacyclic product as in the blind-rotate kernel: key in Montgomery form with 1/N folded, REDC of a lazy product,
+    // inverse transform, CRT back to the integer -- against the schoolbook product mod q (small N only: O(N^2))
     if (N <= 512) {
-        std::vector<u64> fa = a, fb = b, prod(N), sb(N, 0);
+        std::vector<u64> fa(N), fb(N), prod(N), sb(N, 0);
+        for (int i = 0; i < N; i++) { fa[i] = rns_pack(rns_from_int(a[i])); fb[i] = rns_pack(rns_from_int(b[i])); }
         emu_fwd<LOGN, 0>(t, fa); emu_fwd<LOGN, 0>(t, fb);
-        // Montgomery path as in the blind-rotate kernel: fb -> (fb * 2^64 / N) canonical, product reduced lazily by REDC
+        const u32 m1 = mulp((u32)((1ULL << 32) % FQ_P1), t.ninv[0], FQ_P1), m2 = mulp((u32)((1ULL << 32) % FQ_P2), t.ninv[1], FQ_P2);
+        const u32 pin1 = 0xFFFE7FFFu, pin2 = 0xAFFF3FFFu;
         for (int i = 0; i < N; i++) {
-            u64 bm = fq_mul(canon(fb[i]), fq_mul(FQ_R, t.ninv)), lo, hi;
-            fq_mul_wide(fa[i], bm, lo, hi);
-            prod[i] = fq_csub(fq_redc(lo, hi), FQ_2Q);
-            if (prod[i] >= FQ_2Q) bad++;
+            rns2 x = rns_unpack(fa[i]), y = canon4(rns_unpack(fb[i]));
+            u32 k1 = mulp(y.a, m1, FQ_P1), k2 = mulp(y.b, m2, FQ_P2);
+            rns2 o; o.a = r32_fold(r32_redc((u64)x.a * k1, FQ_P1, pin1), 2 * FQ_P1); o.b = r32_fold(r32_redc((u64)x.b * k2, FQ_P2, pin2), 2 * FQ_P2);
+            if (o.a >= 2 * FQ_P1 || o.b >= 2 * FQ_P2) bad++;
+            prod[i] = rns_pack(o);
         }
         emu_inv<LOGN, 0>(t, prod);
-        for (int i = 0; i < N; i++) prod[i] = canon(prod[i]);
         for (int i = 0; i < N; i++) for (int j = 0; j < N; j++) { u64 pr = fq_mul(a[i], b[j]); int k = i + j;
             if (k < N) sb[k] = fq_add(sb[k], pr); else sb[k - N] = fq_sub(sb[k - N], pr); }
-        for (int i = 0; i < N; i++) if (sb[i] != prod[i]) bad++;
+        for (int i = 0; i < N; i++) { rns2 v = canon4(rns_unpack(prod[i])); if (rns_to_int(v) != sb[i]) bad++; }
     }
     printf("LOGN=%d bad=%d\n", LOGN, bad);
     return bad;
 }
 int main() {
     int bad = 0;
-    // field sanity: reduce128 against __int128
-    for (int i = 0; i < 200000; i++) {
+    if ((u128)FQ_P1 * FQ_P2 != FQ_Q) bad++;
+    if (((u64)FQ_P1 * FQ_P1INV_P2) % FQ_P2 != 1) bad++;
+    if ((u32)(FQ_P1 * 0xFFFE7FFFu) != 0xFFFFFFFFu || (u32)(FQ_P2 * 0xAFFF3FFFu) != 0xFFFFFFFFu) bad++;
+    if (FBS_K63 != (1ULL << 63) / FQ_P2) bad++;
+    if (FQ_RQ != (u64)((((u128)1) << 123) / FQ_Q)) bad++;
+    if (FQ_QN != (FQ_Q << 4) || FQ_QNV != (u64)((~(u128)0) / FQ_QN - (((u128)1) << 64))) bad++;
+    // the rounding must be unbiased: a bias of a fraction of a step accumulates over the n*N decompositions of a PBS
+    for (int bits : {12, 15, 23}) {
+        double sum = 0; const int M = 200000;
+        for (int i = 0; i < M; i++) {
+            u64 x = fbs_rnd_uniform(77, 78, i), y = fbs_round_top(x, bits);
+            double exact = (double)x / (double)FQ_Q * (double)(1ULL << bits), d = (double)y - exact;
+            if (d > (double)(1ULL << (bits - 1))) d -= (double)(1ULL << bits);       // wrap-around at the top
+            if (d < -(double)(1ULL << (bits - 1))) d += (double)(1ULL << bits);
+            sum += d;
+        }
+        if (sum / M > 0.005 || sum / M < -0.005) { printf("rounding bias %d bits: %f\n", bits, sum / M); bad++; }
+    }
+    for (int i = 0; i < 300000; i++) {
         u64 a = fbs_rnd_uniform(1, 2, i), b = fbs_rnd_uniform(3, 4, i);
-        if (i < 64) { u64 edge[8] = {0, 1, FQ_Q - 1, FQ_Q - 2, 0xFFFFFFFFULL, 0x100000000ULL, 0x3FFFFFFFFFFF0000ULL, 2}; a = edge[i % 8]; b = edge[i / 8]; }
-        u64 want = (u64)(((unsigned __int128)a * b) % FQ_Q);
+        if (i < 64) { u64 edge[8] = {0, 1, FQ_Q - 1, FQ_Q - 2, 0xFFFFFFFFULL, 0x100000000ULL, FQ_P1, FQ_P2}; a = edge[i % 8]; b = edge[i / 8]; }
+        u64 want = (u64)(((u128)a * b) % FQ_Q);
         if (fq_mul(a, b) != want) bad++;
-        if (fq_add(a, b) != (u64)(((unsigned __int128)a + b) % FQ_Q)) bad++;
-        if (fq_sub(a, b) != (u64)(((unsigned __int128)a + FQ_Q - b) % FQ_Q)) bad++;
-        // Shoup: any 64-bit y, result in [0, 2Q) and congruent
-        u64 y = fbs_rnd64(5, 6, i), sh = fq_mul_shoup(y, a, fq_shoup_host(a));
-        if (sh >= FQ_2Q || sh % FQ_Q != (u64)(((unsigned __int128)a * (y % FQ_Q)) % FQ_Q)) bad++;
-        // Montgomery reduction of a lazy product
-        u64 lz = a + (i % 4) * FQ_Q, lo, hi; fq_mul_wide(lz, b, lo, hi);
-        u64 rd = fq_redc(lo, hi);
-        if (rd >= 3 * FQ_Q || ((unsigned __int128)(rd % FQ_Q) * FQ_R) % FQ_Q != want) bad++;
-        // wide accumulators as in the key switch (hi < 2^22)
+        if (fq_add(a, b) != (u64)(((u128)a + b) % FQ_Q)) bad++;
+        if (fq_sub(a, b) != (u64)(((u128)a + FQ_Q - b) % FQ_Q)) bad++;
+        // wide accumulators as in the key switch (hi < 2^22) and arbitrary hi < q
         u64 lo2 = fbs_rnd64(7, 8, i), hi2 = fbs_rnd64(9, 10, i) >> 42;
-        if (fq_reduce128(lo2, hi2) != (u64)((((unsigned __int128)hi2 << 64) | lo2) % FQ_Q)) bad++;
+        if (fq_reduce128(lo2, hi2) != (u64)((((u128)hi2 << 64) | lo2) % FQ_Q)) bad++;
+        u64 hi3 = fbs_rnd_uniform(11, 12, i);
+        if (fq_reduce128(lo2, hi3) != (u64)((((u128)hi3 << 64) | lo2) % FQ_Q)) bad++;
+        // RNS round trip and CRT
+        rns2 r = rns_from_int(a);
+        if (rns_to_int(r) != a) bad++;
+        if (rns_crt_hi(r) != (u32)(a / FQ_P1)) bad++;
+        rns2 s = rns_sub(rns_from_int(a), rns_from_int(b));
+        if (rns_to_int(s) != fq_sub(a, b)) bad++;
+        // 32-bit Shoup: any y, result in [0,2p) and congruent
+        u32 y = (u32)fbs_rnd64(5, 6, i), w = (u32)(a % FQ_P2), sh = r32_mul_shoup(y, w, shoup32_host(w, FQ_P2), FQ_P2);
+        if (sh >= 2 * FQ_P2 || sh % FQ_P2 != (u32)((u64)w * (y % FQ_P2) % FQ_P2)) bad++;
+        // rounding: both definitions stay within one unit of the exact quotient
+        for (int bits : {12, 15, 23, 24, 30}) {
+            u64 yq = fbs_round_top(a, bits);
+            u128 exact2 = ((u128)a << (bits + 1)) / FQ_Q;              // floor(2 * a * 2^bits / q)
+            u64 nearest = (u64)((exact2 + 1) >> 1) & ((1ULL << bits) - 1);
+            u64 d = (yq - nearest) & ((1ULL << bits) - 1);
+            if (!(d == 0 || d == 1 || d == ((1ULL << bits) - 1))) bad++;
+        }
     }
     printf("field bad=%d\n", bad);
     bad += run<8>(); bad += run<9>(); bad += run<10>(); bad += run<11>(); bad += run<12>();

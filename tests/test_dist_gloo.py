@@ -14,7 +14,7 @@ from tfhe_fbs_map_b200 import levelize, params
 from tfhe_fbs_map_b200.dist import instance_shard, level_node_range, run_node_sharded
 from tfhe_fbs_map_b200.formats import read_lbf
 
-Q = 0x3FFFFFFFFFFF0001
+Q = 0x3FFE8001 * 0x3FFF4001
 
 
 def test_partition_helpers():

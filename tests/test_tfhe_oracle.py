@@ -26,7 +26,7 @@ def test_field_and_prng_primitives():
         assert L.ref_mulmod(a, b) == (a * b) % P
     assert L.ref_mulmod(P - 1, P - 1) == 1
     assert L.ref_delta(17) == (P + 17) // 34
-    assert L.ref_gadget(23, 0) == (P + (1 << 22)) >> 23 and P == 2 ** 62 - 2 ** 16 + 1
+    assert L.ref_gadget(23, 0) == (P + (1 << 22)) >> 23 and P == 0x3FFE8001 * 0x3FFF4001
     # noise: zero mean, std == scale within 5 %
     sc = 1 << 30
     xs = np.array([L.ref_noise(7, 8, i, sc) for i in range(20000)], dtype=np.float64)
@@ -46,7 +46,7 @@ def test_decomposition_reconstructs():
             assert np.all(d >= -(1 << (beta - 1))) and np.all(d < (1 << (beta - 1)))
             rec = sum(int(dj) * gj for dj, gj in zip(d, g)) % P
             err = min((rec - x) % P, (x - rec) % P)
-            assert err <= (P >> (beta * l)) // 2 + (l << beta) + 2 ** 17
+            assert err <= (P >> (beta * l)) // 2 + (l << beta) + 2 ** 32
 
 
 def test_ntt_product_equals_schoolbook(ref):

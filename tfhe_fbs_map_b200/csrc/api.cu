@@ -52,11 +52,11 @@ static const BRVariant g_br_variants[] = {
     BRV(8, 1, 2, true, 2), BRV(8, 2, 1, true, 2), BRV(9, 1, 1, true, 2), BRV(10, 1, 3, true, 1),   // toy sets (tests)
 };
 
-typedef void (*ntt_launch_fn)(const u64 *, u64 *, int, const fq_tw *, const fq_tw *, u64, long long, cudaStream_t);
+typedef void (*ntt_launch_fn)(const u64 *, u64 *, int, const fq_tw *, const fq_tw *, u32, u32, long long, cudaStream_t);
 template <int LOGN>
-static void ntt_launch(const u64 *in, u64 *out, int mode, const fq_tw *pr, const fq_tw *pir, u64 scale, long long count, cudaStream_t st)
+static void ntt_launch(const u64 *in, u64 *out, int mode, const fq_tw *pr, const fq_tw *pir, u32 s1, u32 s2, long long count, cudaStream_t st)
 {
-    k_ntt<LOGN><<<(unsigned)count, NttPlan<LOGN>::T, 0, st>>>(in, out, mode, pr, pir, scale);
+    k_ntt<LOGN><<<(unsigned)count, NttPlan<LOGN>::T, 0, st>>>(in, out, mode, pr, pir, s1, s2);
 }
 static ntt_launch_fn ntt_for(int logN)
 {
@@ -74,7 +74,7 @@ struct fbs_ctx {
     u64 *d_ksk = nullptr, *d_colsum = nullptr, *d_bsk = nullptr, *d_bsk_coef = nullptr;
     fq_tw *d_psi_rev = nullptr, *d_psi_inv_rev = nullptr;
     u64 *d_gad_bsk = nullptr, *d_gad_ks = nullptr;
-    u64 ninv = 0, mont_ninv = 0;
+    u32 ninv[2] = {0, 0}, mont_ninv[2] = {0, 0};     // 1/N and 2^32/N per prime
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[8] = {};
     std::vector<cudaEvent_t> ev_pool;          // 4 per level, for per-phase timing inside fbs_run / fbs_eval_bits
@@ -124,7 +124,7 @@ extern "C" int fbs_ctx_create(const fbs_params *params, int device, uint64_t see
     if ((1 << logN) != P.N) return fail(FBS_ERR_ARG, "N must be a power of two");
     if (P.ks_beta < 1 || P.ks_beta > 8 || P.ks_l < 1 || P.ks_l > 8 || P.ks_beta * P.ks_l > 40)
         return fail(FBS_ERR_ARG, "unsupported key-switch decomposition (need 1<=ks_beta<=8, 1<=ks_l<=8)");
-    if (P.bsk_beta * P.bsk_l > 48 || P.bsk_beta < 2) return fail(FBS_ERR_ARG, "unsupported blind-rotate decomposition");
+    if (P.bsk_beta * P.bsk_l > 48 || P.bsk_beta < 2 || P.bsk_beta > 28) return fail(FBS_ERR_ARG, "unsupported blind-rotate decomposition");
     if (P.n < 1 || P.n > 4095) return fail(FBS_ERR_ARG, "n out of range");
     const BRVariant *br = nullptr, *br1 = nullptr;
     for (const BRVariant &v : g_br_variants) if (v.logN == logN && v.k == P.k && v.l == P.bsk_l) {
@@ -152,14 +152,20 @@ extern "C" int fbs_ctx_create(const fbs_params *params, int device, uint64_t see
     // twiddles psi^bitrev(i): 7 generates Z_P^*
     const int N = P.N;
     std::vector<fq_tw> pr(N), pir(N);
-    const u64 psi = fq_pow_host(7, (FQ_Q - 1) / (2ULL * N)), psi_inv = fq_pow_host(psi, FQ_Q - 2);
-    for (int i = 0; i < N; i++) {
-        u32 r = bitrev32((u32)i, logN);
-        const u64 w = fq_pow_host(psi, r), wi = fq_pow_host(psi_inv, r);
-        pr[i] = fq_tw{w, fq_shoup_host(w)}; pir[i] = fq_tw{wi, fq_shoup_host(wi)};
+    const u32 primes[2] = {FQ_P1, FQ_P2};
+    std::vector<u32> w[2], wi[2];
+    for (int l = 0; l < 2; l++) {          // 3 is a quadratic non-residue mod both primes: 3^((p-1)/2N) has order exactly 2N
+        const u32 p = primes[l];
+        const u64 psi = pow_mod_host(3, (p - 1) / (2ULL * N), p), psi_inv = pow_mod_host(psi, p - 2, p);
+        w[l].resize(N); wi[l].resize(N);
+        for (int i = 0; i < N; i++) { u32 r = bitrev32((u32)i, logN); w[l][i] = (u32)pow_mod_host(psi, r, p); wi[l][i] = (u32)pow_mod_host(psi_inv, r, p); }
+        c->ninv[l] = (u32)pow_mod_host((u64)N, p - 2, p);
+        c->mont_ninv[l] = (u32)((u64)((1ULL << 32) % p) * c->ninv[l] % p);
     }
-    c->ninv = fq_pow_host((u64)N, FQ_Q - 2);
-    c->mont_ninv = fq_mul(FQ_R, c->ninv);                 // 2^64 / N mod Q
+    for (int i = 0; i < N; i++) {
+        pr[i] = fq_tw{w[0][i], shoup32_host(w[0][i], FQ_P1), w[1][i], shoup32_host(w[1][i], FQ_P2)};
+        pir[i] = fq_tw{wi[0][i], shoup32_host(wi[0][i], FQ_P1), wi[1][i], shoup32_host(wi[1][i], FQ_P2)};
+    }
     CKR(dev_alloc(&c->d_psi_rev, N)); CKR(dev_alloc(&c->d_psi_inv_rev, N));
     CK(cudaMemcpy(c->d_psi_rev, pr.data(), sizeof(fq_tw) * N, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(c->d_psi_inv_rev, pir.data(), sizeof(fq_tw) * N, cudaMemcpyHostToDevice));
@@ -193,7 +199,7 @@ extern "C" int fbs_keygen(fbs_ctx *c)
     k_bsk_body<<<n * rows, 256, (size_t)N * 9, st>>>(c->d_bsk_coef, k, N, l, c->d_s_lwe, c->d_s_big, c->d_gad_bsk);
     ntt_launch_fn nf = ntt_for(c->logN);
     if (!nf) return fail(FBS_ERR_ARG, "no NTT kernel for this N");
-    nf(c->d_bsk_coef, c->d_bsk, 2, c->d_psi_rev, c->d_psi_inv_rev, c->mont_ninv, (long long)(total / N), st);
+    nf(c->d_bsk_coef, c->d_bsk, 2, c->d_psi_rev, c->d_psi_inv_rev, c->mont_ninv[0], c->mont_ninv[1], (long long)(total / N), st);
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(st));
     // the coefficient-domain copy is only a parity tap: keep it for toy sizes, drop it for real key sizes
@@ -610,7 +616,7 @@ extern "C" int fbs_debug_ntt(fbs_ctx *c, uint64_t *polys, int64_t count, int32_t
     u64 *d_a = nullptr, *d_b = nullptr; const size_t words = (size_t)count * c->P.N;
     CKR(dev_alloc(&d_a, words)); CKR(dev_alloc(&d_b, words));
     CK(cudaMemcpy(d_a, polys, words * 8, cudaMemcpyHostToDevice));
-    nf(d_a, d_b, inverse ? 1 : 0, c->d_psi_rev, c->d_psi_inv_rev, c->ninv, count, c->stream);
+    nf(d_a, d_b, inverse ? 1 : 0, c->d_psi_rev, c->d_psi_inv_rev, c->ninv[0], c->ninv[1], count, c->stream);
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(c->stream));
     CK(cudaMemcpy(polys, d_b, words * 8, cudaMemcpyDeviceToHost));

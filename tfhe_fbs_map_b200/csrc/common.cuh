@@ -17,10 +17,12 @@ FQ_HD u64 fbs_rnd64(u64 seed, u64 dom, u64 idx)
 }
 FQ_HD u64 fbs_rnd_uniform(u64 seed, u64 dom, u64 idx)
 {
-    u64 u = fbs_rnd64(seed, dom, idx) >> 2;          // 62 bits; Q = 2^62 - 2^16 + 1, bias 2^-46
-    return u >= FQ_Q ? u - FQ_Q : u;
+    // 60 random bits; the 0.02 % of draws that land in [q, 2^60) are replaced by a second, scaled draw
+    u64 u = fbs_rnd64(seed, dom, idx) >> 4;
+    if (u >= FQ_Q) u = fq_mulhi(fbs_rnd64(seed, dom + 64, idx), FQ_Q);
+    return u;
 }
-// Irwin-Hall(12) noise with standard deviation `scale` (units of 1/Q): integer-only so that host, device
+// Irwin-Hall(12) noise with standard deviation `scale` (units of 1/q): integer-only so that host, device
 // and oracle produce identical samples.
 FQ_HD u64 fbs_rnd_noise(u64 seed, u64 dom, u64 idx, u64 scale)
 {
@@ -57,12 +59,23 @@ static inline u64 fbs_gadget_host(int beta, int j)                          // r
     return (u64)(((unsigned __int128)FQ_Q + B / 2) / B);
 }
 
-// closest multiple of Q/2^bits as the bits-wide integer y = round(x * 2^bits / 2^62) (wraps: y == 2^bits -> 0).
-// Q differs from 2^62 by 2^-46 relative, far below the rounding step for every bits <= 48.
+// y = round(x * 2^bits / q) mod 2^bits for x in [0, q)  (the rounding used by gadget decomposition and modulus switch).
+// Write x = r1 + p1 * t (r1 = x mod p1, t = floor(x / p1) in [0, p2)): x/q = t/p2 + r1/q.  Up to 24 bits
+//     y = (t * K63 + 8 * r1 + 2^(s-1)) >> s,   s = 63 - bits,  K63 = floor(2^63 / p2),  8 ~ 2^63 / q
+// which needs only the CRT digit t, no 60-bit reconstruction, inside the blind-rotation loop; the truncation errors
+// are below 2^-9 of a rounding step, so the rounding is unbiased (a biased rounding accumulates over the n*N
+// decompositions of a blind rotation).  Beyond 24 bits the full integer is scaled by a 64-bit reciprocal.
+#define FBS_K63 0x20006000AULL        /* floor(2^63 / p2) */
+FQ_HD u64 fbs_round_top_t(u32 t, u32 r1, int bits)
+{
+    const int s = 63 - bits;
+    return (((u64)t * FBS_K63 + ((u64)r1 << 3) + (1ULL << (s - 1))) >> s) & ((1ULL << bits) - 1);
+}
 FQ_HD u64 fbs_round_top(u64 x, int bits)
 {
-    const u64 t = x + (1ULL << (61 - bits));
-    return (t >> (62 - bits)) & ((1ULL << bits) - 1);
+    if (bits <= 24) { const u64 t = x / FQ_P1; return fbs_round_top_t((u32)t, (u32)(x - t * FQ_P1), bits); }
+    const u64 s = fq_mulhi(x, FQ_RQ);                     // x * 2^59 / q
+    return ((s + (1ULL << (58 - bits))) >> (59 - bits)) & ((1ULL << bits) - 1);
 }
 FQ_HD u32 fbs_modswitch(u64 x, int log2_2N) { return (u32)fbs_round_top(x, log2_2N); }
 

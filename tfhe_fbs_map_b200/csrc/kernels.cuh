@@ -140,12 +140,13 @@ __global__ void __launch_bounds__(256) k_bsk_body(u64 *bsk, int k, int N, int l,
 // ------------------------------------------------------------------------------------------------------
 // K5: stand-alone NTT.  mode 0: forward (natural in, bit-reversed out, array order as oracle/tfhe_ref.c)
 //                       mode 1: inverse incl. 1/N (for tests)
-//                       mode 2: BSK preprocessing: forward, times 2^64/N (Montgomery form with the inverse
-//                               transform's 1/N folded in), stored SWIZZLED for the blind-rotate kernel
+//                       mode 2: BSK preprocessing: forward, residues times 2^32/N (Montgomery form with the inverse
+//                               transform's 1/N folded in), packed (mod p1 | mod p2 << 32), stored SWIZZLED for the
+//                               blind-rotate kernel
 // ------------------------------------------------------------------------------------------------------
 template <int LOGN>
 __global__ void __launch_bounds__(NttPlan<LOGN>::T) k_ntt(const u64 *__restrict__ in, u64 *__restrict__ out, int mode,
-                                                         const fq_tw *__restrict__ psi_rev, const fq_tw *__restrict__ psi_inv_rev, u64 scale)
+                                                         const fq_tw *__restrict__ psi_rev, const fq_tw *__restrict__ psi_inv_rev, u32 scale1, u32 scale2)
 {
     using P = NttPlan<LOGN>;
     __shared__ u64 bufA[P::N];
@@ -153,24 +154,36 @@ __global__ void __launch_bounds__(NttPlan<LOGN>::T) k_ntt(const u64 *__restrict_
     const int tau = threadIdx.x;
     const u64 *src = in + (size_t)blockIdx.x * P::N;
     u64 *dst = out + (size_t)blockIdx.x * P::N;
-    u64 x[8];
+    rns2 x[8];
     auto sync = [] { __syncthreads(); };
-    if (mode == 1) {                                   // inverse, scale = 1/N
+    if (mode == 1) {                                   // inverse, scale = 1/N per prime; integers in, integers out
 #pragma unroll
-        for (int e = 0; e < 8; e++) x[e] = src[P::idx(tau, e, P::inv_lb(0))];
+        for (int e = 0; e < 8; e++) x[e] = rns_from_int(src[P::idx(tau, e, P::inv_lb(0))]);
         ntt_inv_from<LOGN, 0>(x, tau, bufA, bufB, psi_inv_rev, sync, sync);
 #pragma unroll
-        for (int e = 0; e < 8; e++) dst[P::idx(tau, e, P::inv_lb(P::NPASS - 1))] = fq_mul(fq_csub(x[e], FQ_Q), scale);
+        for (int e = 0; e < 8; e++) {
+            rns2 v;
+            v.a = (u32)((u64)r32_csub(x[e].a, FQ_P1) * scale1 % FQ_P1);
+            v.b = (u32)((u64)r32_csub(x[e].b, FQ_P2) * scale2 % FQ_P2);
+            dst[P::idx(tau, e, P::inv_lb(P::NPASS - 1))] = rns_to_int(v);
+        }
     } else {
 #pragma unroll
-        for (int e = 0; e < 8; e++) x[e] = src[P::idx(tau, e, P::fwd_lb(0))];
+        for (int e = 0; e < 8; e++) x[e] = rns_from_int(src[P::idx(tau, e, P::fwd_lb(0))]);
         ntt_forward<LOGN>(x, tau, bufA, bufB, psi_rev, sync);
 #pragma unroll
         for (int e = 0; e < 8; e++) {
             const int id = P::idx(tau, e, P::fwd_lb(P::NPASS - 1));
-            const u64 v = fq_csub(fq_csub(fq_csub(x[e], FQ_2Q), FQ_2Q), FQ_Q);   // lazy (< 2^64 - 2^17) -> canonical
-            if (mode == 0) dst[id] = v;
-            else dst[P::swz(id)] = fq_mul(v, scale);                     // mode 2: scale = 2^64 / N (Montgomery form, 1/N folded)
+            rns2 v;                                                      // lazy [0,4p) -> canonical
+            v.a = r32_csub(r32_fold(x[e].a, 2 * FQ_P1), FQ_P1);
+            v.b = r32_csub(r32_fold(x[e].b, 2 * FQ_P2), FQ_P2);
+            if (mode == 0) {
+                dst[id] = rns_to_int(v);                                 // integer spectrum, as the oracle computes it
+            } else {                                                     // mode 2: residues * 2^32/N, packed, swizzled
+                v.a = (u32)((u64)v.a * scale1 % FQ_P1);
+                v.b = (u32)((u64)v.b * scale2 % FQ_P2);
+                dst[P::swz(id)] = rns_pack(v);
+            }
         }
     }
 }
@@ -453,6 +466,7 @@ __global__ void __launch_bounds__(PB * (K + 1) * (1 << LOGN) / 8 * BR_LB_MULT, 1
         for (int q = 0; q < G * L * G; q++) tma_load_1d(BS + (size_t)q * N, a.bsk + (size_t)q * N, N * 8, mbar);
     }
     // ---- accumulator init: ACC = (0, .., 0, X^{-b~} * TV) ; TV[j] = F(round(j*p/N)), F(x) = tv[x]*Delta - s*Delta/2
+    // The accumulator lives in shared memory as packed residue pairs (mod p1 | mod p2 << 32), canonical.
     u64 *acc = ACC + (size_t)g * N;
     {
         const u64 delta = fbs_delta(p), off = fq_mul((u64)mode, delta >> 1);
@@ -472,7 +486,7 @@ __global__ void __launch_bounds__(PB * (K + 1) * (1 << LOGN) / 8 * BR_LB_MULT, 1
                 const u64 F = fq_sub(fq_mul(tvx, delta), off);
                 val = neg ? fq_neg(F) : F;
             }
-            acc[j] = val;
+            acc[j] = rns_pack(rns_from_int(val));
         }
     }
     __syncthreads();
@@ -481,23 +495,27 @@ __global__ void __launch_bounds__(PB * (K + 1) * (1 << LOGN) / 8 * BR_LB_MULT, 1
     auto gsync = [bar_g] { bar_sync_named(bar_g, T); };
     auto psync = [bar_p] { bar_sync_named(bar_p, C::PT); };
     u64 *sg = S + (size_t)g * N;
-    const int beta = a.beta;
+    const int beta = a.beta, bits = beta * L;
 
     for (int i = 0; i < n; i++) {
         const int ai = s_ms[i];
-        // ---- rotate, subtract, decompose: digits of (X^{ai} ACC_g - ACC_g) in the first forward layout
-        u64 dg[L][8];
+        // ---- rotate, subtract, decompose: digits of (X^{ai} ACC_g - ACC_g) in the first forward layout.
+        // Only the high mixed-radix digit t = floor(x / p1) of the difference is needed for the rounding (<= 24 bits).
+        rns2 dg[L][8];
 #pragma unroll
         for (int e = 0; e < 8; e++) {
             const int j = tau + e * T;
             int src = j - ai;
             if (src < 0) src += 2 * N;
-            const u64 rot = (src < N) ? acc[src] : fq_neg(acc[src - N]);
-            const u64 diff = fq_sub(rot, acc[j]);
+            rns2 rot = rns_unpack(acc[src < N ? src : src - N]);
+            if (src >= N) rot = rns_neg(rot);
+            const rns2 diff = rns_sub(rot, rns_unpack(acc[j]));
+            const u32 t = rns_crt_hi(diff);
+            const u64 y = (bits <= 24) ? fbs_round_top_t(t, diff.a, bits) : fbs_round_top((u64)diff.a + (u64)FQ_P1 * t, bits);
             int d[L];
-            fbs_balanced_digits<L>(fbs_round_top(diff, beta * L), beta, d);
+            fbs_balanced_digits<L>(y, beta, d);
 #pragma unroll
-            for (int jj = 0; jj < L; jj++) dg[jj][e] = fq_from_i64(d[jj]);
+            for (int jj = 0; jj < L; jj++) dg[jj][e] = rns_from_small(d[jj]);
         }
         // ---- forward NTTs through the group's scratch polynomial; spectra to DH (swizzled, layout lb = 0)
 #pragma unroll
@@ -506,33 +524,35 @@ __global__ void __launch_bounds__(PB * (K + 1) * (1 << LOGN) / 8 * BR_LB_MULT, 1
             u64 *dh = DH + (size_t)(g * L + jj) * N;
             if (L == 1 && P::NPASS > 1) gsync();            // DH aliases S: the last transpose's readers are done
 #pragma unroll
-            for (int e = 0; e < 8; e++) dh[P::swz(P::idx(tau, e, 0))] = dg[jj][e];
+            for (int e = 0; e < 8; e++) dh[P::swz(P::idx(tau, e, 0))] = rns_pack(dg[jj][e]);
         }
         psync();
-        // ---- pointwise: out_g = sum_r DH[r] * BSK[r][g].  DH is lazy (< 2^64), the key is canonical and in Montgomery
-        // form, so a PAIR of 128-bit products (< 2^127) is reduced by one REDC to < 3Q, then folded to < 2Q.
+        // ---- pointwise: out_g = sum_r DH[r] * BSK[r][g], per prime.  DH is lazy (< 4p), the key is canonical and in
+        // Montgomery form: a PAIR of 64-bit products (< 8p^2 < 2^63) is reduced by one REDC to < 3p, then folded to < 2p.
         if (BSK_SMEM) mbar_wait(mbar, (u32)(i & 1));
-        u64 x[8];
+        rns2 x[8];
         {
             const u64 *brow = BSK_SMEM ? BS : a.bsk + (size_t)i * C::row_w;
 #pragma unroll
             for (int e = 0; e < 8; e++) {
                 const int id = P::swz(P::idx(tau, e, 0));
-                u64 s = 0;
+                rns2 s;
+                s.a = 0; s.b = 0;
 #pragma unroll
                 for (int r = 0; r < G * L; r += 2) {
-                    u64 lo, hi;
-                    fq_mul_wide(DH[(size_t)r * N + id], brow[((size_t)r * G + g) * N + id], lo, hi);
+                    const rns2 d0 = rns_unpack(DH[(size_t)r * N + id]), k0 = rns_unpack(brow[((size_t)r * G + g) * N + id]);
+                    u64 pa = (u64)d0.a * k0.a, pb2 = (u64)d0.b * k0.b;
                     if (r + 1 < G * L) {
-                        u64 lo2, hi2;
-                        fq_mul_wide(DH[(size_t)(r + 1) * N + id], brow[((size_t)(r + 1) * G + g) * N + id], lo2, hi2);
-                        lo += lo2;
-                        hi += hi2 + (lo < lo2 ? 1 : 0);
+                        const rns2 d1 = rns_unpack(DH[(size_t)(r + 1) * N + id]), k1 = rns_unpack(brow[((size_t)(r + 1) * G + g) * N + id]);
+                        pa += (u64)d1.a * k1.a;
+                        pb2 += (u64)d1.b * k1.b;
                     }
-                    const u64 t = fq_csub(fq_redc(lo, hi), FQ_2Q);
-                    s = (r == 0) ? t : fq_csub(s + t, FQ_2Q);
+                    const u32 ta = r32_fold(r32_redc(pa, FQ_P1, FQ_P1_INVNEG), 2 * FQ_P1);
+                    const u32 tb = r32_fold(r32_redc(pb2, FQ_P2, FQ_P2_INVNEG), 2 * FQ_P2);
+                    s.a = (r == 0) ? ta : r32_fold(s.a + ta, 2 * FQ_P1);
+                    s.b = (r == 0) ? tb : r32_fold(s.b + tb, 2 * FQ_P2);
                 }
-                x[e] = s;                                  // < 2Q: what the inverse butterflies expect
+                x[e] = s;                                  // < 2p per prime: what the inverse butterflies expect
             }
         }
         // ---- inverse NTT.  After its first register pass a CTA-wide barrier guarantees that nobody reads DH / BS of
@@ -551,23 +571,27 @@ __global__ void __launch_bounds__(PB * (K + 1) * (1 << LOGN) / 8 * BR_LB_MULT, 1
 #pragma unroll
         for (int e = 0; e < 8; e++) {
             const int j = P::idx(tau, e, P::inv_lb(P::NPASS - 1));
-            acc[j] = fq_add(acc[j], fq_csub(x[e], FQ_Q));
+            rns2 v;
+            v.a = r32_csub(x[e].a, FQ_P1);
+            v.b = r32_csub(x[e].b, FQ_P2);
+            acc[j] = rns_pack(rns_add(rns_unpack(acc[j]), v));
         }
         gsync();                                         // ACC_g is only read by group g (next step's rotation)
     }
-    // ---- K3: sample extraction of coefficient 0 (+ table-mode offset s*Delta/2 on the body)
+    // ---- K3: sample extraction of coefficient 0 (+ table-mode offset s*Delta/2 on the body); CRT back to integers
     psync();
     if (live) {
         const size_t CT = (size_t)K * N + 1;
         u64 *out = a.wires + ((size_t)a.bs_slot[node] * a.B + inst) * CT;
         for (int w = ptid; w < K * N; w += C::PT) {
             const int u = w / N, j = w % N;
-            out[w] = (j == 0) ? ACC[(size_t)u * N] : fq_neg(ACC[(size_t)u * N + N - j]);
+            const rns2 v = rns_unpack(ACC[(size_t)u * N + (j == 0 ? 0 : N - j)]);
+            out[w] = rns_to_int(j == 0 ? v : rns_neg(v));
         }
-        if (ptid == 0) out[(size_t)K * N] = fq_add(ACC[(size_t)K * N], fq_mul((u64)mode, fbs_delta(p) >> 1));
+        if (ptid == 0) out[(size_t)K * N] = fq_add(rns_to_int(rns_unpack(ACC[(size_t)K * N])), fq_mul((u64)mode, fbs_delta(p) >> 1));
         if (a.tap_acc) {
             u64 *t = a.tap_acc + (size_t)job * G * N;
-            for (int w = ptid; w < G * N; w += C::PT) t[w] = ACC[w];
+            for (int w = ptid; w < G * N; w += C::PT) t[w] = rns_to_int(rns_unpack(ACC[w]));
         }
     }
 }

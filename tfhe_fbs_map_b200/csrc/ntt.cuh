@@ -1,11 +1,12 @@
-// ntt.cuh -- negacyclic NTT over Z_P[X]/(X^N+1) for one polynomial held by N/8 threads, 8 coefficients each.
+// ntt.cuh -- negacyclic NTT over Z_q[X]/(X^N+1), q = p1*p2, in RNS: one polynomial held by N/8 threads, 8 coefficients
+// (= 8 residue pairs) each.
 //
 // Structure: radix-8 register passes (3 butterfly stages on the 8 values a thread
 // holds) separated by shared-memory transposes.  Forward = Cooley-Tukey, natural order in, bit-reversed
 // out, negacyclic twist merged into the twiddles psi_rev[m+i] = psi^bitrev(m+i); inverse = Gentleman-
 // Sande, bit-reversed in, natural out, WITHOUT the 1/N scale (it is folded into the bootstrapping key).
-// Butterflies are Harvey's lazy ones with Shoup twiddles (w, ws = floor(w*2^64/Q)):
-//   forward: inputs and outputs in [0, 2^64 - 2^17] (a little above 4Q);   inverse: inputs and outputs in [0,2Q).
+// Butterflies are Harvey's lazy ones with Shoup twiddles (w, ws = floor(w*2^32/p)), independently per prime:
+//   forward: inputs and outputs in [0,4p);   inverse: inputs and outputs in [0,2p).
 //
 // A pass is described by `lb`, the lowest of its three in-thread index bits:
 //     idx(tau, e) = ((tau >> lb) << (lb+3)) | (e << lb) | (tau & ((1<<lb)-1)),   e = 0..7
@@ -41,19 +42,19 @@ struct NttPlan {
 };
 
 // ---- one forward pass on registers -------------------------------------------------------------------
-struct alignas(16) fq_tw { u64 w, ws; };      // twiddle and its Shoup companion, one 128-bit load
+struct alignas(16) fq_tw { u32 w1, ws1, w2, ws2; };      // twiddle + Shoup companion for both primes: one 128-bit load
 FQ_HD fq_tw fq_tw_load(const fq_tw *p)
 {
 #if defined(__CUDA_ARCH__)
-    const ulonglong2 v = __ldg(reinterpret_cast<const ulonglong2 *>(p));
-    return fq_tw{v.x, v.y};
+    const uint4 v = __ldg(reinterpret_cast<const uint4 *>(p));
+    return fq_tw{v.x, v.y, v.z, v.w};
 #else
     return *p;
 #endif
 }
 
 template <int LOGN, int PASS>
-FQ_HD void ntt_fwd_pass(u64 (&x)[8], int tau, const fq_tw *__restrict__ psi_rev)
+FQ_HD void ntt_fwd_pass(rns2 (&x)[8], int tau, const fq_tw *__restrict__ psi_rev)
 {
     using P = NttPlan<LOGN>;
     constexpr int hi = P::fwd_hi(PASS), lb = P::fwd_lb(PASS);
@@ -67,17 +68,16 @@ FQ_HD void ntt_fwd_pass(u64 (&x)[8], int tau, const fq_tw *__restrict__ psi_rev)
             if (e0 & (1 << q)) continue;
             const int e1 = e0 | (1 << q);
             const fq_tw w = fq_tw_load(psi_rev + m + ((th << (2 - q)) | (e0 >> (q + 1))));
-            // inputs < 2^64 - 2^17: subtracting 2Q when the top bit is set (one test on the high word) brings u below
-            // 2^63; with v < 2Q both outputs stay below 2^63 + 2Q = 2^64 - 2^17 + 2, so the invariant is closed.
-            const u64 u = fq_lazy_fold(x[e0]), v = fq_mul_shoup(x[e1], w.w, w.ws);
-            x[e0] = u + v;
-            x[e1] = u - v + FQ_2Q;
+            const u32 ua = r32_fold(x[e0].a, 2 * FQ_P1), va = r32_mul_shoup(x[e1].a, w.w1, w.ws1, FQ_P1);
+            const u32 ub = r32_fold(x[e0].b, 2 * FQ_P2), vb = r32_mul_shoup(x[e1].b, w.w2, w.ws2, FQ_P2);
+            x[e0].a = ua + va; x[e1].a = ua - va + 2 * FQ_P1;
+            x[e0].b = ub + vb; x[e1].b = ub - vb + 2 * FQ_P2;
         }
     }
 }
 // ---- one inverse pass on registers ---------------------------------------------------------------------
 template <int LOGN, int PASS>
-FQ_HD void ntt_inv_pass(u64 (&x)[8], int tau, const fq_tw *__restrict__ psi_inv_rev)
+FQ_HD void ntt_inv_pass(rns2 (&x)[8], int tau, const fq_tw *__restrict__ psi_inv_rev)
 {
     using P = NttPlan<LOGN>;
     constexpr int lo = P::inv_lo(PASS), lb = P::inv_lb(PASS);
@@ -91,9 +91,11 @@ FQ_HD void ntt_inv_pass(u64 (&x)[8], int tau, const fq_tw *__restrict__ psi_inv_
             if (e0 & (1 << q)) continue;
             const int e1 = e0 | (1 << q);
             const fq_tw w = fq_tw_load(psi_inv_rev + m + ((th << (2 - q)) | (e0 >> (q + 1))));
-            const u64 u = x[e0], v = x[e1];
-            x[e0] = fq_csub(u + v, FQ_2Q);
-            x[e1] = fq_mul_shoup(u - v + FQ_2Q, w.w, w.ws);
+            const u32 ua = x[e0].a, va = x[e1].a, ub = x[e0].b, vb = x[e1].b;
+            x[e0].a = r32_fold(ua + va, 2 * FQ_P1);
+            x[e1].a = r32_mul_shoup(ua - va + 2 * FQ_P1, w.w1, w.ws1, FQ_P1);
+            x[e0].b = r32_fold(ub + vb, 2 * FQ_P2);
+            x[e1].b = r32_mul_shoup(ub - vb + 2 * FQ_P2, w.w2, w.ws2, FQ_P2);
         }
     }
 }
@@ -102,7 +104,7 @@ FQ_HD void ntt_inv_pass(u64 (&x)[8], int tau, const fq_tw *__restrict__ psi_inv_
 // ---- device drivers: transposes through two alternating swizzled buffers -------------------------------
 // `sync` is a callable that synchronises the T threads working on this polynomial.
 template <int LOGN, int PASS, class Sync>
-__device__ __forceinline__ void ntt_fwd_from(u64 (&x)[8], int tau, u64 *bufA, u64 *bufB, const fq_tw *psi_rev, Sync sync)
+__device__ __forceinline__ void ntt_fwd_from(rns2 (&x)[8], int tau, u64 *bufA, u64 *bufB, const fq_tw *psi_rev, Sync sync)
 {
     using P = NttPlan<LOGN>;
     ntt_fwd_pass<LOGN, PASS>(x, tau, psi_rev);
@@ -110,24 +112,24 @@ __device__ __forceinline__ void ntt_fwd_from(u64 (&x)[8], int tau, u64 *bufA, u6
         u64 *buf = (PASS & 1) ? bufB : bufA;
         constexpr int lb0 = P::fwd_lb(PASS), lb1 = P::fwd_lb(PASS + 1);
 #pragma unroll
-        for (int e = 0; e < 8; e++) buf[P::swz(P::idx(tau, e, lb0))] = x[e];
+        for (int e = 0; e < 8; e++) buf[P::swz(P::idx(tau, e, lb0))] = rns_pack(x[e]);
         sync();
 #pragma unroll
-        for (int e = 0; e < 8; e++) x[e] = buf[P::swz(P::idx(tau, e, lb1))];
+        for (int e = 0; e < 8; e++) x[e] = rns_unpack(buf[P::swz(P::idx(tau, e, lb1))]);
         ntt_fwd_from<LOGN, PASS + 1>(x, tau, bufA, bufB, psi_rev, sync);
     }
 }
 // forward NTT: x enters in layout fwd_lb(0) (idx = tau + e*T), leaves in layout fwd_lb(NPASS-1) = 0 (idx = 8*tau+e),
 // values at bit-reversed positions.
 template <int LOGN, class Sync>
-__device__ __forceinline__ void ntt_forward(u64 (&x)[8], int tau, u64 *bufA, u64 *bufB, const fq_tw *psi_rev, Sync sync)
+__device__ __forceinline__ void ntt_forward(rns2 (&x)[8], int tau, u64 *bufA, u64 *bufB, const fq_tw *psi_rev, Sync sync)
 {
     ntt_fwd_from<LOGN, 0>(x, tau, bufA, bufB, psi_rev, sync);
 }
 // ---- single-buffer variants: one scratch polynomial per thread group, two barriers per transpose -----------
 // (used by the blind-rotate kernel, where shared memory rather than barrier count limits residency)
 template <int LOGN, int PASS, class Sync>
-__device__ __forceinline__ void ntt_fwd1_from(u64 (&x)[8], int tau, u64 *buf, const fq_tw *psi_rev, Sync sync, bool buf_free)
+__device__ __forceinline__ void ntt_fwd1_from(rns2 (&x)[8], int tau, u64 *buf, const fq_tw *psi_rev, Sync sync, bool buf_free)
 {
     using P = NttPlan<LOGN>;
     ntt_fwd_pass<LOGN, PASS>(x, tau, psi_rev);
@@ -135,16 +137,16 @@ __device__ __forceinline__ void ntt_fwd1_from(u64 (&x)[8], int tau, u64 *buf, co
         constexpr int lb0 = P::fwd_lb(PASS), lb1 = P::fwd_lb(PASS + 1);
         if (!buf_free) sync();                          // earlier readers of buf are done
 #pragma unroll
-        for (int e = 0; e < 8; e++) buf[P::swz(P::idx(tau, e, lb0))] = x[e];
+        for (int e = 0; e < 8; e++) buf[P::swz(P::idx(tau, e, lb0))] = rns_pack(x[e]);
         sync();
 #pragma unroll
-        for (int e = 0; e < 8; e++) x[e] = buf[P::swz(P::idx(tau, e, lb1))];
+        for (int e = 0; e < 8; e++) x[e] = rns_unpack(buf[P::swz(P::idx(tau, e, lb1))]);
         ntt_fwd1_from<LOGN, PASS + 1>(x, tau, buf, psi_rev, sync, false);
     }
 }
 // inverse: pass 0 is done by the caller's registers; `after_pass0` runs between pass 0 and the first write to buf
 template <int LOGN, int PASS, class Sync0, class Sync>
-__device__ __forceinline__ void ntt_inv1_from(u64 (&x)[8], int tau, u64 *buf, const fq_tw *psi_inv_rev, Sync0 after_pass0, Sync sync)
+__device__ __forceinline__ void ntt_inv1_from(rns2 (&x)[8], int tau, u64 *buf, const fq_tw *psi_inv_rev, Sync0 after_pass0, Sync sync)
 {
     using P = NttPlan<LOGN>;
     ntt_inv_pass<LOGN, PASS>(x, tau, psi_inv_rev);
@@ -152,17 +154,17 @@ __device__ __forceinline__ void ntt_inv1_from(u64 (&x)[8], int tau, u64 *buf, co
     if constexpr (PASS + 1 < P::NPASS) {
         constexpr int lb0 = P::inv_lb(PASS), lb1 = P::inv_lb(PASS + 1);
 #pragma unroll
-        for (int e = 0; e < 8; e++) buf[P::swz(P::idx(tau, e, lb0))] = x[e];
+        for (int e = 0; e < 8; e++) buf[P::swz(P::idx(tau, e, lb0))] = rns_pack(x[e]);
         sync();
 #pragma unroll
-        for (int e = 0; e < 8; e++) x[e] = buf[P::swz(P::idx(tau, e, lb1))];
+        for (int e = 0; e < 8; e++) x[e] = rns_unpack(buf[P::swz(P::idx(tau, e, lb1))]);
         ntt_inv1_from<LOGN, PASS + 1>(x, tau, buf, psi_inv_rev, sync, sync);
     }
 }
 
 // inverse NTT passes PASS.. ; the caller supplies x in layout inv_lb(PASS)
 template <int LOGN, int PASS, class Sync0, class Sync>
-__device__ __forceinline__ void ntt_inv_from(u64 (&x)[8], int tau, u64 *bufA, u64 *bufB, const fq_tw *psi_inv_rev, Sync0 sync_first, Sync sync)
+__device__ __forceinline__ void ntt_inv_from(rns2 (&x)[8], int tau, u64 *bufA, u64 *bufB, const fq_tw *psi_inv_rev, Sync0 sync_first, Sync sync)
 {
     using P = NttPlan<LOGN>;
     ntt_inv_pass<LOGN, PASS>(x, tau, psi_inv_rev);
@@ -170,10 +172,10 @@ __device__ __forceinline__ void ntt_inv_from(u64 (&x)[8], int tau, u64 *bufA, u6
         u64 *buf = (PASS & 1) ? bufB : bufA;
         constexpr int lb0 = P::inv_lb(PASS), lb1 = P::inv_lb(PASS + 1);
 #pragma unroll
-        for (int e = 0; e < 8; e++) buf[P::swz(P::idx(tau, e, lb0))] = x[e];
+        for (int e = 0; e < 8; e++) buf[P::swz(P::idx(tau, e, lb0))] = rns_pack(x[e]);
         if constexpr (PASS == 0) sync_first(); else sync();
 #pragma unroll
-        for (int e = 0; e < 8; e++) x[e] = buf[P::swz(P::idx(tau, e, lb1))];
+        for (int e = 0; e < 8; e++) x[e] = rns_unpack(buf[P::swz(P::idx(tau, e, lb1))]);
         ntt_inv_from<LOGN, PASS + 1>(x, tau, bufA, bufB, psi_inv_rev, sync, sync);
     } else if constexpr (PASS == 0) {
         sync_first();

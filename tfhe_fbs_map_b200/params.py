@@ -7,7 +7,7 @@ noise bound to the *absolute* number of message values p (reference experiments/
 noise by ``sqrt(sq_norm2)`` (concrete.patch:133-134).  ``estimate()`` below applies exactly that bound to the
 parameter sets this executor ships, so every benchmark line can state its PBS failure probability.
 
-Ciphertext modulus is the prime Q = 2^62 - 2^16 + 1; all standard deviations are
+Ciphertext modulus is q = p1*p2, two 30-bit NTT primes; all standard deviations are
 relative to the torus (i.e. in units of Q).
 """
 from __future__ import annotations
@@ -16,7 +16,8 @@ import ctypes
 import math
 from dataclasses import dataclass, asdict
 
-FBS_Q = 0x3FFFFFFFFFFF0001          # ciphertext modulus 2^62 - 2^16 + 1
+FBS_P1, FBS_P2 = 0x3FFE8001, 0x3FFF4001
+FBS_Q = FBS_P1 * FBS_P2             # ciphertext modulus: product of two 30-bit NTT primes (60 bits)
 GOLDILOCKS_P = FBS_Q   # old name kept for the tests' imports
 
 
