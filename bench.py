@@ -126,7 +126,7 @@ def run_reference(args, wl, ps, rank, world):
     v = statistics.mean(x["value"] for x in vals)
     line = dict(metric="PBS/sec", value=v, unit="PBS/s", n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
                 ms_per_step=1e3 * statistics.mean(x["wall_s"] for x in vals),
-                higher_is_better=True, scaling="weak", vs_baseline=None, dtype="u64 (mod 2^62-2^16+1)", data="synthetic",
+                higher_is_better=True, scaling="weak", vs_baseline=None, dtype="u64 (q = p1*p2, two 30-bit NTT primes; RNS u32x2 in the NTT)", data="synthetic",
                 impl="reference", config=dict(workload=args.workload, param_set=ps.name, note="CPU port of the path (oracle/tfhe_ref.c); the reference has no encrypted executor and concrete cannot be built offline"),
                 cpu_baseline=dict(vals[-1], value=v),
                 e2e=dict(value=v, unit="PBS/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
@@ -178,7 +178,7 @@ def run_nodes(args, wl, ps, be, rank, world, local, torch, dist):
         n_pbs = prog.n_boots * B * args.steps
         print(json.dumps(dict(
             metric="PBS/sec", value=n_pbs / (ms * 1e-3), unit="PBS/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
-            ms_per_step=ms / args.steps, higher_is_better=True, scaling="strong", vs_baseline=None, dtype="u64 (mod 2^62-2^16+1)",
+            ms_per_step=ms / args.steps, higher_is_better=True, scaling="strong", vs_baseline=None, dtype="u64 (q = p1*p2, two 30-bit NTT primes; RNS u32x2 in the NTT)",
             data="synthetic", config=dict(workload=args.workload, desc=wl["desc"], param_set=ps.name, fbs_size=wl["p"], instances=B,
                                           pbs_per_instance=prog.n_boots, levels=prog.n_levels, level_width_median=int(np.median(prog.level_widths)),
                                           sharding="nodes of each level split across GPUs; NCCL all-gather of output LWE ciphertexts per level"),
@@ -319,7 +319,7 @@ def main():
         line = dict(
             metric="PBS/sec", value=value, unit="PBS/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
             ms_per_step=ms_res / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
-            dtype="u64 (mod 2^62-2^16+1)", data="synthetic",
+            dtype="u64 (q = p1*p2, two 30-bit NTT primes; RNS u32x2 in the NTT)", data="synthetic",
             config=dict(workload=args.workload, desc=wl["desc"], param_set=ps.name, n=ps.n, k=ps.k, N=ps.N, bsk_l=ps.bsk_l, ks_l=ps.ks_l,
                         fbs_size=wl["p"], instances_per_gpu=B, pbs_per_instance=prog.n_boots, levels=prog.n_levels,
                         p_fail_per_pbs=ps.p_fail(wl["p"], env.stats()["norm2_linprod"]), sharding="instances, keys replicated, no collective",

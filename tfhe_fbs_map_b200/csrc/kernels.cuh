@@ -420,7 +420,8 @@ struct BRCfg {
     __host__ __device__ static constexpr size_t ms_stride(int n) { return (((size_t)(n + 1) * 2 + 15) / 16) * 16; }
     __host__ __device__ static constexpr size_t smem_bytes(int n)
     {
-        return 8 * (PB * per_pbs_w + bs_w) + 16 /* mbarrier */ + PB * ((((size_t)(n + 1) * 2 + 15) / 16) * 16 + 64 /* table */);
+        // keep set A at 2 bootstraps/CTA under 195 KiB so the SM stays in the 196 KiB carve-out and L1 keeps ~60 KB for twiddles
+        return 8 * (PB * per_pbs_w + bs_w) + 16 /* mbarrier */ + PB * ((((size_t)(n + 1) * 2 + 15) / 16) * 16);
     }
 };
 
@@ -442,8 +443,7 @@ __global__ void __launch_bounds__(PB * (K + 1) * (1 << LOGN) / 8 * BR_LB_MULT, 1
     u64 *BS = (u64 *)smem_raw + (size_t)PB * C::per_pbs_w;
     u64 *mbar = BS + C::bs_w;
     const size_t ms_stride = C::ms_stride(a.n);
-    u16 *s_ms = (u16 *)((unsigned char *)(mbar + 2) + (size_t)pb * (ms_stride + 64));
-    u8 *s_tab = (u8 *)s_ms + ms_stride;
+    u16 *s_ms = (u16 *)((unsigned char *)(mbar + 2) + (size_t)pb * ms_stride);
 
     // the second bootstrap of the last CTA may not exist: it recomputes the previous job and skips the store
     long long job = (long long)blockIdx.x * PB + pb;
@@ -456,7 +456,6 @@ __global__ void __launch_bounds__(PB * (K + 1) * (1 << LOGN) / 8 * BR_LB_MULT, 1
     const int tab0 = a.bs_tab_ptr[node], tabL = a.bs_tab_ptr[node + 1] - tab0, mode = a.bs_mode[node];
 
     for (int i = ptid; i <= n; i += C::PT) s_ms[i] = ms[i];
-    if (ptid < 64) s_tab[ptid] = (ptid < tabL) ? a.bs_tab[tab0 + ptid] : 0;
     if (BSK_SMEM && tid == 0) mbar_init(mbar, 1);
     __syncthreads();
     if (BSK_SMEM && tid == 0) {
@@ -482,7 +481,7 @@ __global__ void __launch_bounds__(PB * (K + 1) * (1 << LOGN) / 8 * BR_LB_MULT, 1
                 if (src >= N) { src -= N; neg = true; }
                 int x = (int)((2LL * src * p + N) / (2LL * N));
                 if (x >= p) { x -= p; neg = !neg; }
-                const u64 tvx = (x < tabL) ? (u64)s_tab[x] : 0;
+                const u64 tvx = (x < tabL) ? (u64)__ldg(a.bs_tab + tab0 + x) : 0;
                 const u64 F = fq_sub(fq_mul(tvx, delta), off);
                 val = neg ? fq_neg(F) : F;
             }
