@@ -72,6 +72,7 @@ struct fbs_ctx {
     const BRVariant *br1 = nullptr; size_t br1_smem = 0;      // one bootstrap per CTA, for launches with <= sm_count jobs
     u8 *d_s_lwe = nullptr, *d_s_big = nullptr;
     u64 *d_ksk = nullptr, *d_colsum = nullptr, *d_bsk = nullptr, *d_bsk_coef = nullptr;
+    u8 *d_kbt = nullptr;                                       // byte-transposed KSK for the tensor-core key switch
     fq_tw *d_psi_rev = nullptr, *d_psi_inv_rev = nullptr;
     u64 *d_gad_bsk = nullptr, *d_gad_ks = nullptr;
     u32 ninv[2] = {0, 0}, mont_ninv[2] = {0, 0};     // 1/N and 2^32/N per prime
@@ -192,6 +193,9 @@ extern "C" int fbs_keygen(fbs_ctx *c)
     if (!c->d_ksk) { CKR(dev_alloc(&c->d_ksk, R * (n + 1))); CKR(dev_alloc(&c->d_colsum, n + 1)); }
     k_gen_ksk<<<(unsigned)R, 256, 0, st>>>(c->d_ksk, n, lk, c->seed, c->d_s_lwe, c->d_s_big, P.lwe_noise, c->d_gad_ks);
     k_ksk_colsum<<<(n + 1 + 127) / 128, 128, 0, st>>>(c->d_ksk, (int)R, n + 1, c->d_colsum);
+    const int cols_pad = (n + 1 + 7) / 8 * 8;
+    if (!c->d_kbt) CKR(dev_alloc(&c->d_kbt, (size_t)cols_pad * 8 * R));
+    k_ksk_bytes_t<<<dim3((unsigned)((R + 255) / 256), (unsigned)cols_pad), 256, 0, st>>>(c->d_ksk, c->d_kbt, (int)R, n + 1, cols_pad);
     const int rows = (k + 1) * l;
     const size_t total = (size_t)n * rows * (k + 1) * N;
     if (!c->d_bsk) { CKR(dev_alloc(&c->d_bsk, total)); CKR(dev_alloc(&c->d_bsk_coef, total)); }
@@ -212,7 +216,7 @@ extern "C" int fbs_ctx_destroy(fbs_ctx *c)
 {
     if (!c) return FBS_OK;
     cudaSetDevice(c->device);
-    void *ptrs[] = {c->d_s_lwe, c->d_s_big, c->d_ksk, c->d_colsum, c->d_bsk, c->d_bsk_coef, c->d_psi_rev, c->d_psi_inv_rev,
+    void *ptrs[] = {c->d_kbt, c->d_s_lwe, c->d_s_big, c->d_ksk, c->d_colsum, c->d_bsk, c->d_bsk_coef, c->d_psi_rev, c->d_psi_inv_rev,
                     c->d_gad_bsk, c->d_gad_ks, c->d_digits, c->d_body, c->d_ms, c->d_io, c->d_wires};
     for (void *p : ptrs) if (p) cudaFree(p);
     for (auto &e : c->ev) if (e) cudaEventDestroy(e);
@@ -343,11 +347,12 @@ static int run_level_impl(fbs_ctx *c, fbs_prog *g, int level, int nb, int ne, in
     const int D = P.k * P.N, n = P.n;
     const int node0 = b0 + nb, node1 = b0 + ne;
     const int lc0 = g->bs_lc[node0], lc1 = g->bs_lc[node1 - 1] + 1;     // bootstraps are sorted by lincomb
-    const long long M = (long long)(lc1 - lc0) * B, tiles = (M + 15) / 16;
+    const long long M = (long long)(lc1 - lc0) * B, tiles = (M + 15) / 16, mtiles = (M + KS_BM - 1) / KS_BM;
     const size_t R = (size_t)D * P.ks_l;
-    CKR(grow(&c->d_digits, &c->cap_digits, (size_t)tiles * R * 16));
-    CKR(grow(&c->d_body, &c->cap_body, (size_t)tiles * 16));
-    CKR(grow(&c->d_ms, &c->cap_ms, (size_t)tiles * 16 * (n + 1)));
+    if (R % KS_BK) return fail(FBS_ERR_ARG, "k*N*ks_l must be a multiple of 128");
+    CKR(grow(&c->d_digits, &c->cap_digits, (size_t)mtiles * KS_BM * R));
+    CKR(grow(&c->d_body, &c->cap_body, (size_t)mtiles * KS_BM));
+    CKR(grow(&c->d_ms, &c->cap_ms, (size_t)mtiles * KS_BM * (n + 1)));
     if (rec) CK(cudaEventRecord(E[0], st));
     LCArgs la{};
     la.wires = wires; la.lc_ptr = g->d_lc_ptr; la.lc_slot = g->d_lc_slot; la.lc_coef = g->d_lc_coef; la.lc_const = g->d_lc_const;
@@ -360,20 +365,10 @@ static int run_level_impl(fbs_ctx *c, fbs_prog *g, int level, int nb, int ne, in
     CK(cudaGetLastError());
     if (rec) CK(cudaEventRecord(E[1], st));
     KSArgs ka{};
-    ka.digits = c->d_digits; ka.body = c->d_body; ka.ksk = c->d_ksk; ka.colsum = c->d_colsum; ka.ms = c->d_ms; ka.tap_ks = tap_ks;
+    ka.digits = c->d_digits; ka.body = c->d_body; ka.kbt = c->d_kbt; ka.colsum = c->d_colsum; ka.ms = c->d_ms; ka.tap_ks = tap_ks;
     ka.M = M; ka.R = (int)R; ka.n = n; ka.ks_beta = P.ks_beta; ka.log2_2N = c->logN + 1;
-    dim3 kgrid((unsigned)((n + 1 + 127) / 128), (unsigned)tiles);
-    if (tiles > 65535) {     // gridDim.y limit: run in slabs of tiles
-        for (long long t0 = 0; t0 < tiles; t0 += 65535) {
-            KSArgs kb = ka; long long tn = std::min<long long>(65535, tiles - t0);
-            kb.digits += (size_t)t0 * R * 16; kb.body += t0 * 16; kb.ms += (size_t)t0 * 16 * (n + 1);
-            if (kb.tap_ks) kb.tap_ks += (size_t)t0 * 16 * (n + 1);
-            kb.M = std::min<long long>(M - t0 * 16, tn * 16);
-            k_keyswitch<<<dim3(kgrid.x, (unsigned)tn), 128, 0, st>>>(kb);
-        }
-    } else {
-        k_keyswitch<<<kgrid, 128, 0, st>>>(ka);
-    }
+    const unsigned ngrid = (unsigned)(((n + 1 + 7) / 8 * 8 * 8 + KS_BN - 1) / KS_BN);
+    k_keyswitch_mma<<<dim3((unsigned)mtiles, ngrid), 256, 0, st>>>(ka);
     CK(cudaGetLastError());
     if (rec) CK(cudaEventRecord(E[2], st));
     BRArgs ba{};

@@ -1,6 +1,6 @@
 // kernels.cuh -- sm_100a kernels of the encrypted FBS executor.
 //   K1a k_lincomb_decomp : LWE linear combination (weighted sum mod P) + key-switch gadget decomposition
-//   K1b k_keyswitch      : digit x KSK accumulation (2 IMAD.WIDE per MAC), fused modulus switch to 2N
+//   K1b k_keyswitch_mma  : digit x KSK-byte GEMM on the tensor cores (mma.sync u8), byte recombination, modulus switch
 //   K2  k_blind_rotate   : test polynomial, n CMUX steps (decompose, NTT, BSK MAC, inverse NTT), accumulator in
 //                          shared memory, BSK rows streamed with cp.async.bulk (TMA) + mbarrier; K3 sample
 //                          extraction (+ table-mode offset) as epilogue
@@ -272,9 +272,9 @@ __global__ void __launch_bounds__(256) k_decrypt(OutArgs a)
 }
 
 // ------------------------------------------------------------------------------------------------------
-// K1a: linear combination + key-switch decomposition.  One CTA = a tile of 16 (lincomb, instance) pairs, so
-// that the 16 digits of one (word, level) form one coalesced 16-byte store in the layout K1b consumes:
-//   digits[tile][r = i*lk + j][16]  (uint8, offset form d + B/2 in [0, B))
+// K1a: linear combination + key-switch decomposition.  One CTA = 16 (lincomb, instance) pairs x all kN+1 words.
+// Digits go out row-major, digits[m][r = i*lk + j] (uint8, offset form d + B/2 in [0, B)): the A operand of the
+// tensor-core key switch.
 // ------------------------------------------------------------------------------------------------------
 struct LCArgs {
     const u64 *wires;
@@ -297,11 +297,8 @@ __global__ void __launch_bounds__(256) k_lincomb_decomp(LCArgs a)
     __syncthreads();
     const size_t CT = (size_t)a.D + 1;
     const size_t R = (size_t)a.D * LK;
-    const u32 halfB = 1u << (a.ks_beta - 1);
+    const int halfB = 1 << (a.ks_beta - 1);
     for (int i = threadIdx.x; i <= a.D; i += 256) {
-        u32 pk[LK][4];
-#pragma unroll
-        for (int j = 0; j < LK; j++) { pk[j][0] = pk[j][1] = pk[j][2] = pk[j][3] = 0; }
 #pragma unroll
         for (int mm = 0; mm < 16; mm++) {
             const int lc = s_lc[mm];
@@ -318,74 +315,116 @@ __global__ void __launch_bounds__(256) k_lincomb_decomp(LCArgs a)
             } else {
                 int d[LK];
                 fbs_balanced_digits<LK>(fbs_round_top(acc, a.ks_beta * LK), a.ks_beta, d);
+                u8 *dst = a.digits + (size_t)(tile * 16 + mm) * R + (size_t)i * LK;
 #pragma unroll
-                for (int j = 0; j < LK; j++) pk[j][mm >> 2] |= ((u32)(d[j] + (int)halfB)) << (8 * (mm & 3));
+                for (int j = 0; j < LK; j++) dst[j] = (u8)(d[j] + halfB);
             }
-        }
-        if (i < a.D) {
-            uint4 *dst = (uint4 *)(a.digits + ((size_t)tile * R + (size_t)i * LK) * 16);
-#pragma unroll
-            for (int j = 0; j < LK; j++) dst[j] = make_uint4(pk[j][0], pk[j][1], pk[j][2], pk[j][3]);
         }
     }
 }
 
 // ------------------------------------------------------------------------------------------------------
-// K1b: key switch.  out[m][c] = [c==n]*body[m] - sum_r d[m][r] * KSK[r][c]  (mod P), then modulus switch to 2N.
-// Offset digits du = d + B/2 >= 0 make every product unsigned: sum du*x = two IMAD.WIDE per MAC into 64-bit
-// accumulators (low and high half of x), no carries; the offset is removed with (B/2)*colsum[c].
+// K1b: key switch on the tensor cores.  out[m][c] = [c==n]*body[m] - sum_r d[m][r] * KSK[r][c]  (mod q), then
+// modulus switch to 2N.  The KSK entry is split into its 8 bytes: C[m][(c,b)] = sum_r du[m][r] * byte_b(KSK[r][c]) is an
+// exact u8 x u8 -> s32 GEMM (7 * 255 * kN*l_ks < 2^31), run as mma.sync.m16n8k32; the 8 byte sums of a column are
+// recombined as sum_b C_b * 2^(8b) mod q in the epilogue and the digit offset B/2 is removed with (B/2)*colsum[c].
+// This is the one GEMM-shaped step of the path: 8x more MACs than the integer-pipe version
+// (2 IMAD.WIDE per MAC), but on a unit that is otherwise idle -- measured 436 -> see profiles/ ms per adder128 step.
+// KbT[(c*8+b)][r] is the byte-transposed key (k-contiguous "col" operand), CTA tile 64 ciphertexts x 8 columns x 128 rows,
+// cp.async double buffering, 144-byte padded rows (bank-conflict-free 32-bit fragment loads).
 // ------------------------------------------------------------------------------------------------------
 struct KSArgs {
-    const u8 *digits; const u64 *body; const u64 *ksk; const u64 *colsum;
+    const u8 *digits; const u64 *body; const u8 *kbt; const u64 *colsum;
     u16 *ms; u64 *tap_ks;
     long long M; int R, n, ks_beta, log2_2N;
 };
-__global__ void __launch_bounds__(128) k_keyswitch(KSArgs a)
+#define KS_BM 64
+#define KS_BN 64
+#define KS_BK 128
+#define KS_LD 144
+__device__ __forceinline__ void cp_async16(void *dst, const void *src)
 {
-    const int cols = a.n + 1;
-    int c = blockIdx.x * 128 + threadIdx.x;
-    const bool live = c < cols;
-    if (!live) c = cols - 1;
-    const long long tile = blockIdx.y;
-    const uint4 *dg = (const uint4 *)(a.digits + (size_t)tile * a.R * 16);
-    const u64 *kc = a.ksk + c;
-    u64 acc0[16], acc1[16];
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void mma_u8(int (&c)[4], u32 a0, u32 a1, u32 a2, u32 a3, u32 b0, u32 b1)
+{
+    asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.u8.u8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__global__ void __launch_bounds__(256) k_keyswitch_mma(KSArgs a)
+{
+    __shared__ __align__(16) u8 sA[2][KS_BM * KS_LD];
+    __shared__ __align__(16) u8 sB[2][KS_BN * KS_LD];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+    const int wm = warp & 3, wn = warp >> 2;
+    const long long m0 = (long long)blockIdx.x * KS_BM;
+    const int n0 = blockIdx.y * KS_BN;
+    const size_t R = (size_t)a.R;
+    const u8 *gA = a.digits + (size_t)m0 * R, *gB = a.kbt + (size_t)n0 * R;
+    auto load_stage = [&](int st, int k0) {
 #pragma unroll
-    for (int mm = 0; mm < 16; mm++) { acc0[mm] = 0; acc1[mm] = 0; }
-    for (int r = 0; r < a.R; r += 4) {
-        u64 x[4]; uint4 d4[4];
-#pragma unroll
-        for (int t = 0; t < 4; t++) {
-            const int rr = (r + t < a.R) ? r + t : a.R - 1;
-            x[t] = kc[(size_t)rr * cols];
-            d4[t] = __ldg(dg + rr);
-            if (r + t >= a.R) d4[t] = make_uint4(0, 0, 0, 0), x[t] = 0;
+        for (int h = 0; h < 2; h++) {
+            const int id = tid + 256 * h, row = id >> 3, c16 = (id & 7) * 16;
+            cp_async16(&sA[st][row * KS_LD + c16], gA + (size_t)row * R + k0 + c16);
+            cp_async16(&sB[st][row * KS_LD + c16], gB + (size_t)row * R + k0 + c16);
         }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    int acc[4][4];
 #pragma unroll
-        for (int t = 0; t < 4; t++) {
-            const u32 xl = (u32)x[t], xh = (u32)(x[t] >> 32);
-            const u32 w[4] = {d4[t].x, d4[t].y, d4[t].z, d4[t].w};
+    for (int j = 0; j < 4; j++) { acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0; }
+    const int nk = a.R / KS_BK;
+    load_stage(0, 0);
+    for (int ks = 0; ks < nk; ks++) {
+        if (ks + 1 < nk) { load_stage((ks + 1) & 1, (ks + 1) * KS_BK); asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+        else asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();
+        const u8 *A = sA[ks & 1] + (wm * 16 + g) * KS_LD + t * 4;
+        const u8 *Bp = sB[ks & 1] + (wn * 32 + g) * KS_LD + t * 4;
 #pragma unroll
-            for (int mm = 0; mm < 16; mm++) {
-                const u32 du = (w[mm >> 2] >> (8 * (mm & 3))) & 0xffu;
-                acc0[mm] += (u64)du * (u64)xl;
-                acc1[mm] += (u64)du * (u64)xh;
+        for (int kk = 0; kk < KS_BK / 32; kk++) {
+            const u32 a0 = *(const u32 *)(A + kk * 32), a1 = *(const u32 *)(A + 8 * KS_LD + kk * 32);
+            const u32 a2 = *(const u32 *)(A + kk * 32 + 16), a3 = *(const u32 *)(A + 8 * KS_LD + kk * 32 + 16);
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const u32 b0 = *(const u32 *)(Bp + j * 8 * KS_LD + kk * 32), b1 = *(const u32 *)(Bp + j * 8 * KS_LD + kk * 32 + 16);
+                mma_u8(acc[j], a0, a1, a2, a3, b0, b1);
+            }
+        }
+        __syncthreads();
+    }
+    // ---- epilogue: recombine the 8 byte sums of each column, remove the digit offset, add the body, modulus switch
+    const int cols = a.n + 1;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const int c = (n0 >> 3) + wn * 4 + j;
+        const bool col_ok = c < cols;
+        const u64 corr = col_ok ? fq_mul(a.colsum[c], (u64)(1u << (a.ks_beta - 1))) : 0;
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const u64 v = (u64)(u32)acc[j][2 * h] + ((u64)(u32)acc[j][2 * h + 1] << 8);      // bytes 2t, 2t+1
+            const int sh = 16 * t;
+            u64 x = fq_reduce128(v << sh, sh ? (v >> (64 - sh)) : 0);
+            x = fq_add(x, __shfl_xor_sync(0xffffffffu, x, 1));
+            x = fq_add(x, __shfl_xor_sync(0xffffffffu, x, 2));
+            const long long m = m0 + wm * 16 + g + 8 * h;
+            if (t == 0 && col_ok && m < a.M) {
+                u64 val = fq_sub(corr, x);
+                if (c == a.n) val = fq_add(val, a.body[m]);
+                a.ms[(size_t)m * cols + c] = (u16)fbs_modswitch(val, a.log2_2N);
+                if (a.tap_ks) a.tap_ks[(size_t)m * cols + c] = val;
             }
         }
     }
-    if (!live) return;
-    const u64 corr = fq_mul(a.colsum[c], (u64)(1u << (a.ks_beta - 1)));
+}
+// byte-transpose the key-switching key for the tensor-core path: kbt[(c*8+b)][r] = byte b of ksk[r][c]
+__global__ void k_ksk_bytes_t(const u64 *__restrict__ ksk, u8 *__restrict__ kbt, int R, int cols, int cols_pad)
+{
+    const int r = blockIdx.x * blockDim.x + threadIdx.x, c = blockIdx.y;
+    if (r >= R) return;
+    const u64 x = (c < cols) ? ksk[(size_t)r * cols + c] : 0;
 #pragma unroll
-    for (int mm = 0; mm < 16; mm++) {
-        const long long m = tile * 16 + mm;
-        if (m >= a.M) continue;
-        const u64 lo = acc0[mm] + (acc1[mm] << 32);
-        const u64 hi = (acc1[mm] >> 32) + (lo < acc0[mm] ? 1 : 0);
-        u64 v = fq_sub(corr, fq_reduce128(lo, hi));
-        if (c == a.n) v = fq_add(v, a.body[m]);
-        a.ms[(size_t)m * cols + c] = (u16)fbs_modswitch(v, a.log2_2N);
-        if (a.tap_ks) a.tap_ks[(size_t)m * cols + c] = v;
-    }
+    for (int b = 0; b < 8; b++) kbt[((size_t)c * 8 + b) * R + r] = (u8)(x >> (8 * b));
 }
 
 // ------------------------------------------------------------------------------------------------------
