@@ -327,7 +327,8 @@ def main():
             evals_per_s=world * B * args.steps / (ms_res * 1e-3), mismatches=mism_res,
             phase_ms_per_step=dict(lincomb=st.ms_lincomb / args.steps, keyswitch=st.ms_keyswitch / args.steps, blind_rotate=st.ms_blind_rotate / args.steps),
             roofline=dict(bound="hbm", achieved=achieved, peak=peaks.get("hbm_gbs"), unit="GB/s", frac=achieved / peaks.get("hbm_gbs"),
-                          traffic=None, kernel="k_blind_rotate", launch_ms=br_ms_avg, peak_source=peak_kind,
+                          traffic=61.95e6 / 1e9, traffic_note="GB per launch: dram__bytes_read+write of a 592-PBS launch, profiles/r1_v5_hot_kernels_summary.txt",
+                          kernel="k_blind_rotate", launch_ms=br_ms_avg, peak_source=peak_kind,
                           note="kernel is integer-issue bound by design (accumulator on chip, keys L2-resident); see roofline_int"),
             roofline_int=dict(bound="int32-multiply", achieved=mul32 / 1e12, peak=int_peak / 1e12, unit="T mul32/s", frac=mul32 / int_peak,
                               mul32_per_pbs=ps.mul32_per_pbs(), modmul_per_pbs=ps.modmul_per_pbs(), peak_source="measured (fbs_measure_int_peak: mad.wide.u32 chains)"),
