@@ -136,7 +136,7 @@ def run_reference(args, wl, ps, rank, world):
 def run_nodes(args, wl, ps, be, rank, world, local, torch, dist):
     """BASELINE configs[3]: ONE circuit, node-sharded levels, NCCL all-gather of output LWEs per level."""
     from tfhe_fbs_map_b200 import levelize
-    from tfhe_fbs_map_b200.dist import B200Engine, run_node_sharded
+    from tfhe_fbs_map_b200.dist import B200Engine, FusedB200Engine, run_node_sharded
     from oracle import cleartext
     env = load_env(wl["lbf"])
     prog = levelize(env, wl["p"], shard_pad=world, reuse_slots=False)
@@ -146,7 +146,8 @@ def run_nodes(args, wl, ps, be, rank, world, local, torch, dist):
     bits = rng.integers(0, 2, (prog.n_inputs, B)).astype(np.uint8)
     want = cleartext.lut_eval(env, {nm: bits[i] for i, nm in enumerate(prog.input_names)})
     want_mat = np.array([np.asarray(want[nm]) for nm in prog.output_names], dtype=np.uint8)
-    eng = B200Engine(be, cp, B, torch)
+    fused = args.exchange == "fused" and world > 1
+    eng = FusedB200Engine(be, cp, B, torch, dist, world, rank) if fused else B200Engine(be, cp, B, torch)
     eng.encrypt(bits)
 
     def barrier():
@@ -181,9 +182,11 @@ def run_nodes(args, wl, ps, be, rank, world, local, torch, dist):
             ms_per_step=ms / args.steps, higher_is_better=True, scaling="strong", vs_baseline=None, dtype="u64 (q = p1*p2, two 30-bit NTT primes; RNS u32x2 in the NTT)",
             data="synthetic", config=dict(workload=args.workload, desc=wl["desc"], param_set=ps.name, fbs_size=wl["p"], instances=B,
                                           pbs_per_instance=prog.n_boots, levels=prog.n_levels, level_width_median=int(np.median(prog.level_widths)),
-                                          sharding="nodes of each level split across GPUs; NCCL all-gather of output LWE ciphertexts per level"),
+                                          sharding="nodes of each level split across GPUs; " + ("sample-extract epilogue stores output LWE ciphertexts into every peer replica over NVLink (fused compute+exchange), host barrier per level" if fused else "NCCL in-place all-gather of output LWE ciphertexts per level")),
             evals_per_s=B * args.steps / (ms * 1e-3), mismatches=mism,
             allgather_bytes_per_step=words * 8 // max(1, args.steps), gpu_launches=3 * prog.n_levels * args.steps, clocks=sampler.summary())))
+    if fused:
+        eng.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -202,6 +205,9 @@ def main():
     ap.add_argument("--shard", default="instances", choices=["instances", "nodes"],
                     help="instances: batch split across GPUs, no collective (weak scaling); nodes: one circuit, each level's "
                          "bootstraps split across GPUs + NCCL all-gather of the output LWE ciphertexts per level (strong scaling)")
+    ap.add_argument("--exchange", default="fused", choices=["fused", "nccl"],
+                    help="--shard nodes: 'fused' = sample-extract epilogue stores into all peers' replicas (one kernel does "
+                         "compute + exchange), 'nccl' = separate in-place all-gather per level")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()

@@ -111,6 +111,18 @@ int fbs_run_level(fbs_ctx *ctx, fbs_prog *prog, int32_t level, int32_t node_begi
 int fbs_run(fbs_ctx *ctx, fbs_prog *prog, int64_t B, uint64_t *wires_dev, void *stream, fbs_run_stats *stats);
 int fbs_decrypt_outputs(fbs_ctx *ctx, fbs_prog *prog, int64_t B, const uint64_t *wires_dev, uint8_t *out_dev, void *stream);
 
+/* ---- fused exchange for node-sharded levels (BASELINE.json configs[3]) ---------------------------------
+ * Every rank keeps a replica of the wire buffer.  After fbs_set_peers, the sample-extract epilogue of the blind-rotation
+ * kernel stores each output ciphertext into the local buffer AND into every peer replica (NVLink peer stores), which
+ * replaces the per-level all-gather; the caller only barriers between levels.  Buffers come from fbs_wires_alloc and
+ * travel between processes as CUDA IPC handles (64 opaque bytes). */
+int fbs_wires_alloc(fbs_ctx *ctx, size_t bytes, uint64_t **out);
+int fbs_wires_free(fbs_ctx *ctx, uint64_t *wires_dev);
+int fbs_ipc_export(fbs_ctx *ctx, const uint64_t *wires_dev, unsigned char handle[64]);
+int fbs_ipc_import(fbs_ctx *ctx, const unsigned char handle[64], uint64_t **peer_wires);
+int fbs_ipc_close(fbs_ctx *ctx, uint64_t *peer_wires);
+int fbs_set_peers(fbs_ctx *ctx, uint64_t *const *peer_wires, int32_t n_peers);   /* n_peers = 0 switches it off */
+
 /* ---- PBS micro-benchmark (BASELINE.json configs[4]) -------------------------------------------------
  * count independent bootstraps: encrypt msgs[i] in Z_2p, bootstrap with tables[i*2p .. i*2p+tlen[i]),
  * decrypt into out[i].  Host buffers.  `resident` != 0 keeps ciphertexts on the device across the timed

@@ -167,3 +167,46 @@ def test_error_paths(ctxs):
     with pytest.raises(AssertionError):
         levelize(env, 5)                       # tables of 13 entries do not fit p=5
     nk.close()
+
+
+def test_fused_peer_store_epilogue_single_gpu(ctxs):
+    """The sample-extract epilogue writes each output ciphertext into every registered peer replica.  With one GPU the
+    'peers' are two more buffers on the same device: after a run all three must hold identical bootstrap outputs."""
+    import ctypes
+    import torch
+    be, _ = ctxs("toy3")
+    e = next(x for x in load_ref_mapped() if x["circuit"] == "ascon_lut" and x["p"] == 11 and x["mapper"] == "search")
+    prog = levelize(read_lbf(e["lbf"]), 11, shard_pad=2)
+    cp = be.load(prog)
+    B = 8
+    nbytes = be.wires_bytes(cp, B)
+    main_buf, p1, p2 = be.wires_alloc(nbytes), be.wires_alloc(nbytes), be.wires_alloc(nbytes)
+    try:
+        inputs = selfcheck_inputs(e["input_names"])
+        bits = np.array([inputs[nm][:B] for nm in prog.input_names], dtype=np.uint8)
+        d_in = torch.from_numpy(bits).cuda()
+        for buf in (main_buf, p1, p2):                      # replicas start from the same encrypted inputs
+            be.encrypt_inputs(cp, d_in.data_ptr(), B, buf)
+        be.set_peers([p1, p2])
+        be.run(cp, B, main_buf)
+        be.set_peers([])
+        torch.cuda.synchronize()
+        words = nbytes // 8
+        host = []
+        for buf in (main_buf, p1, p2):
+            t = torch.empty(words, dtype=torch.int64, device="cuda")
+            ctypes.CDLL("libcudart.so").cudaMemcpy(ctypes.c_void_p(t.data_ptr()), ctypes.c_void_p(buf), ctypes.c_size_t(nbytes), 3)
+            host.append(t.cpu().numpy().reshape(prog.n_slots, B, be.params.ct_words))
+        a = prog.arrays
+        for q in range(prog.n_boots):
+            s = int(a["bs_slot"][q])
+            assert np.array_equal(host[0][s], host[1][s]) and np.array_equal(host[0][s], host[2][s]), f"bootstrap {q}"
+        d_out = torch.empty((len(prog.output_names), B), dtype=torch.uint8, device="cuda")
+        be.decrypt_outputs(cp, B, p2, d_out.data_ptr())
+        torch.cuda.synchronize()
+        want = unpack_outputs(e, batch=B)
+        for nm in prog.output_names:
+            assert np.array_equal(d_out.cpu().numpy()[prog.out_index[nm]], want[str(nm)]), nm
+    finally:
+        for buf in (main_buf, p1, p2):
+            be.wires_free(buf)

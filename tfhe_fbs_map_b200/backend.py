@@ -22,6 +22,7 @@ EXPORTS = [
     "fbs_prog_load", "fbs_prog_free", "fbs_eval_bits", "fbs_wires_bytes", "fbs_encrypt_inputs", "fbs_run_level",
     "fbs_run", "fbs_decrypt_outputs", "fbs_pbs_batch", "fbs_clear_eval", "fbs_debug_get_keys", "fbs_debug_ntt",
     "fbs_debug_pbs", "fbs_debug_encrypt", "fbs_debug_decrypt", "fbs_measure_int_peak",
+    "fbs_wires_alloc", "fbs_wires_free", "fbs_ipc_export", "fbs_ipc_import", "fbs_ipc_close", "fbs_set_peers",
 ]
 
 
@@ -72,6 +73,12 @@ def load_library(path: str | None = None):
         lib.fbs_debug_encrypt.argtypes = [vp, i32, vp, vp, i64, u64, vp]
         lib.fbs_debug_decrypt.argtypes = [vp, i32, vp, i64, vp]
         lib.fbs_measure_int_peak.argtypes = [vp, ctypes.POINTER(ctypes.c_double)]
+        lib.fbs_wires_alloc.argtypes = [vp, ctypes.c_size_t, ctypes.POINTER(vp)]
+        lib.fbs_wires_free.argtypes = [vp, vp]
+        lib.fbs_ipc_export.argtypes = [vp, vp, ctypes.c_char_p]
+        lib.fbs_ipc_import.argtypes = [vp, ctypes.c_char_p, ctypes.POINTER(vp)]
+        lib.fbs_ipc_close.argtypes = [vp, vp]
+        lib.fbs_set_peers.argtypes = [vp, ctypes.POINTER(vp), i32]
         for name in EXPORTS:
             if name != "fbs_last_error":
                 getattr(lib, name).restype = ctypes.c_int
@@ -145,6 +152,32 @@ class B200Backend:
         sm, bsk, ksk, sme = ctypes.c_int32(), ctypes.c_int64(), ctypes.c_int64(), ctypes.c_int32()
         self._check(self.lib.fbs_ctx_info(self.ctx, ctypes.byref(sm), ctypes.byref(bsk), ctypes.byref(ksk), ctypes.byref(sme)))
         return dict(sm_count=sm.value, bsk_bytes=bsk.value, ksk_bytes=ksk.value, br_smem_bytes=sme.value)
+
+    # ------------------------------------------------------------------ peer-mapped wire buffers (node sharding)
+    def wires_alloc(self, nbytes: int) -> int:
+        p = ctypes.c_void_p()
+        self._check(self.lib.fbs_wires_alloc(self.ctx, nbytes, ctypes.byref(p)))
+        return p.value
+
+    def wires_free(self, ptr: int):
+        self._check(self.lib.fbs_wires_free(self.ctx, ctypes.c_void_p(ptr)))
+
+    def ipc_export(self, ptr: int) -> bytes:
+        buf = ctypes.create_string_buffer(64)
+        self._check(self.lib.fbs_ipc_export(self.ctx, ctypes.c_void_p(ptr), buf))
+        return buf.raw
+
+    def ipc_import(self, handle: bytes) -> int:
+        p = ctypes.c_void_p()
+        self._check(self.lib.fbs_ipc_import(self.ctx, handle, ctypes.byref(p)))
+        return p.value
+
+    def ipc_close(self, ptr: int):
+        self._check(self.lib.fbs_ipc_close(self.ctx, ctypes.c_void_p(ptr)))
+
+    def set_peers(self, ptrs):
+        arr = (ctypes.c_void_p * max(1, len(ptrs)))(*ptrs)
+        self._check(self.lib.fbs_set_peers(self.ctx, arr, len(ptrs)))
 
     def measure_int_peak(self) -> float:
         """Sustained IMAD.WIDE rate of this device in 32x32->64 multiplies per second."""

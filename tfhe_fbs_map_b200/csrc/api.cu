@@ -73,6 +73,7 @@ struct fbs_ctx {
     u8 *d_s_lwe = nullptr, *d_s_big = nullptr;
     u64 *d_ksk = nullptr, *d_colsum = nullptr, *d_bsk = nullptr, *d_bsk_coef = nullptr;
     u8 *d_kbt = nullptr;                                       // byte-transposed KSK for the tensor-core key switch
+    int n_peers = 0; u64 *peers[8] = {};                       // peer replicas of the wire buffer (fbs_set_peers)
     fq_tw *d_psi_rev = nullptr, *d_psi_inv_rev = nullptr;
     u64 *d_gad_bsk = nullptr, *d_gad_ks = nullptr;
     u32 ninv[2] = {0, 0}, mont_ninv[2] = {0, 0};     // 1/N and 2^32/N per prime
@@ -374,7 +375,9 @@ static int run_level_impl(fbs_ctx *c, fbs_prog *g, int level, int nb, int ne, in
     BRArgs ba{};
     ba.ms = c->d_ms; ba.bsk = c->d_bsk; ba.psi_rev = c->d_psi_rev; ba.psi_inv_rev = c->d_psi_inv_rev;
     ba.bs_lc = g->d_bs_lc; ba.bs_slot = g->d_bs_slot; ba.bs_tab_ptr = g->d_bs_tab_ptr; ba.bs_mode = g->d_bs_mode; ba.bs_tab = g->d_tab;
-    ba.wires = wires; ba.tap_acc = tap_acc; ba.B = B; ba.jobs = (long long)(node1 - node0) * B; ba.node_begin = node0; ba.lc_begin = lc0; ba.n = n; ba.p = g->p; ba.beta = P.bsk_beta;
+    ba.wires = wires; ba.tap_acc = tap_acc; ba.B = B; ba.jobs = (long long)(node1 - node0) * B; ba.node_begin = node0;
+    ba.n_peers = c->n_peers;
+    for (int pr = 0; pr < c->n_peers; pr++) ba.peer_wires[pr] = c->peers[pr]; ba.lc_begin = lc0; ba.n = n; ba.p = g->p; ba.beta = P.bsk_beta;
     const long long jobs = (long long)(node1 - node0) * B;
     if (jobs <= c->sm_count) CK(c->br1->launch(ba, jobs, c->br1_smem, st));   // fill SMs first, pair bootstraps after
     else CK(c->br->launch(ba, jobs, c->br_smem, st));
@@ -720,5 +723,56 @@ extern "C" int fbs_measure_int_peak(fbs_ctx *c, double *mul32_per_s)
     }
     cudaFree(d);
     *mul32_per_s = best;
+    return FBS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// peer-mapped wire buffers for the fused sample-extract + exchange of node-sharded levels
+// ------------------------------------------------------------------------------------------------------
+extern "C" int fbs_wires_alloc(fbs_ctx *c, size_t bytes, uint64_t **out)
+{
+    if (!c || !out || bytes == 0) return fail(FBS_ERR_ARG, "fbs_wires_alloc: bad argument");
+    CK(cudaSetDevice(c->device));
+    CK(cudaMalloc((void **)out, bytes));             // a plain cudaMalloc allocation: exportable with CUDA IPC
+    return FBS_OK;
+}
+extern "C" int fbs_wires_free(fbs_ctx *c, uint64_t *p)
+{
+    if (!c) return fail(FBS_ERR_ARG, "fbs_wires_free: null ctx");
+    CK(cudaSetDevice(c->device));
+    if (p) CK(cudaFree(p));
+    return FBS_OK;
+}
+extern "C" int fbs_ipc_export(fbs_ctx *c, const uint64_t *dev_ptr, unsigned char handle[64])
+{
+    if (!c || !dev_ptr || !handle) return fail(FBS_ERR_ARG, "fbs_ipc_export: bad argument");
+    CK(cudaSetDevice(c->device));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    cudaIpcMemHandle_t h;
+    CK(cudaIpcGetMemHandle(&h, (void *)dev_ptr));
+    memcpy(handle, &h, 64);
+    return FBS_OK;
+}
+extern "C" int fbs_ipc_import(fbs_ctx *c, const unsigned char handle[64], uint64_t **out)
+{
+    if (!c || !handle || !out) return fail(FBS_ERR_ARG, "fbs_ipc_import: bad argument");
+    CK(cudaSetDevice(c->device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    CK(cudaIpcOpenMemHandle((void **)out, h, cudaIpcMemLazyEnablePeerAccess));
+    return FBS_OK;
+}
+extern "C" int fbs_ipc_close(fbs_ctx *c, uint64_t *peer_ptr)
+{
+    if (!c) return fail(FBS_ERR_ARG, "fbs_ipc_close: null ctx");
+    CK(cudaSetDevice(c->device));
+    if (peer_ptr) CK(cudaIpcCloseMemHandle(peer_ptr));
+    return FBS_OK;
+}
+extern "C" int fbs_set_peers(fbs_ctx *c, uint64_t *const *peer_wires, int32_t n_peers)
+{
+    if (!c || n_peers < 0 || n_peers > 8 || (n_peers && !peer_wires)) return fail(FBS_ERR_ARG, "fbs_set_peers: at most 8 peers");
+    c->n_peers = n_peers;
+    for (int i = 0; i < n_peers; i++) c->peers[i] = peer_wires[i];
     return FBS_OK;
 }

@@ -447,6 +447,9 @@ struct BRArgs {
     u64 *wires; u64 *tap_acc;
     long long B, jobs;
     int node_begin, lc_begin, n, p, beta;
+    u32 zero;                           // always 0; unknown to ptxas, see ntt.cuh (pins adds to the ALU pipe)
+    int n_peers;                        // node-sharded multi-GPU: replicas of the wire buffer on the other GPUs
+    u64 *peer_wires[8];                 // (peer-mapped pointers, same layout): the sample-extract epilogue stores to all
 };
 template <int LOGN, int K, int L, bool BSK_SMEM, int PB>
 struct BRCfg {
@@ -558,7 +561,7 @@ __global__ void __launch_bounds__(PB * (K + 1) * (1 << LOGN) / 8 * BR_LB_MULT, 1
         // ---- forward NTTs through the group's scratch polynomial; spectra to DH (swizzled, layout lb = 0)
 #pragma unroll
         for (int jj = 0; jj < L; jj++) {
-            ntt_fwd1_from<LOGN, 0>(dg[jj], tau, sg, a.psi_rev, gsync, jj == 0);
+            ntt_fwd1_from<LOGN, 0>(dg[jj], tau, sg, a.psi_rev, gsync, jj == 0, a.zero);
             u64 *dh = DH + (size_t)(g * L + jj) * N;
             if (L == 1 && P::NPASS > 1) gsync();            // DH aliases S: the last transpose's readers are done
 #pragma unroll
@@ -605,7 +608,7 @@ __global__ void __launch_bounds__(PB * (K + 1) * (1 << LOGN) / 8 * BR_LB_MULT, 1
                 for (int q = 0; q < G * L * G; q++) tma_load_1d(BS + (size_t)q * N, src + (size_t)q * N, N * 8, mbar);
             }
         };
-        ntt_inv1_from<LOGN, 0>(x, tau, sg, a.psi_inv_rev, after_pass0, gsync);
+        ntt_inv1_from<LOGN, 0>(x, tau, sg, a.psi_inv_rev, after_pass0, gsync, a.zero);
 #pragma unroll
         for (int e = 0; e < 8; e++) {
             const int j = P::idx(tau, e, P::inv_lb(P::NPASS - 1));
@@ -616,17 +619,27 @@ __global__ void __launch_bounds__(PB * (K + 1) * (1 << LOGN) / 8 * BR_LB_MULT, 1
         }
         gsync();                                         // ACC_g is only read by group g (next step's rotation)
     }
-    // ---- K3: sample extraction of coefficient 0 (+ table-mode offset s*Delta/2 on the body); CRT back to integers
+    // ---- K3: sample extraction of coefficient 0 (+ table-mode offset s*Delta/2 on the body); CRT back to integers.
+    // Fused exchange for node-sharded levels: besides the local wire buffer the extracted ciphertext is stored straight
+    // into every peer GPU's replica (NVLink peer stores), so no separate all-gather pass over the level's outputs is
+    // needed -- the host only barriers between levels (tfhe_fbs_map_b200/dist.py).
     psync();
     if (live) {
         const size_t CT = (size_t)K * N + 1;
-        u64 *out = a.wires + ((size_t)a.bs_slot[node] * a.B + inst) * CT;
+        const size_t off = ((size_t)a.bs_slot[node] * a.B + inst) * CT;
+        u64 *out = a.wires + off;
         for (int w = ptid; w < K * N; w += C::PT) {
             const int u = w / N, j = w % N;
             const rns2 v = rns_unpack(ACC[(size_t)u * N + (j == 0 ? 0 : N - j)]);
-            out[w] = rns_to_int(j == 0 ? v : rns_neg(v));
+            const u64 val = rns_to_int(j == 0 ? v : rns_neg(v));
+            out[w] = val;
+            for (int pr = 0; pr < a.n_peers; pr++) a.peer_wires[pr][off + w] = val;
         }
-        if (ptid == 0) out[(size_t)K * N] = fq_add(rns_to_int(rns_unpack(ACC[(size_t)K * N])), fq_mul((u64)mode, fbs_delta(p) >> 1));
+        if (ptid == 0) {
+            const u64 val = fq_add(rns_to_int(rns_unpack(ACC[(size_t)K * N])), fq_mul((u64)mode, fbs_delta(p) >> 1));
+            out[(size_t)K * N] = val;
+            for (int pr = 0; pr < a.n_peers; pr++) a.peer_wires[pr][off + (size_t)K * N] = val;
+        }
         if (a.tap_acc) {
             u64 *t = a.tap_acc + (size_t)job * G * N;
             for (int w = ptid; w < G * N; w += C::PT) t[w] = rns_to_int(rns_unpack(ACC[w]));

@@ -53,8 +53,12 @@ FQ_HD fq_tw fq_tw_load(const fq_tw *p)
 #endif
 }
 
+// ptxas balances 2-input integer adds between IADD3 (ALU pipe) and IMAD.IADD (FMA-heavy pipe) assuming equal pipe
+// load; in these kernels the FMA-heavy pipe is the busier one (IMAD, IMAD.HI).  Adding a zero that only exists at run
+// time (a kernel argument) makes the add 3-input, which only IADD3 can do, and pins it to the ALU pipe.
+struct NttZero { u32 z; };
 template <int LOGN, int PASS>
-FQ_HD void ntt_fwd_pass(rns2 (&x)[8], int tau, const fq_tw *__restrict__ psi_rev)
+FQ_HD void ntt_fwd_pass(rns2 (&x)[8], int tau, const fq_tw *__restrict__ psi_rev, u32 z = 0)
 {
     using P = NttPlan<LOGN>;
     constexpr int hi = P::fwd_hi(PASS), lb = P::fwd_lb(PASS);
@@ -70,14 +74,14 @@ FQ_HD void ntt_fwd_pass(rns2 (&x)[8], int tau, const fq_tw *__restrict__ psi_rev
             const fq_tw w = fq_tw_load(psi_rev + m + ((th << (2 - q)) | (e0 >> (q + 1))));
             const u32 ua = r32_fold(x[e0].a, 2 * FQ_P1), va = r32_mul_shoup(x[e1].a, w.w1, w.ws1, FQ_P1);
             const u32 ub = r32_fold(x[e0].b, 2 * FQ_P2), vb = r32_mul_shoup(x[e1].b, w.w2, w.ws2, FQ_P2);
-            x[e0].a = ua + va; x[e1].a = ua - va + 2 * FQ_P1;
-            x[e0].b = ub + vb; x[e1].b = ub - vb + 2 * FQ_P2;
+            x[e0].a = ua + va + z; x[e1].a = ua - va + 2 * FQ_P1;
+            x[e0].b = ub + vb + z; x[e1].b = ub - vb + 2 * FQ_P2;
         }
     }
 }
 // ---- one inverse pass on registers ---------------------------------------------------------------------
 template <int LOGN, int PASS>
-FQ_HD void ntt_inv_pass(rns2 (&x)[8], int tau, const fq_tw *__restrict__ psi_inv_rev)
+FQ_HD void ntt_inv_pass(rns2 (&x)[8], int tau, const fq_tw *__restrict__ psi_inv_rev, u32 z = 0)
 {
     using P = NttPlan<LOGN>;
     constexpr int lo = P::inv_lo(PASS), lb = P::inv_lb(PASS);
@@ -92,9 +96,9 @@ FQ_HD void ntt_inv_pass(rns2 (&x)[8], int tau, const fq_tw *__restrict__ psi_inv
             const int e1 = e0 | (1 << q);
             const fq_tw w = fq_tw_load(psi_inv_rev + m + ((th << (2 - q)) | (e0 >> (q + 1))));
             const u32 ua = x[e0].a, va = x[e1].a, ub = x[e0].b, vb = x[e1].b;
-            x[e0].a = r32_fold(ua + va, 2 * FQ_P1);
+            x[e0].a = r32_fold(ua + va + z, 2 * FQ_P1);
             x[e1].a = r32_mul_shoup(ua - va + 2 * FQ_P1, w.w1, w.ws1, FQ_P1);
-            x[e0].b = r32_fold(ub + vb, 2 * FQ_P2);
+            x[e0].b = r32_fold(ub + vb + z, 2 * FQ_P2);
             x[e1].b = r32_mul_shoup(ub - vb + 2 * FQ_P2, w.w2, w.ws2, FQ_P2);
         }
     }
@@ -129,10 +133,10 @@ __device__ __forceinline__ void ntt_forward(rns2 (&x)[8], int tau, u64 *bufA, u6
 // ---- single-buffer variants: one scratch polynomial per thread group, two barriers per transpose -----------
 // (used by the blind-rotate kernel, where shared memory rather than barrier count limits residency)
 template <int LOGN, int PASS, class Sync>
-__device__ __forceinline__ void ntt_fwd1_from(rns2 (&x)[8], int tau, u64 *buf, const fq_tw *psi_rev, Sync sync, bool buf_free)
+__device__ __forceinline__ void ntt_fwd1_from(rns2 (&x)[8], int tau, u64 *buf, const fq_tw *psi_rev, Sync sync, bool buf_free, u32 z = 0)
 {
     using P = NttPlan<LOGN>;
-    ntt_fwd_pass<LOGN, PASS>(x, tau, psi_rev);
+    ntt_fwd_pass<LOGN, PASS>(x, tau, psi_rev, z);
     if constexpr (PASS + 1 < P::NPASS) {
         constexpr int lb0 = P::fwd_lb(PASS), lb1 = P::fwd_lb(PASS + 1);
         if (!buf_free) sync();                          // earlier readers of buf are done
@@ -141,15 +145,15 @@ __device__ __forceinline__ void ntt_fwd1_from(rns2 (&x)[8], int tau, u64 *buf, c
         sync();
 #pragma unroll
         for (int e = 0; e < 8; e++) x[e] = rns_unpack(buf[P::swz(P::idx(tau, e, lb1))]);
-        ntt_fwd1_from<LOGN, PASS + 1>(x, tau, buf, psi_rev, sync, false);
+        ntt_fwd1_from<LOGN, PASS + 1>(x, tau, buf, psi_rev, sync, false, z);
     }
 }
 // inverse: pass 0 is done by the caller's registers; `after_pass0` runs between pass 0 and the first write to buf
 template <int LOGN, int PASS, class Sync0, class Sync>
-__device__ __forceinline__ void ntt_inv1_from(rns2 (&x)[8], int tau, u64 *buf, const fq_tw *psi_inv_rev, Sync0 after_pass0, Sync sync)
+__device__ __forceinline__ void ntt_inv1_from(rns2 (&x)[8], int tau, u64 *buf, const fq_tw *psi_inv_rev, Sync0 after_pass0, Sync sync, u32 z = 0)
 {
     using P = NttPlan<LOGN>;
-    ntt_inv_pass<LOGN, PASS>(x, tau, psi_inv_rev);
+    ntt_inv_pass<LOGN, PASS>(x, tau, psi_inv_rev, z);
     if constexpr (PASS == 0) after_pass0(); else if constexpr (PASS + 1 < P::NPASS) sync();
     if constexpr (PASS + 1 < P::NPASS) {
         constexpr int lb0 = P::inv_lb(PASS), lb1 = P::inv_lb(PASS + 1);
@@ -158,7 +162,7 @@ __device__ __forceinline__ void ntt_inv1_from(rns2 (&x)[8], int tau, u64 *buf, c
         sync();
 #pragma unroll
         for (int e = 0; e < 8; e++) x[e] = rns_unpack(buf[P::swz(P::idx(tau, e, lb1))]);
-        ntt_inv1_from<LOGN, PASS + 1>(x, tau, buf, psi_inv_rev, sync, sync);
+        ntt_inv1_from<LOGN, PASS + 1>(x, tau, buf, psi_inv_rev, sync, sync, z);
     }
 }
 

@@ -67,6 +67,63 @@ class B200Engine:
         return self.wires[slot_begin * per:(slot_begin + n_slots) * per]
 
 
+class FusedB200Engine(B200Engine):
+    """Node-sharded engine whose blind-rotation epilogue stores every output ciphertext into all peers' wire replicas
+    (peer-mapped NVLink stores): the compute step and the exchange are ONE kernel, the host only barriers per level.
+    The wire buffer is a cudaMalloc allocation of the library, shared between the per-GPU processes by CUDA IPC."""
+
+    fused = True
+
+    def __init__(self, backend, cprog, B, torch_mod, dist, world, rank):
+        self.be, self.cp, self.B, self.torch = backend, cprog, B, torch_mod
+        self.ct_words = backend.params.ct_words
+        self.stream = torch_mod.cuda.current_stream().cuda_stream
+        self.nbytes = backend.wires_bytes(cprog, B)
+        self.ptr = backend.wires_alloc(self.nbytes)
+        handles = [None] * world
+        dist.all_gather_object(handles, backend.ipc_export(self.ptr))
+        self.peer_ptrs = [backend.ipc_import(h) for r, h in enumerate(handles) if r != rank]
+        backend.set_peers(self.peer_ptrs)
+        self.dist, self.world, self.rank = dist, world, rank
+
+    class _Ptr:
+        def __init__(self, p):
+            self.p = p
+
+        def data_ptr(self):
+            return self.p
+
+    @property
+    def wires(self):
+        return FusedB200Engine._Ptr(self.ptr)
+
+    def encrypt(self, bits, inst_offset=0, total=None):
+        d_in = self.torch.from_numpy(np.ascontiguousarray(bits, dtype=np.uint8)).cuda()
+        self.be.encrypt_inputs(self.cp, d_in.data_ptr(), self.B, self.ptr, stream=self.stream, inst_offset=inst_offset, total=total or self.B)
+        self.torch.cuda.synchronize()
+
+    def run_level(self, level, node_begin, node_end):
+        self.be.run_level(self.cp, level, self.B, self.ptr, node_begin, node_end, stream=self.stream)
+
+    def decrypt(self):
+        n_out = len(self.cp.program.output_names)
+        d_out = self.torch.empty((n_out, self.B), dtype=self.torch.uint8, device="cuda")
+        self.be.decrypt_outputs(self.cp, self.B, self.ptr, d_out.data_ptr(), stream=self.stream)
+        self.torch.cuda.synchronize()
+        return d_out.cpu().numpy()
+
+    def level_barrier(self):
+        self.torch.cuda.synchronize()          # this rank's peer stores are complete ...
+        self.dist.barrier()                    # ... and so are everybody else's
+
+    def close(self):
+        self.be.set_peers([])
+        for p in self.peer_ptrs:
+            self.be.ipc_close(p)
+        self.dist.barrier()
+        self.be.wires_free(self.ptr)
+
+
 def run_node_sharded(engine, program, dist, world: int, rank: int, in_place: bool = True):
     """Evaluate all levels with the bootstraps of each level split over ``world`` ranks and an all-gather of the new
     output ciphertexts after every level.  ``program`` must come from ``levelize(..., shard_pad=world)``.
@@ -82,6 +139,10 @@ def run_node_sharded(engine, program, dist, world: int, rank: int, in_place: boo
         if ne > nb:
             engine.run_level(lv, nb, ne)
         if world == 1:
+            continue
+        if getattr(engine, "fused", False):      # outputs already sit in every replica: only order the levels
+            engine.level_barrier()
+            exchanged += chunk * world * engine.B * engine.ct_words
             continue
         first_slot = int(a["bs_slot"][b0])
         region = engine.slot_view(first_slot, chunk * world)
