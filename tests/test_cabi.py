@@ -39,7 +39,7 @@ def test_library_exports_every_declared_symbol(libpath):
 def test_library_is_sm100a_with_tma(libpath):
     out = subprocess.run(["cuobjdump", "-lelf", libpath], capture_output=True, text=True).stdout
     assert "sm_100a" in out
-    sass = subprocess.run(["cuobjdump", "-sass", "-fun", "_Z14k_blind_rotateILi11ELi1ELi1ELb1ELi2EEv6BRArgs", libpath],
+    sass = subprocess.run(["cuobjdump", "-sass", "-fun", "_Z14k_blind_rotateILi11ELi1ELi1ELb1ELi2ELi2EEv6BRArgs", libpath],
                           capture_output=True, text=True).stdout
     assert "UBLKCP" in sass          # cp.async.bulk = TMA bulk copy streams the bootstrapping key
     assert "IMAD.WIDE" in sass       # the arithmetic runs on the integer pipes

@@ -28,28 +28,31 @@ extern "C" int fbs_abi_version(void) { return 1; }
 // blind-rotate kernel variants
 // ------------------------------------------------------------------------------------------------------
 typedef cudaError_t (*br_launch_fn)(const BRArgs &, long long jobs, size_t smem, cudaStream_t);
-struct BRVariant { int logN, k, l; bool bsk_smem; int pb, threads; size_t (*smem)(int n); br_launch_fn launch; cudaError_t (*prepare)(size_t smem); };
+struct BRVariant { int logN, k, l; bool bsk_smem; int pb, tp, threads; size_t (*smem)(int n); br_launch_fn launch; cudaError_t (*prepare)(size_t smem); };
 
-template <int LOGN, int K, int L, bool SM, int PB>
+template <int LOGN, int K, int L, bool SM, int PB, int TP>
 static cudaError_t br_launch(const BRArgs &a, long long jobs, size_t smem, cudaStream_t st)
 {
     const long long grid = (jobs + PB - 1) / PB;
-    k_blind_rotate<LOGN, K, L, SM, PB><<<(unsigned)grid, BRCfg<LOGN, K, L, SM, PB>::THREADS, smem, st>>>(a);
+    k_blind_rotate<LOGN, K, L, SM, PB, TP><<<(unsigned)grid, BRCfg<LOGN, K, L, SM, PB, TP>::THREADS, smem, st>>>(a);
     return cudaGetLastError();
 }
-template <int LOGN, int K, int L, bool SM, int PB>
+template <int LOGN, int K, int L, bool SM, int PB, int TP>
 static cudaError_t br_prepare(size_t smem)
 {
-    return cudaFuncSetAttribute(k_blind_rotate<LOGN, K, L, SM, PB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    return cudaFuncSetAttribute(k_blind_rotate<LOGN, K, L, SM, PB, TP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 }
-template <int LOGN, int K, int L, bool SM, int PB> static size_t br_smem(int n) { return BRCfg<LOGN, K, L, SM, PB>::smem_bytes(n); }
-#define BRV(LOGN, K, L, SM, PB) { LOGN, K, L, SM, PB, BRCfg<LOGN, K, L, SM, PB>::THREADS, br_smem<LOGN, K, L, SM, PB>, br_launch<LOGN, K, L, SM, PB>, br_prepare<LOGN, K, L, SM, PB> }
+template <int LOGN, int K, int L, bool SM, int PB, int TP> static size_t br_smem(int n) { return BRCfg<LOGN, K, L, SM, PB, TP>::smem_bytes(n); }
+#define BRV(LOGN, K, L, SM, PB, TP) { LOGN, K, L, SM, PB, TP, BRCfg<LOGN, K, L, SM, PB, TP>::THREADS, br_smem<LOGN, K, L, SM, PB, TP>, br_launch<LOGN, K, L, SM, PB, TP>, br_prepare<LOGN, K, L, SM, PB, TP> }
+#ifndef FBS_SETA_TP
+#define FBS_SETA_TP 2     /* bootstraps per thread in the set-A kernel: 2 = every thread carries both bootstraps of its CTA */
+#endif
 static const BRVariant g_br_variants[] = {
-    BRV(11, 1, 1, true, 2),    // set A: two bootstraps per CTA share the TMA-streamed BSK row (192 KB shared memory)
-    BRV(11, 1, 1, true, 1),    // set A, one bootstrap per CTA: used when a launch has no more jobs than SMs
-    BRV(11, 1, 2, false, 1),   // set C (row does not fit shared memory next to the accumulator: BSK read from L2)
-    BRV(10, 2, 1, true, 1),    // set S
-    BRV(8, 1, 2, true, 2), BRV(8, 2, 1, true, 2), BRV(9, 1, 1, true, 2), BRV(10, 1, 3, true, 1),   // toy sets (tests)
+    BRV(11, 1, 1, true, 2, FBS_SETA_TP),   // set A: two bootstraps per CTA share the TMA-streamed BSK row (192 KB shared memory)
+    BRV(11, 1, 1, true, 1, 1),             // set A, one bootstrap per CTA: used when a launch has no more jobs than SMs
+    BRV(11, 1, 2, false, 1, 1),            // set C (row does not fit shared memory next to the accumulator: BSK read from L2)
+    BRV(10, 2, 1, true, 1, 1),             // set S
+    BRV(8, 1, 2, true, 2, 2), BRV(8, 2, 1, true, 2, 1), BRV(9, 1, 1, true, 2, 2), BRV(10, 1, 3, true, 1, 1),   // toy sets (tests)
 };
 
 typedef void (*ntt_launch_fn)(const u64 *, u64 *, int, const fq_tw *, const fq_tw *, u32, u32, long long, cudaStream_t);

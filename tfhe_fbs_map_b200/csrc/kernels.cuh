@@ -451,9 +451,12 @@ struct BRArgs {
     int n_peers;                        // node-sharded multi-GPU: replicas of the wire buffer on the other GPUs
     u64 *peer_wires[8];                 // (peer-mapped pointers, same layout): the sample-extract epilogue stores to all
 };
-template <int LOGN, int K, int L, bool BSK_SMEM, int PB>
+// TP = bootstraps carried by each thread (1, or PB: every thread works on all PB bootstraps of the CTA, so twiddle loads,
+// BSK reads, index arithmetic and barriers are shared between them and the instruction-level parallelism doubles).
+template <int LOGN, int K, int L, bool BSK_SMEM, int PB, int TP>
 struct BRCfg {
-    static constexpr int N = 1 << LOGN, G = K + 1, T = N / 8, PT = G * T, THREADS = PB * PT;
+    static_assert(TP == 1 || TP == PB, "a thread carries one bootstrap or all of the CTA's");
+    static constexpr int N = 1 << LOGN, G = K + 1, T = N / 8, PT = G * T, THREADS = (PB / TP) * PT;
     static constexpr size_t acc_w = (size_t)G * N, s_w = (size_t)G * N;
     static constexpr size_t dh_w = (L == 1) ? 0 : (size_t)G * L * N;
     static constexpr size_t per_pbs_w = acc_w + s_w + dh_w;
@@ -467,37 +470,39 @@ struct BRCfg {
     }
 };
 
-#ifndef BR_LB_MULT
-#define BR_LB_MULT 1      /* experiment knob: pretend the CTA is this many times larger to cap registers */
-#endif
-template <int LOGN, int K, int L, bool BSK_SMEM, int PB>
-__global__ void __launch_bounds__(PB * (K + 1) * (1 << LOGN) / 8 * BR_LB_MULT, 1) k_blind_rotate(BRArgs a)
+template <int LOGN, int K, int L, bool BSK_SMEM, int PB, int TP>
+__global__ void __launch_bounds__((PB / TP) * (K + 1) * (1 << LOGN) / 8, 1) k_blind_rotate(BRArgs a)
 {
-    using C = BRCfg<LOGN, K, L, BSK_SMEM, PB>;
+    using C = BRCfg<LOGN, K, L, BSK_SMEM, PB, TP>;
     using P = NttPlan<LOGN>;
     constexpr int N = C::N, G = C::G, T = C::T;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const int tid = threadIdx.x, pb = tid / C::PT, ptid = tid % C::PT, g = ptid / T, tau = ptid % T;
-    u64 *base = (u64 *)smem_raw + (size_t)pb * C::per_pbs_w;
+    const int tid = threadIdx.x, pb0 = (TP == 1) ? tid / C::PT : 0, ptid = tid % C::PT, g = ptid / T, tau = ptid % T;
+    u64 *base = (u64 *)smem_raw + (size_t)pb0 * C::per_pbs_w;   // bootstrap q of this thread lives at base + q*per_pbs_w
     u64 *ACC = base;
     u64 *S = ACC + C::acc_w;
     u64 *DH = (L == 1) ? S : S + C::s_w;
     u64 *BS = (u64 *)smem_raw + (size_t)PB * C::per_pbs_w;
     u64 *mbar = BS + C::bs_w;
     const size_t ms_stride = C::ms_stride(a.n);
-    u16 *s_ms = (u16 *)((unsigned char *)(mbar + 2) + (size_t)pb * ms_stride);
-
-    // the second bootstrap of the last CTA may not exist: it recomputes the previous job and skips the store
-    long long job = (long long)blockIdx.x * PB + pb;
-    const bool live = job < a.jobs;
-    if (!live) job = a.jobs - 1;
-    const int node = a.node_begin + (int)(job / a.B);
-    const long long inst = job % a.B;
+    u16 *s_ms = (u16 *)((unsigned char *)(mbar + 2) + (size_t)pb0 * ms_stride);
+    constexpr size_t PW = C::per_pbs_w;
     const int n = a.n, p = a.p;
-    const u16 *ms = a.ms + ((size_t)(a.bs_lc[node] - a.lc_begin) * a.B + inst) * (size_t)(n + 1);
-    const int tab0 = a.bs_tab_ptr[node], tabL = a.bs_tab_ptr[node + 1] - tab0, mode = a.bs_mode[node];
 
-    for (int i = ptid; i <= n; i += C::PT) s_ms[i] = ms[i];
+    // a bootstrap slot beyond the job list recomputes the last job and skips the store
+    bool live[TP]; int node[TP], tabL[TP], tab0[TP], mode[TP]; long long inst[TP], job[TP];
+#pragma unroll
+    for (int q = 0; q < TP; q++) {
+        job[q] = (long long)blockIdx.x * PB + pb0 + q;
+        live[q] = job[q] < a.jobs;
+        if (!live[q]) job[q] = a.jobs - 1;
+        node[q] = a.node_begin + (int)(job[q] / a.B);
+        inst[q] = job[q] % a.B;
+        const u16 *ms = a.ms + ((size_t)(a.bs_lc[node[q]] - a.lc_begin) * a.B + inst[q]) * (size_t)(n + 1);
+        tab0[q] = a.bs_tab_ptr[node[q]]; tabL[q] = a.bs_tab_ptr[node[q] + 1] - tab0[q]; mode[q] = a.bs_mode[node[q]];
+        u16 *dst = (u16 *)((unsigned char *)s_ms + (size_t)q * ms_stride);
+        for (int i = ptid; i <= n; i += C::PT) dst[i] = ms[i];
+    }
     if (BSK_SMEM && tid == 0) mbar_init(mbar, 1);
     __syncthreads();
     if (BSK_SMEM && tid == 0) {
@@ -509,9 +514,10 @@ __global__ void __launch_bounds__(PB * (K + 1) * (1 << LOGN) / 8 * BR_LB_MULT, 1
     // ---- accumulator init: ACC = (0, .., 0, X^{-b~} * TV) ; TV[j] = F(round(j*p/N)), F(x) = tv[x]*Delta - s*Delta/2
     // The accumulator lives in shared memory as packed residue pairs (mod p1 | mod p2 << 32), canonical.
     u64 *acc = ACC + (size_t)g * N;
-    {
-        const u64 delta = fbs_delta(p), off = fq_mul((u64)mode, delta >> 1);
-        const int bt = s_ms[n];
+#pragma unroll
+    for (int q = 0; q < TP; q++) {
+        const u64 delta = fbs_delta(p), off = fq_mul((u64)mode[q], delta >> 1);
+        const int bt = ((const u16 *)((const unsigned char *)s_ms + (size_t)q * ms_stride))[n];
 #pragma unroll
         for (int e = 0; e < 8; e++) {
             const int j = tau + e * T;
@@ -523,77 +529,89 @@ __global__ void __launch_bounds__(PB * (K + 1) * (1 << LOGN) / 8 * BR_LB_MULT, 1
                 if (src >= N) { src -= N; neg = true; }
                 int x = (int)((2LL * src * p + N) / (2LL * N));
                 if (x >= p) { x -= p; neg = !neg; }
-                const u64 tvx = (x < tabL) ? (u64)__ldg(a.bs_tab + tab0 + x) : 0;
+                const u64 tvx = (x < tabL[q]) ? (u64)__ldg(a.bs_tab + tab0[q] + x) : 0;
                 const u64 F = fq_sub(fq_mul(tvx, delta), off);
                 val = neg ? fq_neg(F) : F;
             }
-            acc[j] = rns_pack(rns_from_int(val));
+            acc[q * PW + j] = rns_pack(rns_from_int(val));
         }
     }
     __syncthreads();
 
-    const int bar_g = 1 + pb * G + g, bar_p = 1 + PB * G + pb;      // named barriers: per group, per bootstrap
+    const int bar_g = 1 + pb0 * G + g, bar_p = 1 + PB * G + pb0;    // named barriers: per group, per bootstrap
     auto gsync = [bar_g] { bar_sync_named(bar_g, T); };
-    auto psync = [bar_p] { bar_sync_named(bar_p, C::PT); };
+    auto psync = [bar_p] { if (TP == 1) bar_sync_named(bar_p, C::PT); else __syncthreads(); };
     u64 *sg = S + (size_t)g * N;
     const int beta = a.beta, bits = beta * L;
 
     for (int i = 0; i < n; i++) {
-        const int ai = s_ms[i];
         // ---- rotate, subtract, decompose: digits of (X^{ai} ACC_g - ACC_g) in the first forward layout.
         // Only the high mixed-radix digit t = floor(x / p1) of the difference is needed for the rounding (<= 24 bits).
-        rns2 dg[L][8];
+        rns2 dg[L][TP][8];
 #pragma unroll
-        for (int e = 0; e < 8; e++) {
-            const int j = tau + e * T;
-            int src = j - ai;
-            if (src < 0) src += 2 * N;
-            rns2 rot = rns_unpack(acc[src < N ? src : src - N]);
-            if (src >= N) rot = rns_neg(rot);
-            const rns2 diff = rns_sub(rot, rns_unpack(acc[j]));
-            const u32 t = rns_crt_hi(diff);
-            const u64 y = (bits <= 24) ? fbs_round_top_t(t, diff.a, bits) : fbs_round_top((u64)diff.a + (u64)FQ_P1 * t, bits);
-            int d[L];
-            fbs_balanced_digits<L>(y, beta, d);
+        for (int q = 0; q < TP; q++) {
+            const int ai = ((const u16 *)((const unsigned char *)s_ms + (size_t)q * ms_stride))[i];
+            const u64 *ac = acc + q * PW;
 #pragma unroll
-            for (int jj = 0; jj < L; jj++) dg[jj][e] = rns_from_small(d[jj]);
+            for (int e = 0; e < 8; e++) {
+                const int j = tau + e * T;
+                int src = j - ai;
+                if (src < 0) src += 2 * N;
+                rns2 rot = rns_unpack(ac[src < N ? src : src - N]);
+                if (src >= N) rot = rns_neg(rot);
+                const rns2 diff = rns_sub(rot, rns_unpack(ac[j]));
+                const u32 t = rns_crt_hi(diff);
+                const u64 y = (bits <= 24) ? fbs_round_top_t(t, diff.a, bits) : fbs_round_top((u64)diff.a + (u64)FQ_P1 * t, bits);
+                int d[L];
+                fbs_balanced_digits<L>(y, beta, d);
+#pragma unroll
+                for (int jj = 0; jj < L; jj++) dg[jj][q][e] = rns_from_small(d[jj]);
+            }
         }
         // ---- forward NTTs through the group's scratch polynomial; spectra to DH (swizzled, layout lb = 0)
 #pragma unroll
         for (int jj = 0; jj < L; jj++) {
-            ntt_fwd1_from<LOGN, 0>(dg[jj], tau, sg, a.psi_rev, gsync, jj == 0, a.zero);
+            ntt_fwd1_from<LOGN, 0, TP>(dg[jj], tau, sg, PW, a.psi_rev, gsync, jj == 0, a.zero);
             u64 *dh = DH + (size_t)(g * L + jj) * N;
             if (L == 1 && P::NPASS > 1) gsync();            // DH aliases S: the last transpose's readers are done
 #pragma unroll
-            for (int e = 0; e < 8; e++) dh[P::swz(P::idx(tau, e, 0))] = rns_pack(dg[jj][e]);
+            for (int e = 0; e < 8; e++) {
+                const int id = P::swz(P::idx(tau, e, 0));
+#pragma unroll
+                for (int q = 0; q < TP; q++) dh[q * PW + id] = rns_pack(dg[jj][q][e]);
+            }
         }
         psync();
         // ---- pointwise: out_g = sum_r DH[r] * BSK[r][g], per prime.  DH is lazy (< 4p), the key is canonical and in
         // Montgomery form: a PAIR of 64-bit products (< 8p^2 < 2^63) is reduced by one REDC to < 3p, then folded to < 2p.
+        // The key word is read once and used for every bootstrap the thread carries.
         if (BSK_SMEM) mbar_wait(mbar, (u32)(i & 1));
-        rns2 x[8];
+        rns2 x[TP][8];
         {
             const u64 *brow = BSK_SMEM ? BS : a.bsk + (size_t)i * C::row_w;
 #pragma unroll
             for (int e = 0; e < 8; e++) {
                 const int id = P::swz(P::idx(tau, e, 0));
-                rns2 s;
-                s.a = 0; s.b = 0;
 #pragma unroll
                 for (int r = 0; r < G * L; r += 2) {
-                    const rns2 d0 = rns_unpack(DH[(size_t)r * N + id]), k0 = rns_unpack(brow[((size_t)r * G + g) * N + id]);
-                    u64 pa = (u64)d0.a * k0.a, pb2 = (u64)d0.b * k0.b;
-                    if (r + 1 < G * L) {
-                        const rns2 d1 = rns_unpack(DH[(size_t)(r + 1) * N + id]), k1 = rns_unpack(brow[((size_t)(r + 1) * G + g) * N + id]);
-                        pa += (u64)d1.a * k1.a;
-                        pb2 += (u64)d1.b * k1.b;
+                    const rns2 k0 = rns_unpack(brow[((size_t)r * G + g) * N + id]);
+                    rns2 k1; k1.a = 0; k1.b = 0;
+                    if (r + 1 < G * L) k1 = rns_unpack(brow[((size_t)(r + 1) * G + g) * N + id]);
+#pragma unroll
+                    for (int q = 0; q < TP; q++) {
+                        const rns2 d0 = rns_unpack(DH[q * PW + (size_t)r * N + id]);
+                        u64 pa = (u64)d0.a * k0.a, pb2 = (u64)d0.b * k0.b;
+                        if (r + 1 < G * L) {
+                            const rns2 d1 = rns_unpack(DH[q * PW + (size_t)(r + 1) * N + id]);
+                            pa += (u64)d1.a * k1.a;
+                            pb2 += (u64)d1.b * k1.b;
+                        }
+                        const u32 ta = r32_fold(r32_redc(pa, FQ_P1, FQ_P1_INVNEG), 2 * FQ_P1);
+                        const u32 tb = r32_fold(r32_redc(pb2, FQ_P2, FQ_P2_INVNEG), 2 * FQ_P2);
+                        x[q][e].a = (r == 0) ? ta : r32_fold(x[q][e].a + ta, 2 * FQ_P1);
+                        x[q][e].b = (r == 0) ? tb : r32_fold(x[q][e].b + tb, 2 * FQ_P2);
                     }
-                    const u32 ta = r32_fold(r32_redc(pa, FQ_P1, FQ_P1_INVNEG), 2 * FQ_P1);
-                    const u32 tb = r32_fold(r32_redc(pb2, FQ_P2, FQ_P2_INVNEG), 2 * FQ_P2);
-                    s.a = (r == 0) ? ta : r32_fold(s.a + ta, 2 * FQ_P1);
-                    s.b = (r == 0) ? tb : r32_fold(s.b + tb, 2 * FQ_P2);
                 }
-                x[e] = s;                                  // < 2p per prime: what the inverse butterflies expect
             }
         }
         // ---- inverse NTT.  After its first register pass a CTA-wide barrier guarantees that nobody reads DH / BS of
@@ -608,14 +626,17 @@ __global__ void __launch_bounds__(PB * (K + 1) * (1 << LOGN) / 8 * BR_LB_MULT, 1
                 for (int q = 0; q < G * L * G; q++) tma_load_1d(BS + (size_t)q * N, src + (size_t)q * N, N * 8, mbar);
             }
         };
-        ntt_inv1_from<LOGN, 0>(x, tau, sg, a.psi_inv_rev, after_pass0, gsync, a.zero);
+        ntt_inv1_from<LOGN, 0, TP>(x, tau, sg, PW, a.psi_inv_rev, after_pass0, gsync, a.zero);
 #pragma unroll
         for (int e = 0; e < 8; e++) {
             const int j = P::idx(tau, e, P::inv_lb(P::NPASS - 1));
-            rns2 v;
-            v.a = r32_csub(x[e].a, FQ_P1);
-            v.b = r32_csub(x[e].b, FQ_P2);
-            acc[j] = rns_pack(rns_add(rns_unpack(acc[j]), v));
+#pragma unroll
+            for (int q = 0; q < TP; q++) {
+                rns2 v;
+                v.a = r32_csub(x[q][e].a, FQ_P1);
+                v.b = r32_csub(x[q][e].b, FQ_P2);
+                acc[q * PW + j] = rns_pack(rns_add(rns_unpack(acc[q * PW + j]), v));
+            }
         }
         gsync();                                         // ACC_g is only read by group g (next step's rotation)
     }
@@ -624,25 +645,28 @@ __global__ void __launch_bounds__(PB * (K + 1) * (1 << LOGN) / 8 * BR_LB_MULT, 1
     // into every peer GPU's replica (NVLink peer stores), so no separate all-gather pass over the level's outputs is
     // needed -- the host only barriers between levels (tfhe_fbs_map_b200/dist.py).
     psync();
-    if (live) {
+#pragma unroll
+    for (int q = 0; q < TP; q++) {
+        if (!live[q]) continue;
+        const u64 *A = ACC + q * PW;
         const size_t CT = (size_t)K * N + 1;
-        const size_t off = ((size_t)a.bs_slot[node] * a.B + inst) * CT;
+        const size_t off = ((size_t)a.bs_slot[node[q]] * a.B + inst[q]) * CT;
         u64 *out = a.wires + off;
         for (int w = ptid; w < K * N; w += C::PT) {
             const int u = w / N, j = w % N;
-            const rns2 v = rns_unpack(ACC[(size_t)u * N + (j == 0 ? 0 : N - j)]);
+            const rns2 v = rns_unpack(A[(size_t)u * N + (j == 0 ? 0 : N - j)]);
             const u64 val = rns_to_int(j == 0 ? v : rns_neg(v));
             out[w] = val;
             for (int pr = 0; pr < a.n_peers; pr++) a.peer_wires[pr][off + w] = val;
         }
         if (ptid == 0) {
-            const u64 val = fq_add(rns_to_int(rns_unpack(ACC[(size_t)K * N])), fq_mul((u64)mode, fbs_delta(p) >> 1));
+            const u64 val = fq_add(rns_to_int(rns_unpack(A[(size_t)K * N])), fq_mul((u64)mode[q], fbs_delta(p) >> 1));
             out[(size_t)K * N] = val;
             for (int pr = 0; pr < a.n_peers; pr++) a.peer_wires[pr][off + (size_t)K * N] = val;
         }
         if (a.tap_acc) {
-            u64 *t = a.tap_acc + (size_t)job * G * N;
-            for (int w = ptid; w < G * N; w += C::PT) t[w] = rns_to_int(rns_unpack(ACC[w]));
+            u64 *t = a.tap_acc + (size_t)job[q] * G * N;
+            for (int w = ptid; w < G * N; w += C::PT) t[w] = rns_to_int(rns_unpack(A[w]));
         }
     }
 }

@@ -57,8 +57,9 @@ FQ_HD fq_tw fq_tw_load(const fq_tw *p)
 // load; in these kernels the FMA-heavy pipe is the busier one (IMAD, IMAD.HI).  Adding a zero that only exists at run
 // time (a kernel argument) makes the add 3-input, which only IADD3 can do, and pins it to the ALU pipe.
 struct NttZero { u32 z; };
-template <int LOGN, int PASS>
-FQ_HD void ntt_fwd_pass(rns2 (&x)[8], int tau, const fq_tw *__restrict__ psi_rev, u32 z = 0)
+// NB = bootstraps per thread: the NB butterflies at one position share the twiddle load and the index arithmetic
+template <int LOGN, int PASS, int NB>
+FQ_HD void ntt_fwd_pass_n(rns2 (&x)[NB][8], int tau, const fq_tw *__restrict__ psi_rev, u32 z = 0)
 {
     using P = NttPlan<LOGN>;
     constexpr int hi = P::fwd_hi(PASS), lb = P::fwd_lb(PASS);
@@ -72,16 +73,24 @@ FQ_HD void ntt_fwd_pass(rns2 (&x)[8], int tau, const fq_tw *__restrict__ psi_rev
             if (e0 & (1 << q)) continue;
             const int e1 = e0 | (1 << q);
             const fq_tw w = fq_tw_load(psi_rev + m + ((th << (2 - q)) | (e0 >> (q + 1))));
-            const u32 ua = r32_fold(x[e0].a, 2 * FQ_P1), va = r32_mul_shoup(x[e1].a, w.w1, w.ws1, FQ_P1);
-            const u32 ub = r32_fold(x[e0].b, 2 * FQ_P2), vb = r32_mul_shoup(x[e1].b, w.w2, w.ws2, FQ_P2);
-            x[e0].a = ua + va + z; x[e1].a = ua - va + 2 * FQ_P1;
-            x[e0].b = ub + vb + z; x[e1].b = ub - vb + 2 * FQ_P2;
+#pragma unroll
+            for (int b = 0; b < NB; b++) {
+                const u32 ua = r32_fold(x[b][e0].a, 2 * FQ_P1), va = r32_mul_shoup(x[b][e1].a, w.w1, w.ws1, FQ_P1);
+                const u32 ub = r32_fold(x[b][e0].b, 2 * FQ_P2), vb = r32_mul_shoup(x[b][e1].b, w.w2, w.ws2, FQ_P2);
+                x[b][e0].a = ua + va + z; x[b][e1].a = ua - va + 2 * FQ_P1;
+                x[b][e0].b = ub + vb + z; x[b][e1].b = ub - vb + 2 * FQ_P2;
+            }
         }
     }
 }
-// ---- one inverse pass on registers ---------------------------------------------------------------------
 template <int LOGN, int PASS>
-FQ_HD void ntt_inv_pass(rns2 (&x)[8], int tau, const fq_tw *__restrict__ psi_inv_rev, u32 z = 0)
+FQ_HD void ntt_fwd_pass(rns2 (&x)[8], int tau, const fq_tw *__restrict__ psi_rev, u32 z = 0)
+{
+    ntt_fwd_pass_n<LOGN, PASS, 1>(*reinterpret_cast<rns2(*)[1][8]>(&x), tau, psi_rev, z);
+}
+// ---- one inverse pass on registers ---------------------------------------------------------------------
+template <int LOGN, int PASS, int NB>
+FQ_HD void ntt_inv_pass_n(rns2 (&x)[NB][8], int tau, const fq_tw *__restrict__ psi_inv_rev, u32 z = 0)
 {
     using P = NttPlan<LOGN>;
     constexpr int lo = P::inv_lo(PASS), lb = P::inv_lb(PASS);
@@ -95,13 +104,21 @@ FQ_HD void ntt_inv_pass(rns2 (&x)[8], int tau, const fq_tw *__restrict__ psi_inv
             if (e0 & (1 << q)) continue;
             const int e1 = e0 | (1 << q);
             const fq_tw w = fq_tw_load(psi_inv_rev + m + ((th << (2 - q)) | (e0 >> (q + 1))));
-            const u32 ua = x[e0].a, va = x[e1].a, ub = x[e0].b, vb = x[e1].b;
-            x[e0].a = r32_fold(ua + va + z, 2 * FQ_P1);
-            x[e1].a = r32_mul_shoup(ua - va + 2 * FQ_P1, w.w1, w.ws1, FQ_P1);
-            x[e0].b = r32_fold(ub + vb + z, 2 * FQ_P2);
-            x[e1].b = r32_mul_shoup(ub - vb + 2 * FQ_P2, w.w2, w.ws2, FQ_P2);
+#pragma unroll
+            for (int b = 0; b < NB; b++) {
+                const u32 ua = x[b][e0].a, va = x[b][e1].a, ub = x[b][e0].b, vb = x[b][e1].b;
+                x[b][e0].a = r32_fold(ua + va + z, 2 * FQ_P1);
+                x[b][e1].a = r32_mul_shoup(ua - va + 2 * FQ_P1, w.w1, w.ws1, FQ_P1);
+                x[b][e0].b = r32_fold(ub + vb + z, 2 * FQ_P2);
+                x[b][e1].b = r32_mul_shoup(ub - vb + 2 * FQ_P2, w.w2, w.ws2, FQ_P2);
+            }
         }
     }
+}
+template <int LOGN, int PASS>
+FQ_HD void ntt_inv_pass(rns2 (&x)[8], int tau, const fq_tw *__restrict__ psi_inv_rev, u32 z = 0)
+{
+    ntt_inv_pass_n<LOGN, PASS, 1>(*reinterpret_cast<rns2(*)[1][8]>(&x), tau, psi_inv_rev, z);
 }
 
 #if defined(__CUDACC__)
@@ -130,39 +147,56 @@ __device__ __forceinline__ void ntt_forward(rns2 (&x)[8], int tau, u64 *bufA, u6
 {
     ntt_fwd_from<LOGN, 0>(x, tau, bufA, bufB, psi_rev, sync);
 }
-// ---- single-buffer variants: one scratch polynomial per thread group, two barriers per transpose -----------
-// (used by the blind-rotate kernel, where shared memory rather than barrier count limits residency)
-template <int LOGN, int PASS, class Sync>
-__device__ __forceinline__ void ntt_fwd1_from(rns2 (&x)[8], int tau, u64 *buf, const fq_tw *psi_rev, Sync sync, bool buf_free, u32 z = 0)
+// ---- single-buffer variants: one scratch polynomial per thread group and bootstrap, two barriers per transpose ------
+// (used by the blind-rotate kernel, where shared memory rather than barrier count limits residency).  A thread may carry
+// NB bootstraps: their scratch polynomials are `stride` words apart and are transposed under the same barriers.
+template <int LOGN, int PASS, int NB, class Sync>
+__device__ __forceinline__ void ntt_fwd1_from(rns2 (&x)[NB][8], int tau, u64 *buf, size_t stride, const fq_tw *psi_rev, Sync sync, bool buf_free, u32 z = 0)
 {
     using P = NttPlan<LOGN>;
-    ntt_fwd_pass<LOGN, PASS>(x, tau, psi_rev, z);
+    ntt_fwd_pass_n<LOGN, PASS, NB>(x, tau, psi_rev, z);
     if constexpr (PASS + 1 < P::NPASS) {
         constexpr int lb0 = P::fwd_lb(PASS), lb1 = P::fwd_lb(PASS + 1);
         if (!buf_free) sync();                          // earlier readers of buf are done
 #pragma unroll
-        for (int e = 0; e < 8; e++) buf[P::swz(P::idx(tau, e, lb0))] = rns_pack(x[e]);
+        for (int e = 0; e < 8; e++) {
+            const int id = P::swz(P::idx(tau, e, lb0));
+#pragma unroll
+            for (int b = 0; b < NB; b++) buf[b * stride + id] = rns_pack(x[b][e]);
+        }
         sync();
 #pragma unroll
-        for (int e = 0; e < 8; e++) x[e] = rns_unpack(buf[P::swz(P::idx(tau, e, lb1))]);
-        ntt_fwd1_from<LOGN, PASS + 1>(x, tau, buf, psi_rev, sync, false, z);
+        for (int e = 0; e < 8; e++) {
+            const int id = P::swz(P::idx(tau, e, lb1));
+#pragma unroll
+            for (int b = 0; b < NB; b++) x[b][e] = rns_unpack(buf[b * stride + id]);
+        }
+        ntt_fwd1_from<LOGN, PASS + 1, NB>(x, tau, buf, stride, psi_rev, sync, false, z);
     }
 }
-// inverse: pass 0 is done by the caller's registers; `after_pass0` runs between pass 0 and the first write to buf
-template <int LOGN, int PASS, class Sync0, class Sync>
-__device__ __forceinline__ void ntt_inv1_from(rns2 (&x)[8], int tau, u64 *buf, const fq_tw *psi_inv_rev, Sync0 after_pass0, Sync sync, u32 z = 0)
+// inverse: `after_pass0` runs between pass 0 and the first write to buf
+template <int LOGN, int PASS, int NB, class Sync0, class Sync>
+__device__ __forceinline__ void ntt_inv1_from(rns2 (&x)[NB][8], int tau, u64 *buf, size_t stride, const fq_tw *psi_inv_rev, Sync0 after_pass0, Sync sync, u32 z = 0)
 {
     using P = NttPlan<LOGN>;
-    ntt_inv_pass<LOGN, PASS>(x, tau, psi_inv_rev, z);
+    ntt_inv_pass_n<LOGN, PASS, NB>(x, tau, psi_inv_rev, z);
     if constexpr (PASS == 0) after_pass0(); else if constexpr (PASS + 1 < P::NPASS) sync();
     if constexpr (PASS + 1 < P::NPASS) {
         constexpr int lb0 = P::inv_lb(PASS), lb1 = P::inv_lb(PASS + 1);
 #pragma unroll
-        for (int e = 0; e < 8; e++) buf[P::swz(P::idx(tau, e, lb0))] = rns_pack(x[e]);
+        for (int e = 0; e < 8; e++) {
+            const int id = P::swz(P::idx(tau, e, lb0));
+#pragma unroll
+            for (int b = 0; b < NB; b++) buf[b * stride + id] = rns_pack(x[b][e]);
+        }
         sync();
 #pragma unroll
-        for (int e = 0; e < 8; e++) x[e] = rns_unpack(buf[P::swz(P::idx(tau, e, lb1))]);
-        ntt_inv1_from<LOGN, PASS + 1>(x, tau, buf, psi_inv_rev, sync, sync, z);
+        for (int e = 0; e < 8; e++) {
+            const int id = P::swz(P::idx(tau, e, lb1));
+#pragma unroll
+            for (int b = 0; b < NB; b++) x[b][e] = rns_unpack(buf[b * stride + id]);
+        }
+        ntt_inv1_from<LOGN, PASS + 1, NB>(x, tau, buf, stride, psi_inv_rev, sync, sync, z);
     }
 }
 
