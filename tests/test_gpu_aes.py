@@ -1,0 +1,41 @@
+"""AES under TFHE on the B200 (BASELINE configs[2] stand-in): the mapped circuit evaluated encrypted must decrypt to the
+cleartext circuit's output; the full cipher must reproduce the FIPS-197 known answer."""
+import gzip
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLD
+from oracle import cleartext
+from tfhe_fbs_map_b200 import circuits
+from tfhe_fbs_map_b200.formats import read_lbf
+from test_circuits import aes_inputs, aes_outputs
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def be():
+    from tfhe_fbs_map_b200.backend import B200Backend
+    b = B200Backend("A", device=0, seed=99)
+    yield b
+    b.close()
+
+
+@pytest.mark.parametrize("fn,rounds,B", [("aes128_r1_p11.lbf.gz", 1, 16), ("aes128_r10_p11.lbf.gz", 10, 4)])
+def test_aes_encrypted_equals_cleartext(be, fn, rounds, B):
+    path = os.path.join(GOLD, "lbf", fn)
+    if not os.path.exists(path):
+        pytest.skip(f"{fn} not generated (tools/map_aes128.py)")
+    lut = read_lbf(gzip.open(path, "rt").read())
+    rng = np.random.default_rng(2)
+    keys = [bytes(range(16))] + [rng.bytes(16) for _ in range(B - 1)]
+    pts = [bytes.fromhex("00112233445566778899aabbccddeeff")] + [rng.bytes(16) for _ in range(B - 1)]
+    inp = aes_inputs(keys, pts)
+    want = cleartext.bit_eval(circuits.aes128(rounds=rounds), inp)
+    got = lut.eval(inp, fbs_size=11, backend=be)
+    for k in want:
+        assert np.array_equal(got[k], np.asarray(want[k])), k
+    if rounds == 10:
+        assert aes_outputs(got, 1)[0].hex() == "69c4e0d86a7b0430d8cdb78070b4c55a"      # FIPS-197 C.1, computed under encryption

@@ -210,3 +210,38 @@ def test_fused_peer_store_epilogue_single_gpu(ctxs):
     finally:
         for buf in (main_buf, p1, p2):
             be.wires_free(buf)
+
+
+def test_edge_cases(ctxs):
+    """Batch of one, a circuit without any bootstrap (outputs are inputs / constants / negations only), the smallest
+    message space with a full-length negacyclic table, and a ragged batch that is not a multiple of any tile size."""
+    from tfhe_fbs_map_b200 import LutExecEnv
+    be, _ = ctxs("toy3")
+    # no bootstrap at all
+    env = LutExecEnv()
+    a, b = env.input("a"), env.input("b")
+    env.output("na", env.linear([-1], [a], 1)); env.output("b", b); env.output("zero", env.const(0)); env.output("sum", env.linear([1, 1], [a, b]))
+    iv = {"a": [0, 1, 1], "b": [1, 1, 0]}
+    got = env.eval(iv, fbs_size=3, backend=be)
+    assert got["na"].tolist() == [1, 0, 0] and got["b"].tolist() == [1, 1, 0] and got["zero"] == 0 and got["sum"].tolist() == [1, 2, 1]
+    # p = 2 with a table of length 2p = 4 (neg mode) and a batch of one
+    env = LutExecEnv()
+    a, b = env.input("a"), env.input("b")
+    x = env.bootstrap(env.linear([1, 2], [a, b]), [0, 1, 1, 0])
+    env.output("x", x)
+    for va, vb in ((0, 0), (1, 0), (0, 1), (1, 1)):
+        assert env.eval({"a": [va], "b": [vb]}, fbs_size=2, backend=be)["x"].tolist() == [[0, 1, 1, 0][va + 2 * vb]]
+    # ragged batch
+    e = next(x for x in load_ref_mapped() if x["circuit"] == "full_adder" and x["p"] == 15 and x["mapper"] == "search")
+    lut = read_lbf(e["lbf"])
+    inputs = {k: v[:37] for k, v in selfcheck_inputs(e["input_names"]).items()}
+    got = lut.eval(inputs, fbs_size=15, backend=be)
+    want = unpack_outputs(e, batch=37)
+    for k in got:
+        assert np.array_equal(got[k], want[str(k)])
+    # a table that is not realisable for the requested p is rejected before anything runs
+    env = LutExecEnv()
+    a, b, c = env.input("a"), env.input("b"), env.input("c")
+    env.output("y", env.bootstrap(env.linear([1, 2, 4], [a, b, c]), [0, 1, 1, 0, 1, 1, 0, 1]))
+    with pytest.raises((ValueError, AssertionError)):
+        env.eval({"a": [0], "b": [0], "c": [0]}, fbs_size=5, backend=be)
