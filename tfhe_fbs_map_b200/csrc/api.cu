@@ -121,7 +121,16 @@ template <class T> static int grow(T **p, size_t *cap, size_t need)
 static u32 bitrev32(u32 x, int bits) { u32 r = 0; for (int i = 0; i < bits; i++) { r = (r << 1) | (x & 1); x >>= 1; } return r; }
 
 // ------------------------------------------------------------------------------------------------------
+extern "C" int fbs_ctx_destroy(fbs_ctx *c);
+static int ctx_create_impl(const fbs_params *params, int device, uint64_t seed, fbs_ctx **out, fbs_ctx **partial);
 extern "C" int fbs_ctx_create(const fbs_params *params, int device, uint64_t seed, fbs_ctx **out)
+{
+    fbs_ctx *partial = nullptr;
+    const int rc = ctx_create_impl(params, device, seed, out, &partial);
+    if (rc != FBS_OK && partial) { const std::string keep = g_err; fbs_ctx_destroy(partial); g_err = keep; }   // no leak on failure
+    return rc;
+}
+static int ctx_create_impl(const fbs_params *params, int device, uint64_t seed, fbs_ctx **out, fbs_ctx **partial)
 {
     if (!params || !out) return fail(FBS_ERR_ARG, "fbs_ctx_create: null argument");
     const fbs_params &P = *params;
@@ -142,6 +151,7 @@ extern "C" int fbs_ctx_create(const fbs_params *params, int device, uint64_t see
     if (device < 0 || device >= ndev) return fail(FBS_ERR_ARG, "no such CUDA device");
     CK(cudaSetDevice(device));
     fbs_ctx *c = new fbs_ctx();
+    *partial = c;
     c->P = P; c->device = device; c->seed = seed; c->logN = logN; c->br = br; c->br1 = br1 ? br1 : br;
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, device));
@@ -181,6 +191,7 @@ extern "C" int fbs_ctx_create(const fbs_params *params, int device, uint64_t see
     CK(cudaMemcpy(c->d_gad_bsk, gb.data(), 64, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(c->d_gad_ks, gk.data(), 64, cudaMemcpyHostToDevice));
     *out = c;
+    *partial = nullptr;
     return FBS_OK;
 }
 
@@ -487,18 +498,25 @@ extern "C" int fbs_eval_bits(fbs_ctx *c, fbs_prog *g, const uint8_t *in, int64_t
         const int64_t bc = std::min<int64_t>(Bc, B - off);
         if (g->n_inputs) {
             CK(cudaMemcpy2DAsync(d_in, (size_t)bc, in + off, (size_t)B, (size_t)bc, (size_t)g->n_inputs, cudaMemcpyHostToDevice, st));
+            if (stats) CK(cudaEventRecord(c->ev[0], st));
             CKR(fbs_encrypt_inputs(c, g, d_in, bc, inst_offset + off, B_total, enc_seed, c->d_wires, st));
-            if (stats) stats->n_launches += 1;
+            if (stats) { CK(cudaEventRecord(c->ev[1], st)); stats->n_launches += 1; }
         }
         if (stats) CKR(ensure_pool(c, 4 * (size_t)g->n_levels));
         for (int lv = 0; lv < g->n_levels; lv++)
             CKR(run_level_impl(c, g, lv, -1, -1, bc, c->d_wires, st, stats, nullptr, nullptr, false, stats ? &c->ev_pool[4 * (size_t)lv] : nullptr));
         if (g->n_outputs) {
+            if (stats) CK(cudaEventRecord(c->ev[2], st));
             CKR(fbs_decrypt_outputs(c, g, bc, c->d_wires, d_out, st));
-            if (stats) stats->n_launches += 1;
+            if (stats) { CK(cudaEventRecord(c->ev[3], st)); stats->n_launches += 1; }
             CK(cudaMemcpy2DAsync(out + off, (size_t)B, d_out, (size_t)bc, (size_t)bc, (size_t)g->n_outputs, cudaMemcpyDeviceToHost, st));
         }
-        if (stats) CKR(collect_phase_times(c, g->n_levels, stats));
+        if (stats) {
+            CKR(collect_phase_times(c, g->n_levels, stats));
+            float t;
+            if (g->n_inputs) { CK(cudaEventSynchronize(c->ev[1])); CK(cudaEventElapsedTime(&t, c->ev[0], c->ev[1])); stats->ms_encrypt += t; }
+            if (g->n_outputs) { CK(cudaEventSynchronize(c->ev[3])); CK(cudaEventElapsedTime(&t, c->ev[2], c->ev[3])); stats->ms_decrypt += t; }
+        }
     }
     if (stats) {
         CK(cudaEventRecord(c->ev[7], st));
