@@ -139,6 +139,7 @@ static int ctx_create_impl(const fbs_params *params, int device, uint64_t seed, 
     if (P.ks_beta < 1 || P.ks_beta > 8 || P.ks_l < 1 || P.ks_l > 8 || P.ks_beta * P.ks_l > 40)
         return fail(FBS_ERR_ARG, "unsupported key-switch decomposition (need 1<=ks_beta<=8, 1<=ks_l<=8)");
     if (P.bsk_beta * P.bsk_l > 48 || P.bsk_beta < 2 || P.bsk_beta > 28) return fail(FBS_ERR_ARG, "unsupported blind-rotate decomposition");
+    if (P.bsk_l == 1 && P.bsk_beta > 24) return fail(FBS_ERR_ARG, "one-level blind-rotate decomposition needs bsk_beta <= 24");
     if (P.n < 1 || P.n > 4095) return fail(FBS_ERR_ARG, "n out of range");
     const BRVariant *br = nullptr, *br1 = nullptr;
     for (const BRVariant &v : g_br_variants) if (v.logN == logN && v.k == P.k && v.l == P.bsk_l) {

@@ -94,6 +94,17 @@ FQ_HD void fbs_balanced_digits(u64 y, int beta, int (&d)[L])
     }
 }
 
+// One-level case (L = 1, beta <= 24) of the two functions above in six instructions: the digit is y sign-extended from
+// beta bits.  With W = t*K63 + 8*r1 + 2^(s-1), s = 63 - beta, y occupies bits [s, 63) of W, i.e. bits [31-beta, 31) of
+// W's high word; K63 = 2^33 + 0x6000A, so W_hi = hi32(t*0x6000A + 8*r1 + 2^(s-1)) + 2t.  `rc` = 2^(s-1) = 2^(62-beta).
+FQ_HD int fbs_digit1_t(u32 t, u32 r1, int beta, u64 rc)
+{
+    // beta <= 24: rc >= 2^38 has no low word, 8*r1 < 2^33 splits into (r1 << 3, r1 >> 29)
+    const u64 v = r32_madwide2(t, (u32)(FBS_K63 & 0xFFFFFFFFu), r1 << 3, (r1 >> 29) + (u32)(rc >> 32));
+    const u32 whi = (u32)(v >> 32) + 2u * t;
+    return (int)(whi << 1) >> (32 - beta);
+}
+
 // decode phase -> message in Z_2p
 FQ_HD int fbs_decode(u64 phase, int p)
 {

@@ -103,13 +103,50 @@ FQ_HD u32 r32_mulhi(u32 a, u32 b)
 }
 // Shoup multiplication by the constant w (ws = floor(w * 2^32 / p)): w*y mod p + {0, p}, for ANY 32-bit y
 FQ_HD u32 r32_mul_shoup(u32 y, u32 w, u32 ws, u32 p) { return w * y - r32_mulhi(ws, y) * p; }
-// Montgomery reduction of acc < 2^63: acc * 2^-32 mod p, result < acc/2^32 + p
+// 32 x 32 -> 64 multiply(-add).  On the device these are spelled as mul.wide / mad.wide: left to the compiler the operands
+// get widened to 64 bits first and every product drags an extra add of a zero high word along.
+FQ_HD u64 r32_mulwide(u32 a, u32 b)
+{
+#if defined(__CUDA_ARCH__)
+    u64 r;
+    asm("mul.wide.u32 %0, %1, %2;" : "=l"(r) : "r"(a), "r"(b));
+    return r;
+#else
+    return (u64)a * b;
+#endif
+}
+FQ_HD u64 r32_madwide(u32 a, u32 b, u64 c)
+{
+#if defined(__CUDA_ARCH__)
+    u64 r;
+    asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(r) : "r"(a), "r"(b), "l"(c));
+    return r;
+#else
+    return (u64)a * b + c;
+#endif
+}
+FQ_HD u64 r32_madwide2(u32 a, u32 b, u32 clo, u32 chi)     // a*b + (chi:clo)
+{
+#if defined(__CUDA_ARCH__)
+    u64 r;
+    asm("{\n\t.reg .b64 c;\n\tmov.b64 c, {%3, %4};\n\tmad.wide.u32 %0, %1, %2, c;\n\t}" : "=l"(r) : "r"(a), "r"(b), "r"(clo), "r"(chi));
+    return r;
+#else
+    return (u64)a * b + (((u64)chi << 32) | clo);
+#endif
+}
+// Montgomery reduction of acc < 2^63: a representative of acc * 2^-32 mod p in (0, acc/2^32 + p].  Borrow-free form:
+// with m = lo(acc) * p^-1 mod 2^32 the low words of acc and m*p agree, so (acc - m*p) / 2^32 = hi(acc) - mulhi(m, p).
 FQ_HD u32 r32_redc(u64 acc, u32 p, u32 pinv_neg)
 {
-    const u32 m = (u32)acc * pinv_neg;
-    return (u32)((acc + (u64)m * p) >> 32);
+    const u32 m = (u32)acc * (0u - pinv_neg);
+    return (u32)(acc >> 32) - r32_mulhi(m, p) + p;
 }
-FQ_HD u32 r32_csub(u32 x, u32 p) { return x >= p ? x - p : x; }
+FQ_HD u32 r32_csub(u32 x, u32 p)                       // x >= p ? x - p : x, written as an unsigned min (one VIADDMNMX)
+{
+    const u32 y = x - p;
+    return y < x ? y : x;
+}
 
 // residue pair <-> packed word
 struct rns2 { u32 a, b; };

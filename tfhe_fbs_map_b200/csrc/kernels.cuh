@@ -462,6 +462,10 @@ struct BRCfg {
     static constexpr size_t per_pbs_w = acc_w + s_w + dh_w;
     static constexpr size_t bs_w = BSK_SMEM ? (size_t)G * L * G * N : 0;
     static constexpr size_t row_w = (size_t)G * L * G * N;       // BSK words per CMUX step
+    // Position of key polynomial (row r = rg*L + jj, column v) of a GGSW row in SHARED memory: [(rg - v) mod G][jj][v].  With this
+    // rotation the keys thread group v multiplies its own spectra with sit at a compile-time distance from the word the
+    // thread addresses in its own scratch polynomial (the TMA copy permutes; the layout in HBM stays [r][v]).
+    __host__ __device__ static constexpr int key_slot(int r, int v) { return ((((r / L) - v + G) % G) * L + (r % L)) * G + v; }
     __host__ __device__ static constexpr size_t ms_stride(int n) { return (((size_t)(n + 1) * 2 + 15) / 16) * 16; }
     __host__ __device__ static constexpr size_t smem_bytes(int n)
     {
@@ -509,7 +513,7 @@ __global__ void __launch_bounds__((PB / TP) * (K + 1) * (1 << LOGN) / 8, 1) k_bl
         fence_proxy_async();
         mbar_expect_tx(mbar, (u32)(C::row_w * 8));
 #pragma unroll 1
-        for (int q = 0; q < G * L * G; q++) tma_load_1d(BS + (size_t)q * N, a.bsk + (size_t)q * N, N * 8, mbar);
+        for (int q = 0; q < G * L * G; q++) tma_load_1d(BS + (size_t)C::key_slot(q / G, q % G) * N, a.bsk + (size_t)q * N, N * 8, mbar);
     }
     // ---- accumulator init: ACC = (0, .., 0, X^{-b~} * TV) ; TV[j] = F(round(j*p/N)), F(x) = tv[x]*Delta - s*Delta/2
     // The accumulator lives in shared memory as packed residue pairs (mod p1 | mod p2 << 32), canonical.
@@ -541,8 +545,25 @@ __global__ void __launch_bounds__((PB / TP) * (K + 1) * (1 << LOGN) / 8, 1) k_bl
     const int bar_g = 1 + pb0 * G + g, bar_p = 1 + PB * G + pb0;    // named barriers: per group, per bootstrap
     auto gsync = [bar_g] { bar_sync_named(bar_g, T); };
     auto psync = [bar_p] { if (TP == 1) bar_sync_named(bar_p, C::PT); else __syncthreads(); };
-    u64 *sg = S + (size_t)g * N;
     const int beta = a.beta, bits = beta * L;
+    constexpr bool one_digit = (L == 1);                           // fbs_digit1_t applies (beta <= 24 checked by fbs_ctx_create)
+    const u64 rc = 1ULL << (62 - (one_digit ? beta : 24));
+    static_assert(P::idx(1, 1, P::inv_lb(P::NPASS - 1)) == 1 + T && P::fwd_lb(0) == P::inv_lb(P::NPASS - 1),
+                  "the inverse transform leaves coefficient tau + e*T in register e, the layout the rotation reads");
+    // Shared-memory addressing (ntt.cuh): byte offset of a word = (thread part, one register per layout, including the
+    // group's polynomial select g << SH) XOR (compile-time element part).
+    constexpr int SH = LOGN + 3;                                   // log2 of a polynomial's size in bytes
+    constexpr size_t PWB = PW * 8;
+    unsigned char *Sb = (unsigned char *)S, *DHb = (unsigned char *)DH, *BSb = (unsigned char *)BS;
+    u32 bo[LOGN];
+#pragma unroll
+    for (int lb = 0; lb < LOGN; lb++) bo[lb] = P::tau_boff(tau, lb) | ((u32)g << SH);
+    // this thread's own accumulator coefficients j = tau + e*T stay mirrored in registers between the steps
+    rns2 av[TP][8];
+#pragma unroll
+    for (int q = 0; q < TP; q++)
+#pragma unroll
+        for (int e = 0; e < 8; e++) av[q][e] = rns_unpack(acc[q * PW + tau + e * T]);
 
     for (int i = 0; i < n; i++) {
         // ---- rotate, subtract, decompose: digits of (X^{ai} ACC_g - ACC_g) in the first forward layout.
@@ -551,65 +572,93 @@ __global__ void __launch_bounds__((PB / TP) * (K + 1) * (1 << LOGN) / 8, 1) k_bl
 #pragma unroll
         for (int q = 0; q < TP; q++) {
             const int ai = ((const u16 *)((const unsigned char *)s_ms + (size_t)q * ms_stride))[i];
-            const u64 *ac = acc + q * PW;
+            const unsigned char *ac = (const unsigned char *)(acc + q * PW);
+            const int base8 = (tau - ai) * 8;               // source of coefficient j = tau + e*T is (tau - ai + e*T) mod 2N
 #pragma unroll
             for (int e = 0; e < 8; e++) {
-                const int j = tau + e * T;
-                int src = j - ai;
-                if (src < 0) src += 2 * N;
-                rns2 rot = rns_unpack(ac[src < N ? src : src - N]);
-                if (src >= N) rot = rns_neg(rot);
-                const rns2 diff = rns_sub(rot, rns_unpack(ac[j]));
+                const int src8 = base8 + e * T * 8;
+                const rns2 rot = rns_unpack(*(const u64 *)(ac + (src8 & ((N - 1) * 8))));
+                const bool neg = (src8 & (N * 8)) != 0;     // X^N = -1
+                // +-rot - acc, made canonical with unsigned minima: r in [0,p], r - acc + p in [1,2p]
+                const u32 ra = neg ? FQ_P1 - rot.a : rot.a, rb = neg ? FQ_P2 - rot.b : rot.b;
+                rns2 diff;
+                diff.a = r32_csub(r32_csub(ra - av[q][e].a + FQ_P1, FQ_P1), FQ_P1);
+                diff.b = r32_csub(rb - av[q][e].b + FQ_P2, FQ_P2);        // in [0,p2]: enough for the CRT digit
                 const u32 t = rns_crt_hi(diff);
-                const u64 y = (bits <= 24) ? fbs_round_top_t(t, diff.a, bits) : fbs_round_top((u64)diff.a + (u64)FQ_P1 * t, bits);
-                int d[L];
-                fbs_balanced_digits<L>(y, beta, d);
+                if constexpr (one_digit) {
+                    const u32 d = (u32)fbs_digit1_t(t, diff.a, beta, rc);
+                    dg[0][q][e].a = d + FQ_P1;              // lazy residues in (0, 2p) of a digit in [-B/2, B/2)
+                    dg[0][q][e].b = d + FQ_P2;
+                } else {
+                    const u64 y = (bits <= 24) ? fbs_round_top_t(t, diff.a, bits) : fbs_round_top((u64)diff.a + (u64)FQ_P1 * t, bits);
+                    int d[L];
+                    fbs_balanced_digits<L>(y, beta, d);
 #pragma unroll
-                for (int jj = 0; jj < L; jj++) dg[jj][q][e] = rns_from_small(d[jj]);
+                    for (int jj = 0; jj < L; jj++) dg[jj][q][e] = rns_from_small(d[jj]);
+                }
             }
         }
-        // ---- forward NTTs through the group's scratch polynomial; spectra to DH (swizzled, layout lb = 0)
+        // ---- forward NTTs through the group's scratch polynomial; spectra to DH (swizzled, layout lb = 0).  With L == 1
+        // DH aliases S and the spectrum goes to the words this thread read in the last transpose: no barrier in between.
 #pragma unroll
         for (int jj = 0; jj < L; jj++) {
-            ntt_fwd1_from<LOGN, 0, TP>(dg[jj], tau, sg, PW, a.psi_rev, gsync, jj == 0, a.zero);
-            u64 *dh = DH + (size_t)(g * L + jj) * N;
-            if (L == 1 && P::NPASS > 1) gsync();            // DH aliases S: the last transpose's readers are done
+            ntt_fwd1_from<LOGN, 0, TP>(dg[jj], tau, Sb, PWB, bo, a.psi_rev, gsync, jj == 0, a.zero);
 #pragma unroll
             for (int e = 0; e < 8; e++) {
-                const int id = P::swz(P::idx(tau, e, 0));
+                const u32 o = bo[0] ^ P::elem_boff(e, 0);
 #pragma unroll
-                for (int q = 0; q < TP; q++) dh[q * PW + id] = rns_pack(dg[jj][q][e]);
+                for (int q = 0; q < TP; q++) {
+                    if constexpr (L == 1) *(u64 *)(Sb + q * PWB + o) = rns_pack(dg[jj][q][e]);
+                    else *(u64 *)(DHb + q * PWB + ((size_t)(g * L + jj) << SH) + (o & (N * 8 - 1))) = rns_pack(dg[jj][q][e]);
+                }
             }
         }
         psync();
         // ---- pointwise: out_g = sum_r DH[r] * BSK[r][g], per prime.  DH is lazy (< 4p), the key is canonical and in
         // Montgomery form: a PAIR of 64-bit products (< 8p^2 < 2^63) is reduced by one REDC to < 3p, then folded to < 2p.
-        // The key word is read once and used for every bootstrap the thread carries.
+        // The key word is read once and used for every bootstrap the thread carries.  Term order: the thread's own L
+        // spectra first (still in registers), then the other groups' from shared memory.
         if (BSK_SMEM) mbar_wait(mbar, (u32)(i & 1));
         rns2 x[TP][8];
         {
-            const u64 *brow = BSK_SMEM ? BS : a.bsk + (size_t)i * C::row_w;
+            const unsigned char *browb = (const unsigned char *)(a.bsk + (size_t)i * C::row_w);     // !BSK_SMEM: row in L2
+            auto key = [&](int tt, u32 o) -> rns2 {          // key of term tt = og*L + jj for this thread's column g
+                const int og = tt / L, jj = tt % L;
+                if constexpr (BSK_SMEM) return rns_unpack(*(const u64 *)(BSb + (((size_t)(og * L + jj) * G) << SH) + o));
+                int gg = g + og; if (gg >= G) gg -= G;
+                return rns_unpack(*(const u64 *)(browb + (((size_t)(gg * L + jj) * G + g) << SH) + (o & (N * 8 - 1))));
+            };
+            auto digit = [&](int tt, int q, int e, u32 o) -> rns2 {
+                const int og = tt / L, jj = tt % L;
+                if (og == 0) return dg[jj < L ? jj : 0][q][e];
+                int gg = g + og; if (gg >= G) gg -= G;
+                if constexpr (L == 1) {
+                    const u32 xg = (G == 2) ? (1u << SH) : ((u32)(g ^ gg) << SH);     // o selects polynomial g: flip to gg
+                    return rns_unpack(*(const u64 *)(Sb + q * PWB + (o ^ xg)));
+                }
+                return rns_unpack(*(const u64 *)(DHb + q * PWB + ((size_t)(gg * L + jj) << SH) + (o & (N * 8 - 1))));
+            };
 #pragma unroll
             for (int e = 0; e < 8; e++) {
-                const int id = P::swz(P::idx(tau, e, 0));
+                const u32 o = bo[0] ^ P::elem_boff(e, 0);
 #pragma unroll
-                for (int r = 0; r < G * L; r += 2) {
-                    const rns2 k0 = rns_unpack(brow[((size_t)r * G + g) * N + id]);
+                for (int t0 = 0; t0 < G * L; t0 += 2) {
+                    const rns2 k0 = key(t0, o);
                     rns2 k1; k1.a = 0; k1.b = 0;
-                    if (r + 1 < G * L) k1 = rns_unpack(brow[((size_t)(r + 1) * G + g) * N + id]);
+                    if (t0 + 1 < G * L) k1 = key(t0 + 1, o);
 #pragma unroll
                     for (int q = 0; q < TP; q++) {
-                        const rns2 d0 = rns_unpack(DH[q * PW + (size_t)r * N + id]);
-                        u64 pa = (u64)d0.a * k0.a, pb2 = (u64)d0.b * k0.b;
-                        if (r + 1 < G * L) {
-                            const rns2 d1 = rns_unpack(DH[q * PW + (size_t)(r + 1) * N + id]);
-                            pa += (u64)d1.a * k1.a;
-                            pb2 += (u64)d1.b * k1.b;
+                        const rns2 d0 = digit(t0, q, e, o);
+                        u64 pa = r32_mulwide(d0.a, k0.a), pb2 = r32_mulwide(d0.b, k0.b);
+                        if (t0 + 1 < G * L) {
+                            const rns2 d1 = digit(t0 + 1, q, e, o);
+                            pa = r32_madwide(d1.a, k1.a, pa);
+                            pb2 = r32_madwide(d1.b, k1.b, pb2);
                         }
                         const u32 ta = r32_fold(r32_redc(pa, FQ_P1, FQ_P1_INVNEG), 2 * FQ_P1);
                         const u32 tb = r32_fold(r32_redc(pb2, FQ_P2, FQ_P2_INVNEG), 2 * FQ_P2);
-                        x[q][e].a = (r == 0) ? ta : r32_fold(x[q][e].a + ta, 2 * FQ_P1);
-                        x[q][e].b = (r == 0) ? tb : r32_fold(x[q][e].b + tb, 2 * FQ_P2);
+                        x[q][e].a = (t0 == 0) ? ta : r32_fold(x[q][e].a + ta, 2 * FQ_P1);
+                        x[q][e].b = (t0 == 0) ? tb : r32_fold(x[q][e].b + tb, 2 * FQ_P2);
                     }
                 }
             }
@@ -623,19 +672,18 @@ __global__ void __launch_bounds__((PB / TP) * (K + 1) * (1 << LOGN) / 8, 1) k_bl
                 mbar_expect_tx(mbar, (u32)(C::row_w * 8));
                 const u64 *src = a.bsk + (size_t)(i + 1) * C::row_w;
 #pragma unroll 1
-                for (int q = 0; q < G * L * G; q++) tma_load_1d(BS + (size_t)q * N, src + (size_t)q * N, N * 8, mbar);
+                for (int q = 0; q < G * L * G; q++) tma_load_1d(BS + (size_t)C::key_slot(q / G, q % G) * N, src + (size_t)q * N, N * 8, mbar);
             }
         };
-        ntt_inv1_from<LOGN, 0, TP>(x, tau, sg, PW, a.psi_inv_rev, after_pass0, gsync, a.zero);
+        ntt_inv1_from<LOGN, 0, TP>(x, tau, Sb, PWB, bo, a.psi_rev, after_pass0, gsync, a.zero);
+        // ---- accumulate: ACC_g += out_g (inverse output < 2p), canonical; coefficient tau + e*T sits in register e
 #pragma unroll
         for (int e = 0; e < 8; e++) {
-            const int j = P::idx(tau, e, P::inv_lb(P::NPASS - 1));
 #pragma unroll
             for (int q = 0; q < TP; q++) {
-                rns2 v;
-                v.a = r32_csub(x[q][e].a, FQ_P1);
-                v.b = r32_csub(x[q][e].b, FQ_P2);
-                acc[q * PW + j] = rns_pack(rns_add(rns_unpack(acc[q * PW + j]), v));
+                av[q][e].a = r32_csub(r32_fold(av[q][e].a + x[q][e].a + a.zero, 2 * FQ_P1), FQ_P1);
+                av[q][e].b = r32_csub(r32_fold(av[q][e].b + x[q][e].b + a.zero, 2 * FQ_P2), FQ_P2);
+                acc[q * PW + tau + e * T] = rns_pack(av[q][e]);
             }
         }
         gsync();                                         // ACC_g is only read by group g (next step's rotation)

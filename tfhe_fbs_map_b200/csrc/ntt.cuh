@@ -39,7 +39,13 @@ struct NttPlan {
     {
         return ((tau >> lb) << (lb + 3)) | (e << lb) | (tau & ((1 << lb) - 1));
     }
+    // swz and idx are GF(2)-linear in (tau, e): swz(idx(tau, e, lb)) = swz(idx(tau, 0, lb)) ^ swz(idx(0, e, lb)).  The kernels keep
+    // the thread part as a BYTE offset in a register (one per layout) and XOR the compile-time element part into it.
+    FQ_HDM static constexpr u32 tau_boff(int tau, int lb) { return 8u * (u32)swz(idx(tau, 0, lb)); }
+    FQ_HDM static constexpr u32 elem_boff(int e, int lb) { return 8u * (u32)swz(idx(0, e, lb)); }
 };
+static_assert(NttPlan<11>::swz(NttPlan<11>::idx(173, 5, 2)) * 8 == (NttPlan<11>::tau_boff(173, 2) ^ NttPlan<11>::elem_boff(5, 2)), "linear addressing");
+static_assert(NttPlan<10>::swz(NttPlan<10>::idx(97, 3, 4)) * 8 == (NttPlan<10>::tau_boff(97, 4) ^ NttPlan<10>::elem_boff(3, 4)), "linear addressing");
 
 // ---- one forward pass on registers -------------------------------------------------------------------
 struct alignas(16) fq_tw { u32 w1, ws1, w2, ws2; };      // twiddle + Shoup companion for both primes: one 128-bit load
@@ -89,7 +95,9 @@ FQ_HD void ntt_fwd_pass(rns2 (&x)[8], int tau, const fq_tw *__restrict__ psi_rev
     ntt_fwd_pass_n<LOGN, PASS, 1>(*reinterpret_cast<rns2(*)[1][8]>(&x), tau, psi_rev, z);
 }
 // ---- one inverse pass on registers ---------------------------------------------------------------------
-template <int LOGN, int PASS, int NB>
+// MIRROR: psi^-bitrev(m+i) = -psi^bitrev(2m-1-i), so the inverse can read the FORWARD table mirrored within each block
+// [m, 2m) and swap the operands of its subtraction; the blind-rotate kernel does, which halves the twiddle footprint in L1.
+template <int LOGN, int PASS, int NB, bool MIRROR = false>
 FQ_HD void ntt_inv_pass_n(rns2 (&x)[NB][8], int tau, const fq_tw *__restrict__ psi_inv_rev, u32 z = 0)
 {
     using P = NttPlan<LOGN>;
@@ -103,14 +111,15 @@ FQ_HD void ntt_inv_pass_n(rns2 (&x)[NB][8], int tau, const fq_tw *__restrict__ p
         for (int e0 = 0; e0 < 8; e0++) {
             if (e0 & (1 << q)) continue;
             const int e1 = e0 | (1 << q);
-            const fq_tw w = fq_tw_load(psi_inv_rev + m + ((th << (2 - q)) | (e0 >> (q + 1))));
+            const int ti = (th << (2 - q)) | (e0 >> (q + 1));
+            const fq_tw w = fq_tw_load(psi_inv_rev + (MIRROR ? 2 * m - 1 - ti : m + ti));
 #pragma unroll
             for (int b = 0; b < NB; b++) {
                 const u32 ua = x[b][e0].a, va = x[b][e1].a, ub = x[b][e0].b, vb = x[b][e1].b;
                 x[b][e0].a = r32_fold(ua + va + z, 2 * FQ_P1);
-                x[b][e1].a = r32_mul_shoup(ua - va + 2 * FQ_P1, w.w1, w.ws1, FQ_P1);
+                x[b][e1].a = r32_mul_shoup(MIRROR ? va - ua + 2 * FQ_P1 : ua - va + 2 * FQ_P1, w.w1, w.ws1, FQ_P1);
                 x[b][e0].b = r32_fold(ub + vb + z, 2 * FQ_P2);
-                x[b][e1].b = r32_mul_shoup(ub - vb + 2 * FQ_P2, w.w2, w.ws2, FQ_P2);
+                x[b][e1].b = r32_mul_shoup(MIRROR ? vb - ub + 2 * FQ_P2 : ub - vb + 2 * FQ_P2, w.w2, w.ws2, FQ_P2);
             }
         }
     }
@@ -150,53 +159,59 @@ __device__ __forceinline__ void ntt_forward(rns2 (&x)[8], int tau, u64 *bufA, u6
 // ---- single-buffer variants: one scratch polynomial per thread group and bootstrap, two barriers per transpose ------
 // (used by the blind-rotate kernel, where shared memory rather than barrier count limits residency).  A thread may carry
 // NB bootstraps: their scratch polynomials are `stride` words apart and are transposed under the same barriers.
+// ONE barrier per transpose suffices: a word's address depends only on its logical index, so the words a thread writes
+// for transpose t+1 are exactly the words it read itself in transpose t (nobody else reads them in between).  Only the
+// first write needs the caller's guarantee (`buf_free`) that the previous users of the scratch are done.
+// Addressing: `bo[lb]` = NttPlan::tau_boff(tau, lb) (+ any higher-order offset that selects the polynomial) for every
+// layout lb, `buf` a byte pointer, `stride` the byte distance between the scratch polynomials of the NB bootstraps.
 template <int LOGN, int PASS, int NB, class Sync>
-__device__ __forceinline__ void ntt_fwd1_from(rns2 (&x)[NB][8], int tau, u64 *buf, size_t stride, const fq_tw *psi_rev, Sync sync, bool buf_free, u32 z = 0)
+__device__ __forceinline__ void ntt_fwd1_from(rns2 (&x)[NB][8], int tau, unsigned char *buf, size_t stride, const u32 (&bo)[LOGN], const fq_tw *psi_rev, Sync sync, bool buf_free, u32 z = 0)
 {
     using P = NttPlan<LOGN>;
     ntt_fwd_pass_n<LOGN, PASS, NB>(x, tau, psi_rev, z);
     if constexpr (PASS + 1 < P::NPASS) {
         constexpr int lb0 = P::fwd_lb(PASS), lb1 = P::fwd_lb(PASS + 1);
-        if (!buf_free) sync();                          // earlier readers of buf are done
+        if (!buf_free) sync();                          // earlier readers of buf (other threads) are done
 #pragma unroll
         for (int e = 0; e < 8; e++) {
-            const int id = P::swz(P::idx(tau, e, lb0));
+            const u32 o = bo[lb0] ^ P::elem_boff(e, lb0);
 #pragma unroll
-            for (int b = 0; b < NB; b++) buf[b * stride + id] = rns_pack(x[b][e]);
+            for (int b = 0; b < NB; b++) *(u64 *)(buf + b * stride + o) = rns_pack(x[b][e]);
         }
         sync();
 #pragma unroll
         for (int e = 0; e < 8; e++) {
-            const int id = P::swz(P::idx(tau, e, lb1));
+            const u32 o = bo[lb1] ^ P::elem_boff(e, lb1);
 #pragma unroll
-            for (int b = 0; b < NB; b++) x[b][e] = rns_unpack(buf[b * stride + id]);
+            for (int b = 0; b < NB; b++) x[b][e] = rns_unpack(*(const u64 *)(buf + b * stride + o));
         }
-        ntt_fwd1_from<LOGN, PASS + 1, NB>(x, tau, buf, stride, psi_rev, sync, false, z);
+        ntt_fwd1_from<LOGN, PASS + 1, NB>(x, tau, buf, stride, bo, psi_rev, sync, true, z);
     }
 }
 // inverse: `after_pass0` runs between pass 0 and the first write to buf
+// `psi_rev` is the FORWARD table (read mirrored, see ntt_inv_pass_n)
 template <int LOGN, int PASS, int NB, class Sync0, class Sync>
-__device__ __forceinline__ void ntt_inv1_from(rns2 (&x)[NB][8], int tau, u64 *buf, size_t stride, const fq_tw *psi_inv_rev, Sync0 after_pass0, Sync sync, u32 z = 0)
+__device__ __forceinline__ void ntt_inv1_from(rns2 (&x)[NB][8], int tau, unsigned char *buf, size_t stride, const u32 (&bo)[LOGN], const fq_tw *psi_rev, Sync0 after_pass0, Sync sync, u32 z = 0)
 {
     using P = NttPlan<LOGN>;
-    ntt_inv_pass_n<LOGN, PASS, NB>(x, tau, psi_inv_rev, z);
-    if constexpr (PASS == 0) after_pass0(); else if constexpr (PASS + 1 < P::NPASS) sync();
+    ntt_inv_pass_n<LOGN, PASS, NB, true>(x, tau, psi_rev, z);
+    if constexpr (PASS == 0) after_pass0();             // later passes write the words they read themselves: no barrier
     if constexpr (PASS + 1 < P::NPASS) {
         constexpr int lb0 = P::inv_lb(PASS), lb1 = P::inv_lb(PASS + 1);
 #pragma unroll
         for (int e = 0; e < 8; e++) {
-            const int id = P::swz(P::idx(tau, e, lb0));
+            const u32 o = bo[lb0] ^ P::elem_boff(e, lb0);
 #pragma unroll
-            for (int b = 0; b < NB; b++) buf[b * stride + id] = rns_pack(x[b][e]);
+            for (int b = 0; b < NB; b++) *(u64 *)(buf + b * stride + o) = rns_pack(x[b][e]);
         }
         sync();
 #pragma unroll
         for (int e = 0; e < 8; e++) {
-            const int id = P::swz(P::idx(tau, e, lb1));
+            const u32 o = bo[lb1] ^ P::elem_boff(e, lb1);
 #pragma unroll
-            for (int b = 0; b < NB; b++) x[b][e] = rns_unpack(buf[b * stride + id]);
+            for (int b = 0; b < NB; b++) x[b][e] = rns_unpack(*(const u64 *)(buf + b * stride + o));
         }
-        ntt_inv1_from<LOGN, PASS + 1, NB>(x, tau, buf, stride, psi_inv_rev, sync, sync, z);
+        ntt_inv1_from<LOGN, PASS + 1, NB>(x, tau, buf, stride, bo, psi_rev, sync, sync, z);
     }
 }
 
