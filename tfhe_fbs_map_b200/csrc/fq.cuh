@@ -137,10 +137,11 @@ FQ_HD u64 r32_madwide2(u32 a, u32 b, u32 clo, u32 chi)     // a*b + (chi:clo)
 }
 // Montgomery reduction of acc < 2^63: a representative of acc * 2^-32 mod p in (0, acc/2^32 + p].  Borrow-free form:
 // with m = lo(acc) * p^-1 mod 2^32 the low words of acc and m*p agree, so (acc - m*p) / 2^32 = hi(acc) - mulhi(m, p).
-FQ_HD u32 r32_redc(u64 acc, u32 p, u32 pinv_neg)
+// (`z` is the kernels' run-time zero that keeps the subtraction a 3-input IADD3 on the ALU pipe, see ntt.cuh)
+FQ_HD u32 r32_redc(u64 acc, u32 p, u32 pinv_neg, u32 z = 0)
 {
     const u32 m = (u32)acc * (0u - pinv_neg);
-    return (u32)(acc >> 32) - r32_mulhi(m, p) + p;
+    return (u32)(acc >> 32) - r32_mulhi(m, p) + z + p;
 }
 FQ_HD u32 r32_csub(u32 x, u32 p)                       // x >= p ? x - p : x, written as an unsigned min (one VIADDMNMX)
 {

@@ -582,8 +582,8 @@ __global__ void __launch_bounds__((PB / TP) * (K + 1) * (1 << LOGN) / 8, 1) k_bl
                 // +-rot - acc, made canonical with unsigned minima: r in [0,p], r - acc + p in [1,2p]
                 const u32 ra = neg ? FQ_P1 - rot.a : rot.a, rb = neg ? FQ_P2 - rot.b : rot.b;
                 rns2 diff;
-                diff.a = r32_csub(r32_csub(ra - av[q][e].a + FQ_P1, FQ_P1), FQ_P1);
-                diff.b = r32_csub(rb - av[q][e].b + FQ_P2, FQ_P2);        // in [0,p2]: enough for the CRT digit
+                diff.a = r32_csub(r32_csub(ra - av[q][e].a + a.zero + FQ_P1, FQ_P1), FQ_P1);
+                diff.b = r32_csub(rb - av[q][e].b + a.zero + FQ_P2, FQ_P2);        // in [0,p2]: enough for the CRT digit
                 const u32 t = rns_crt_hi(diff);
                 if constexpr (one_digit) {
                     const u32 d = (u32)fbs_digit1_t(t, diff.a, beta, rc);
@@ -655,8 +655,8 @@ __global__ void __launch_bounds__((PB / TP) * (K + 1) * (1 << LOGN) / 8, 1) k_bl
                             pa = r32_madwide(d1.a, k1.a, pa);
                             pb2 = r32_madwide(d1.b, k1.b, pb2);
                         }
-                        const u32 ta = r32_fold(r32_redc(pa, FQ_P1, FQ_P1_INVNEG), 2 * FQ_P1);
-                        const u32 tb = r32_fold(r32_redc(pb2, FQ_P2, FQ_P2_INVNEG), 2 * FQ_P2);
+                        const u32 ta = r32_fold(r32_redc(pa, FQ_P1, FQ_P1_INVNEG, a.zero), 2 * FQ_P1);
+                        const u32 tb = r32_fold(r32_redc(pb2, FQ_P2, FQ_P2_INVNEG, a.zero), 2 * FQ_P2);
                         x[q][e].a = (t0 == 0) ? ta : r32_fold(x[q][e].a + ta, 2 * FQ_P1);
                         x[q][e].b = (t0 == 0) ? tb : r32_fold(x[q][e].b + tb, 2 * FQ_P2);
                     }

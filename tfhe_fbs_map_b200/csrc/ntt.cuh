@@ -83,8 +83,8 @@ FQ_HD void ntt_fwd_pass_n(rns2 (&x)[NB][8], int tau, const fq_tw *__restrict__ p
             for (int b = 0; b < NB; b++) {
                 const u32 ua = r32_fold(x[b][e0].a, 2 * FQ_P1), va = r32_mul_shoup(x[b][e1].a, w.w1, w.ws1, FQ_P1);
                 const u32 ub = r32_fold(x[b][e0].b, 2 * FQ_P2), vb = r32_mul_shoup(x[b][e1].b, w.w2, w.ws2, FQ_P2);
-                x[b][e0].a = ua + va + z; x[b][e1].a = ua - va + 2 * FQ_P1;
-                x[b][e0].b = ub + vb + z; x[b][e1].b = ub - vb + 2 * FQ_P2;
+                x[b][e0].a = ua + va + z; x[b][e1].a = ua - va + z + 2 * FQ_P1;
+                x[b][e0].b = ub + vb + z; x[b][e1].b = ub - vb + z + 2 * FQ_P2;
             }
         }
     }
