@@ -15,7 +15,7 @@ from . import params as _params
 from .levelize import CProgDesc, Program, levelize
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libfbs_b200.so")
+LIB_PATH = os.environ.get("FBS_B200_LIB") or os.path.join(_HERE, "libfbs_b200.so")   # env override: kernel-variant experiments
 
 EXPORTS = [
     "fbs_last_error", "fbs_abi_version", "fbs_ctx_create", "fbs_keygen", "fbs_ctx_destroy", "fbs_ctx_info",
