@@ -39,12 +39,21 @@ WORKLOADS = {
                          desc="128-bit AIG ripple-carry adder (synthetic stand-in for EPFL adder.blif), fbs_size 15, search mapper"),
     "mult16_p17": dict(lbf="mult16_p17.lbf", p=17, cpu_sample="mult8_p17.lbf", desc="16x16 array multiplier, fbs_size 17"),
     "aes_sbox_p11": dict(lbf="aes_sbox_p11.lbf", p=11, cpu_sample="aes_sbox_p11.lbf", desc="AES s-box non-linear core, fbs_size 11"),
+    # BASELINE configs[2]: the full cipher (tfhe_fbs_map_b200/circuits.py generator, FIPS-197 verified; Bristol aes_128.txt is not
+    # available offline), 14 954 bootstraps per instance: time-boxed with a small per-GPU batch, evals/s extrapolates linearly
+    "aes128_p11": dict(lbf="aes128_r10_p11.lbf.gz", p=11, cpu_sample="aes_sbox_p11.lbf", batch=16,
+                       desc="AES-128 (10 rounds, key schedule included; in-repo generator standing in for Bristol aes_128.txt), fbs_size 11, search mapper"),
 }
 
 
 def load_env(fn):
-    from tfhe_fbs_map_b200.formats import read_lbf_file
-    return read_lbf_file(os.path.join(ROOT, "tests", "golden", "lbf", fn))
+    from tfhe_fbs_map_b200.formats import read_lbf, read_lbf_file
+    path = os.path.join(ROOT, "tests", "golden", "lbf", fn)
+    if fn.endswith(".gz"):
+        import gzip
+        with gzip.open(path, "rt") as f:
+            return read_lbf(f.read())
+    return read_lbf_file(path)
 
 
 class ClockSampler(threading.Thread):
@@ -199,7 +208,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="adder128_p15", choices=sorted(WORKLOADS))
-    ap.add_argument("--batch", type=int, default=296, help="encrypted instances per GPU per step")
+    ap.add_argument("--batch", type=int, default=None, help="encrypted instances per GPU per step (default 296; 16 for aes128_p11)")
     ap.add_argument("--param-set", default="A")
     ap.add_argument("--seed", type=int, default=20241018)
     ap.add_argument("--shard", default="instances", choices=["instances", "nodes"],
@@ -218,6 +227,8 @@ def main():
     from tfhe_fbs_map_b200 import params, levelize
     ps = params.get(args.param_set)
     wl = WORKLOADS[args.workload]
+    if args.batch is None:
+        args.batch = wl.get("batch", 296)
 
     if args.impl == "reference":
         run_reference(args, wl, ps, rank, world)

@@ -33,7 +33,7 @@ struct BRVariant { int logN, k, l; bool bsk_smem; int pb, tp, threads; size_t (*
 template <int LOGN, int K, int L, bool SM, int PB, int TP>
 static cudaError_t br_launch(const BRArgs &a, long long jobs, size_t smem, cudaStream_t st)
 {
-    const long long grid = (jobs + PB - 1) / PB;
+    const long long grid = (jobs - a.job_begin + PB - 1) / PB;
     k_blind_rotate<LOGN, K, L, SM, PB, TP><<<(unsigned)grid, BRCfg<LOGN, K, L, SM, PB, TP>::THREADS, smem, st>>>(a);
     return cudaGetLastError();
 }
@@ -394,10 +394,18 @@ static int run_level_impl(fbs_ctx *c, fbs_prog *g, int level, int nb, int ne, in
     ba.n_peers = c->n_peers;
     for (int pr = 0; pr < c->n_peers; pr++) ba.peer_wires[pr] = c->peers[pr]; ba.lc_begin = lc0; ba.n = n; ba.p = g->p; ba.beta = P.bsk_beta;
     const long long jobs = (long long)(node1 - node0) * B;
-    if (jobs <= c->sm_count) CK(c->br1->launch(ba, jobs, c->br1_smem, st));   // fill SMs first, pair bootstraps after
-    else CK(c->br->launch(ba, jobs, c->br_smem, st));
+    // Full waves run the widest variant (pb bootstraps per CTA, one CTA per SM).  A last partial wave of at most one job
+    // per SM goes to the one-bootstrap-per-CTA variant instead: it spreads over all SMs and finishes sooner than half-idle
+    // paired CTAs would (and starts as soon as SMs drain from the first launch).
+    const long long wave = (long long)c->sm_count * c->br->pb, tail = jobs % wave;
+    int n_br_launches = 1;
+    if (c->br1 != c->br && tail > 0 && tail <= c->sm_count) {
+        if (jobs > tail) { BRArgs bw = ba; CK(c->br->launch(bw, jobs - tail, c->br_smem, st)); n_br_launches = 2; }
+        ba.job_begin = jobs - tail;
+        CK(c->br1->launch(ba, jobs, c->br1_smem, st));
+    } else CK(c->br->launch(ba, jobs, c->br_smem, st));
     if (rec) CK(cudaEventRecord(E[3], st));
-    if (stats) { stats->n_pbs += jobs; stats->n_launches += 3; }
+    if (stats) { stats->n_pbs += jobs; stats->n_launches += 2 + n_br_launches; }
     if (timed && stats) {
         CK(cudaEventSynchronize(c->ev[3]));
         float t;

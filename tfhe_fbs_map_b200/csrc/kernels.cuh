@@ -445,7 +445,7 @@ struct BRArgs {
     const int32_t *bs_lc, *bs_slot, *bs_tab_ptr, *bs_mode;
     const u8 *bs_tab;
     u64 *wires; u64 *tap_acc;
-    long long B, jobs;
+    long long B, jobs, job_begin;       // this launch covers jobs [job_begin, jobs) of the level
     int node_begin, lc_begin, n, p, beta;
     u32 zero;                           // always 0; unknown to ptxas, see ntt.cuh (pins adds to the ALU pipe)
     int n_peers;                        // node-sharded multi-GPU: replicas of the wire buffer on the other GPUs
@@ -497,7 +497,7 @@ __global__ void __launch_bounds__((PB / TP) * (K + 1) * (1 << LOGN) / 8, 1) k_bl
     bool live[TP]; int node[TP], tabL[TP], tab0[TP], mode[TP]; long long inst[TP], job[TP];
 #pragma unroll
     for (int q = 0; q < TP; q++) {
-        job[q] = (long long)blockIdx.x * PB + pb0 + q;
+        job[q] = a.job_begin + (long long)blockIdx.x * PB + pb0 + q;
         live[q] = job[q] < a.jobs;
         if (!live[q]) job[q] = a.jobs - 1;
         node[q] = a.node_begin + (int)(job[q] / a.B);
