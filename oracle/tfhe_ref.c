@@ -89,7 +89,7 @@ enum { DOM_SLWE = 1, DOM_SGLWE = 2, DOM_BSK_MASK = 3, DOM_BSK_NOISE = 4, DOM_KSK
 
 /* ---------------- parameters / context ---------------- */
 typedef struct {
-    int32_t n, k, N, bsk_l, bsk_beta, ks_l, ks_beta, reserved;
+    int32_t n, k, N, bsk_l, bsk_beta, ks_l, ks_beta, bsk_unroll;   /* bsk_unroll: 0/1 classic, 2 = two key bits per step */
     u64 lwe_noise, glwe_noise;   /* round(sigma * P) */
 } ref_params;
 
@@ -98,7 +98,7 @@ typedef struct {
     u8 *s_lwe;      /* [n] */
     u8 *s_big;      /* [k*N]  (s_big[u*N+j] = S_u[j]) */
     u64 *ksk;       /* [k*N*ks_l][n+1] */
-    u64 *bsk_coef;  /* [n][(k+1)*l][k+1][N] coefficient domain */
+    u64 *bsk_coef;  /* [n_ggsw][(k+1)*l][k+1][N] coefficient domain (n_ggsw = n, or 3n/2 when unrolled) */
     u64 *bsk_ntt;   /* same, oracle-order NTT domain */
     u64 *psi_rev, *psi_inv_rev; u64 ninv;
 } ref_ctx;
@@ -216,6 +216,17 @@ void ref_ctx_destroy(ref_ctx *c)
     free(c->s_lwe); free(c->s_big); free(c->ksk); free(c->bsk_coef); free(c->bsk_ntt); free(c->psi_rev); free(c->psi_inv_rev); free(c);
 }
 
+/* Key unrolling (two key bits per blind-rotation step): X^(a1 s1 + a2 s2) - 1 =
+ *   (X^(a1+a2) - 1) s1 s2 + (X^a1 - 1) s1 (1 - s2) + (X^a2 - 1) (1 - s1) s2,
+ * so pair t of the key gets three GGSW ciphertexts, of the bits m_0 = s1 s2, m_1 = s1 (1-s2), m_2 = (1-s1) s2 (GGSW index 3t + c).
+ * Classic: GGSW i encrypts s_i. */
+static int n_ggsw(const ref_params *P) { return P->bsk_unroll == 2 ? 3 * (P->n / 2) : P->n; }
+static int ggsw_bit(const ref_ctx *c, int g)
+{
+    if (c->P.bsk_unroll != 2) return c->s_lwe[g];
+    int t = g / 3, cc = g % 3, s1 = c->s_lwe[2 * t], s2 = c->s_lwe[2 * t + 1];
+    return cc == 0 ? (s1 & s2) : cc == 1 ? (s1 & !s2) : (!s1 & s2);
+}
 void ref_keygen(ref_ctx *c)
 {
     const ref_params *P = &c->P; int n = P->n, k = P->k, N = P->N, l = P->bsk_l, lk = P->ks_l;
@@ -238,10 +249,10 @@ void ref_keygen(ref_ctx *c)
         row[n] = body;
     }
     /* BSK: GGSW(s_lwe[i]); row r = u*l + j (u <= k input poly, j level); polys v = 0..k (v = k is the body) */
-    int rows = (k + 1) * l; size_t polys = (size_t)n * rows * (k + 1);
+    int rows = (k + 1) * l; const int ng = n_ggsw(P); size_t polys = (size_t)ng * rows * (k + 1);
     c->bsk_coef = malloc(polys * N * 8); c->bsk_ntt = malloc(polys * N * 8);
 #pragma omp parallel for schedule(dynamic, 4)
-    for (int ir = 0; ir < n * rows; ir++) {
+    for (int ir = 0; ir < ng * rows; ir++) {
         int i = ir / rows, r = ir % rows, u = r / l, j = r % l;
         u64 *row = c->bsk_coef + (size_t)ir * (k + 1) * N;
         u64 *body = row + (size_t)k * N; u64 *sp = malloc(8 * N), *tmp = malloc(8 * N);
@@ -252,7 +263,7 @@ void ref_keygen(ref_ctx *c)
             ref_polymul_ntt(c, A, sp, tmp);
             for (int q = 0; q < N; q++) body[q] = f_add(body[q], tmp[q]);
         }
-        if (c->s_lwe[i]) { u64 g = gadget(P->bsk_beta, j); u64 *tgt = row + (size_t)u * N; tgt[0] = f_add(tgt[0], g); }
+        if (ggsw_bit(c, i)) { u64 g = gadget(P->bsk_beta, j); u64 *tgt = row + (size_t)u * N; tgt[0] = f_add(tgt[0], g); }
         free(sp); free(tmp);
         u64 *rown = c->bsk_ntt + (size_t)ir * (k + 1) * N;
         memcpy(rown, row, (size_t)(k + 1) * N * 8);
@@ -265,7 +276,7 @@ void ref_get_keys(const ref_ctx *c, u8 *s_lwe, u8 *s_big, u64 *ksk, u64 *bsk_coe
     if (s_lwe) memcpy(s_lwe, c->s_lwe, P->n);
     if (s_big) memcpy(s_big, c->s_big, (size_t)P->k * P->N);
     if (ksk) memcpy(ksk, c->ksk, (size_t)P->k * P->N * P->ks_l * (P->n + 1) * 8);
-    if (bsk_coef) memcpy(bsk_coef, c->bsk_coef, (size_t)P->n * (P->k + 1) * P->bsk_l * (P->k + 1) * P->N * 8);
+    if (bsk_coef) memcpy(bsk_coef, c->bsk_coef, (size_t)n_ggsw(P) * (P->k + 1) * P->bsk_l * (P->k + 1) * P->N * 8);
 }
 
 /* ---------------- LWE ops on "big" ciphertexts (dimension kN, body last) ---------------- */
@@ -351,6 +362,35 @@ static inline u64 rot_coef(const u64 *poly, int N, int j, int a)
     int idx = j - a; while (idx < 0) idx += 2 * N;
     return idx < N ? poly[idx] : f_neg(poly[idx - N]);
 }
+/* dig[r] = NTT of digit polynomial r of the gadget decomposition of `src` (k+1 polynomials) */
+static void decompose_ntt(const ref_ctx *c, const u64 *src, int rotate_by /* < 0: decompose src itself; else X^a src - src */, u64 *dig)
+{
+    const ref_params *P = &c->P; int k = P->k, N = P->N, l = P->bsk_l;
+    int32_t d[16];
+    for (int u = 0; u <= k; u++) {
+        const u64 *pu = src + (size_t)u * N;
+        for (int j = 0; j < N; j++) {
+            u64 x = rotate_by < 0 ? pu[j] : f_sub(rot_coef(pu, N, j, rotate_by), pu[j]);
+            decompose(x, P->bsk_beta, l, d);
+            for (int jj = 0; jj < l; jj++) dig[((size_t)(u * l + jj)) * N + j] = f_from_i64(d[jj]);
+        }
+    }
+    for (int r = 0; r < (k + 1) * l; r++) ntt_fwd(c, dig + (size_t)r * N);
+}
+/* outp[v] = sum_r dig[r] * GGSW_g[r][v]  (external product with the already decomposed input), coefficient domain */
+static void ext_product(const ref_ctx *c, const u64 *dig, int g, u64 *outp)
+{
+    const ref_params *P = &c->P; int k = P->k, N = P->N, rows = (k + 1) * P->bsk_l;
+    for (int v = 0; v <= k; v++) {
+        u64 *o = outp + (size_t)v * N;
+        for (int j = 0; j < N; j++) o[j] = 0;
+        for (int r = 0; r < rows; r++) {
+            const u64 *b = c->bsk_ntt + (((size_t)g * rows + r) * (k + 1) + v) * N; const u64 *dd = dig + (size_t)r * N;
+            for (int j = 0; j < N; j++) o[j] = f_add(o[j], f_mul(dd[j], b[j]));
+        }
+        ntt_inv(c, o);
+    }
+}
 void ref_blind_rotate(const ref_ctx *c, const uint16_t *ms, const u64 *tv, u64 *acc /* [(k+1)][N] */)
 {
     const ref_params *P = &c->P; int n = P->n, k = P->k, N = P->N, l = P->bsk_l, rows = (k + 1) * l;
@@ -358,28 +398,28 @@ void ref_blind_rotate(const ref_ctx *c, const uint16_t *ms, const u64 *tv, u64 *
     int bt = ms[n];
     for (int j = 0; j < N; j++) acc[(size_t)k * N + j] = rot_coef(tv, N, j, (2 * N - bt) % (2 * N));
     u64 *dig = malloc((size_t)rows * N * 8), *outp = malloc((size_t)(k + 1) * N * 8);
-    int32_t d[16];
-    for (int i = 0; i < n; i++) {
-        int a = ms[i];
-        for (int u = 0; u <= k; u++) {
-            const u64 *pu = acc + (size_t)u * N;
-            for (int j = 0; j < N; j++) {
-                u64 diff = f_sub(rot_coef(pu, N, j, a), pu[j]);
-                decompose(diff, P->bsk_beta, l, d);
-                for (int jj = 0; jj < l; jj++) dig[((size_t)(u * l + jj)) * N + j] = f_from_i64(d[jj]);
+    if (P->bsk_unroll == 2) {
+        /* ACC <- ACC + sum_c (X^{e_c} - 1) * (Dec(ACC) [x] GGSW_{3t+c}),  e = (a1 + a2, a1, a2): one decomposition per key pair */
+        u64 *delta = malloc((size_t)(k + 1) * N * 8);
+        for (int t = 0; t < n / 2; t++) {
+            const int a1 = ms[2 * t], a2 = ms[2 * t + 1], e[3] = {(a1 + a2) % (2 * N), a1, a2};
+            decompose_ntt(c, acc, -1, dig);
+            memset(delta, 0, (size_t)(k + 1) * N * 8);
+            for (int cc = 0; cc < 3; cc++) {
+                ext_product(c, dig, 3 * t + cc, outp);
+                for (int v = 0; v <= k; v++) for (int j = 0; j < N; j++) {
+                    const u64 *o = outp + (size_t)v * N;
+                    delta[(size_t)v * N + j] = f_add(delta[(size_t)v * N + j], f_sub(rot_coef(o, N, j, e[cc]), o[j]));
+                }
             }
+            for (size_t w = 0; w < (size_t)(k + 1) * N; w++) acc[w] = f_add(acc[w], delta[w]);
         }
-        for (int r = 0; r < rows; r++) ntt_fwd(c, dig + (size_t)r * N);
-        for (int v = 0; v <= k; v++) {
-            u64 *o = outp + (size_t)v * N;
-            for (int j = 0; j < N; j++) o[j] = 0;
-            for (int r = 0; r < rows; r++) {
-                const u64 *b = c->bsk_ntt + (((size_t)i * rows + r) * (k + 1) + v) * N; const u64 *dd = dig + (size_t)r * N;
-                for (int j = 0; j < N; j++) o[j] = f_add(o[j], f_mul(dd[j], b[j]));
-            }
-            ntt_inv(c, o);
-            u64 *pv = acc + (size_t)v * N;
-            for (int j = 0; j < N; j++) pv[j] = f_add(pv[j], o[j]);
+        free(delta);
+    } else {
+        for (int i = 0; i < n; i++) {
+            decompose_ntt(c, acc, ms[i], dig);
+            ext_product(c, dig, i, outp);
+            for (size_t w = 0; w < (size_t)(k + 1) * N; w++) acc[w] = f_add(acc[w], outp[w]);
         }
     }
     free(dig); free(outp);

@@ -24,7 +24,7 @@ def build(force=False):
 class RefParams(ctypes.Structure):
     _fields_ = [("n", ctypes.c_int32), ("k", ctypes.c_int32), ("N", ctypes.c_int32), ("bsk_l", ctypes.c_int32),
                 ("bsk_beta", ctypes.c_int32), ("ks_l", ctypes.c_int32), ("ks_beta", ctypes.c_int32),
-                ("reserved", ctypes.c_int32), ("lwe_noise", ctypes.c_uint64), ("glwe_noise", ctypes.c_uint64)]
+                ("bsk_unroll", ctypes.c_int32), ("lwe_noise", ctypes.c_uint64), ("glwe_noise", ctypes.c_uint64)]
 
 
 class RefProgDesc(ctypes.Structure):
@@ -103,7 +103,7 @@ class RefTFHE:
     def __init__(self, ps, seed, keygen=True):
         self.L = lib()
         self.ps = ps
-        self.cp = RefParams(ps.n, ps.k, ps.N, ps.bsk_l, ps.bsk_beta, ps.ks_l, ps.ks_beta, 0,
+        self.cp = RefParams(ps.n, ps.k, ps.N, ps.bsk_l, ps.bsk_beta, ps.ks_l, ps.ks_beta, getattr(ps, "bsk_unroll", 1),
                             ps.lwe_noise_scale, ps.glwe_noise_scale)
         self.ctx = self.L.ref_ctx_create(ctypes.byref(self.cp), seed)
         self.ct_words = ps.k * ps.N + 1
@@ -121,7 +121,8 @@ class RefTFHE:
         s_lwe = np.zeros(ps.n, np.uint8)
         s_big = np.zeros(ps.k * ps.N, np.uint8)
         ksk = np.zeros((ps.k * ps.N * ps.ks_l, ps.n + 1), np.uint64)
-        bsk = np.zeros((ps.n, (ps.k + 1) * ps.bsk_l, ps.k + 1, ps.N), np.uint64)
+        n_ggsw = 3 * (ps.n // 2) if getattr(ps, "bsk_unroll", 1) == 2 else ps.n
+        bsk = np.zeros((n_ggsw, (ps.k + 1) * ps.bsk_l, ps.k + 1, ps.N), np.uint64)
         self.L.ref_get_keys(self.ctx, _p(s_lwe), _p(s_big), _p(ksk), _p(bsk))
         return s_lwe, s_big, ksk, bsk
 

@@ -287,7 +287,7 @@ class B200Backend:
         s_lwe = np.zeros(P.n, np.uint8)
         s_big = np.zeros(P.k * P.N, np.uint8)
         ksk = np.zeros((P.k * P.N * P.ks_l, P.n + 1), np.uint64)
-        bsk = np.zeros((P.n, (P.k + 1) * P.bsk_l, P.k + 1, P.N), np.uint64) if want_bsk else None
+        bsk = np.zeros((P.n_ggsw, (P.k + 1) * P.bsk_l, P.k + 1, P.N), np.uint64) if want_bsk else None
         self._check(self.lib.fbs_debug_get_keys(self.ctx, _ptr(s_lwe), _ptr(s_big), _ptr(ksk), _ptr(bsk)))
         return s_lwe, s_big, ksk, bsk
 

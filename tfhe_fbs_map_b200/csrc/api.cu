@@ -28,7 +28,7 @@ extern "C" int fbs_abi_version(void) { return 1; }
 // blind-rotate kernel variants
 // ------------------------------------------------------------------------------------------------------
 typedef cudaError_t (*br_launch_fn)(const BRArgs &, long long jobs, size_t smem, cudaStream_t);
-struct BRVariant { int logN, k, l; bool bsk_smem; int pb, tp, threads; size_t (*smem)(int n); br_launch_fn launch; cudaError_t (*prepare)(size_t smem); };
+struct BRVariant { int logN, k, l; bool bsk_smem; int pb, tp, threads; size_t (*smem)(int n); br_launch_fn launch; cudaError_t (*prepare)(size_t smem); int unr; };
 
 template <int LOGN, int K, int L, bool SM, int PB, int TP>
 static cudaError_t br_launch(const BRArgs &a, long long jobs, size_t smem, cudaStream_t st)
@@ -43,7 +43,22 @@ static cudaError_t br_prepare(size_t smem)
     return cudaFuncSetAttribute(k_blind_rotate<LOGN, K, L, SM, PB, TP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 }
 template <int LOGN, int K, int L, bool SM, int PB, int TP> static size_t br_smem(int n) { return BRCfg<LOGN, K, L, SM, PB, TP>::smem_bytes(n); }
-#define BRV(LOGN, K, L, SM, PB, TP) { LOGN, K, L, SM, PB, TP, BRCfg<LOGN, K, L, SM, PB, TP>::THREADS, br_smem<LOGN, K, L, SM, PB, TP>, br_launch<LOGN, K, L, SM, PB, TP>, br_prepare<LOGN, K, L, SM, PB, TP> }
+#define BRV(LOGN, K, L, SM, PB, TP) { LOGN, K, L, SM, PB, TP, BRCfg<LOGN, K, L, SM, PB, TP>::THREADS, br_smem<LOGN, K, L, SM, PB, TP>, br_launch<LOGN, K, L, SM, PB, TP>, br_prepare<LOGN, K, L, SM, PB, TP>, 1 }
+// key-unrolled kernels (bsk_unroll = 2, one decomposition level)
+template <int LOGN, int K, int PB, int TP>
+static cudaError_t br2_launch(const BRArgs &a, long long jobs, size_t smem, cudaStream_t st)
+{
+    const long long grid = (jobs - a.job_begin + PB - 1) / PB;
+    k_blind_rotate2<LOGN, K, PB, TP><<<(unsigned)grid, BR2Cfg<LOGN, K, PB, TP>::THREADS, smem, st>>>(a);
+    return cudaGetLastError();
+}
+template <int LOGN, int K, int PB, int TP>
+static cudaError_t br2_prepare(size_t smem)
+{
+    return cudaFuncSetAttribute(k_blind_rotate2<LOGN, K, PB, TP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+}
+template <int LOGN, int K, int PB, int TP> static size_t br2_smem(int n) { return BR2Cfg<LOGN, K, PB, TP>::smem_bytes(n); }
+#define BRV2(LOGN, K, PB, TP) { LOGN, K, 1, false, PB, TP, BR2Cfg<LOGN, K, PB, TP>::THREADS, br2_smem<LOGN, K, PB, TP>, br2_launch<LOGN, K, PB, TP>, br2_prepare<LOGN, K, PB, TP>, 2 }
 #ifndef FBS_SETA_TP
 #define FBS_SETA_TP 2     /* bootstraps per thread in the set-A kernel: 2 = every thread carries both bootstraps of its CTA */
 #endif
@@ -53,6 +68,8 @@ static const BRVariant g_br_variants[] = {
     BRV(11, 1, 2, false, 1, 1),            // set C (row does not fit shared memory next to the accumulator: BSK read from L2)
     BRV(10, 2, 1, true, 1, 1),             // set S
     BRV(8, 1, 2, true, 2, 2), BRV(8, 2, 1, true, 2, 1), BRV(9, 1, 1, true, 2, 2), BRV(10, 1, 3, true, 1, 1),   // toy sets (tests)
+    BRV2(11, 1, 2, 2), BRV2(11, 1, 1, 1),          // set A2 (two key bits per step)
+    BRV2(9, 1, 2, 2), BRV2(8, 2, 2, 1),            // toy3u, toy2u
 };
 
 typedef void (*ntt_launch_fn)(const u64 *, u64 *, int, const fq_tw *, const fq_tw *, u32, u32, long long, cudaStream_t);
@@ -78,6 +95,8 @@ struct fbs_ctx {
     u8 *d_kbt = nullptr;                                       // byte-transposed KSK for the tensor-core key switch
     int n_peers = 0; u64 *peers[8] = {};                       // peer replicas of the wire buffer (fbs_set_peers)
     fq_tw *d_psi_rev = nullptr, *d_psi_inv_rev = nullptr;
+    u64 *d_psi_pow = nullptr;                                  // psi^x, x < 2N, packed residues (key-unrolled kernel)
+    int unroll = 1, n_ggsw = 0; u32 mont2_ninv[2] = {0, 0};    // 2^64/N per prime
     u64 *d_gad_bsk = nullptr, *d_gad_ks = nullptr;
     u32 ninv[2] = {0, 0}, mont_ninv[2] = {0, 0};     // 1/N and 2^32/N per prime
     cudaStream_t stream = nullptr;
@@ -142,7 +161,10 @@ static int ctx_create_impl(const fbs_params *params, int device, uint64_t seed, 
     if (P.bsk_l == 1 && P.bsk_beta > 24) return fail(FBS_ERR_ARG, "one-level blind-rotate decomposition needs bsk_beta <= 24");
     if (P.n < 1 || P.n > 4095) return fail(FBS_ERR_ARG, "n out of range");
     const BRVariant *br = nullptr, *br1 = nullptr;
-    for (const BRVariant &v : g_br_variants) if (v.logN == logN && v.k == P.k && v.l == P.bsk_l) {
+    const int unroll = P.bsk_unroll == 2 ? 2 : 1;
+    if (P.bsk_unroll < 0 || P.bsk_unroll > 2) return fail(FBS_ERR_ARG, "bsk_unroll must be 0, 1 or 2");
+    if (unroll == 2 && ((P.n & 1) || P.bsk_l != 1)) return fail(FBS_ERR_ARG, "bsk_unroll = 2 needs an even n and bsk_l = 1");
+    for (const BRVariant &v : g_br_variants) if (v.logN == logN && v.k == P.k && v.l == P.bsk_l && v.unr == unroll) {
         if (!br || v.pb > br->pb) br = &v;
         if (v.pb == 1) br1 = &v;
     }
@@ -154,6 +176,7 @@ static int ctx_create_impl(const fbs_params *params, int device, uint64_t seed, 
     fbs_ctx *c = new fbs_ctx();
     *partial = c;
     c->P = P; c->device = device; c->seed = seed; c->logN = logN; c->br = br; c->br1 = br1 ? br1 : br;
+    c->unroll = unroll; c->n_ggsw = unroll == 2 ? 3 * (P.n / 2) : P.n;
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, device));
     c->sm_count = prop.multiProcessorCount;
@@ -177,6 +200,15 @@ static int ctx_create_impl(const fbs_params *params, int device, uint64_t seed, 
         for (int i = 0; i < N; i++) { u32 r = bitrev32((u32)i, logN); w[l][i] = (u32)pow_mod_host(psi, r, p); wi[l][i] = (u32)pow_mod_host(psi_inv, r, p); }
         c->ninv[l] = (u32)pow_mod_host((u64)N, p - 2, p);
         c->mont_ninv[l] = (u32)((u64)((1ULL << 32) % p) * c->ninv[l] % p);
+        c->mont2_ninv[l] = (u32)((u64)((1ULL << 32) % p) * c->mont_ninv[l] % p);
+    }
+    {
+        std::vector<u64> pp(2 * (size_t)N);
+        const u64 ps1 = pow_mod_host(3, (FQ_P1 - 1) / (2ULL * N), FQ_P1), ps2 = pow_mod_host(3, (FQ_P2 - 1) / (2ULL * N), FQ_P2);
+        u64 x1 = 1, x2 = 1;
+        for (int x = 0; x < 2 * N; x++) { pp[x] = x1 | (x2 << 32); x1 = x1 * ps1 % FQ_P1; x2 = x2 * ps2 % FQ_P2; }
+        CKR(dev_alloc(&c->d_psi_pow, 2 * (size_t)N));
+        CK(cudaMemcpy(c->d_psi_pow, pp.data(), 16 * (size_t)N, cudaMemcpyHostToDevice));
     }
     for (int i = 0; i < N; i++) {
         pr[i] = fq_tw{w[0][i], shoup32_host(w[0][i], FQ_P1), w[1][i], shoup32_host(w[1][i], FQ_P2)};
@@ -213,13 +245,14 @@ extern "C" int fbs_keygen(fbs_ctx *c)
     if (!c->d_kbt) CKR(dev_alloc(&c->d_kbt, (size_t)cols_pad * 8 * R));
     k_ksk_bytes_t<<<dim3((unsigned)((R + 255) / 256), (unsigned)cols_pad), 256, 0, st>>>(c->d_ksk, c->d_kbt, (int)R, n + 1, cols_pad);
     const int rows = (k + 1) * l;
-    const size_t total = (size_t)n * rows * (k + 1) * N;
+    const size_t total = (size_t)c->n_ggsw * rows * (k + 1) * N;
     if (!c->d_bsk) { CKR(dev_alloc(&c->d_bsk, total)); CKR(dev_alloc(&c->d_bsk_coef, total)); }
     k_gen_bsk_fill<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(c->d_bsk_coef, k, N, c->seed, P.glwe_noise, total);
-    k_bsk_body<<<n * rows, 256, (size_t)N * 9, st>>>(c->d_bsk_coef, k, N, l, c->d_s_lwe, c->d_s_big, c->d_gad_bsk);
+    k_bsk_body<<<c->n_ggsw * rows, 256, (size_t)N * 9, st>>>(c->d_bsk_coef, k, N, l, c->d_s_lwe, c->d_s_big, c->d_gad_bsk, c->unroll);
     ntt_launch_fn nf = ntt_for(c->logN);
     if (!nf) return fail(FBS_ERR_ARG, "no NTT kernel for this N");
-    nf(c->d_bsk_coef, c->d_bsk, 2, c->d_psi_rev, c->d_psi_inv_rev, c->mont_ninv[0], c->mont_ninv[1], (long long)(total / N), st);
+    if (c->unroll == 2) nf(c->d_bsk_coef, c->d_bsk, 3, c->d_psi_rev, c->d_psi_inv_rev, c->mont2_ninv[0], c->mont2_ninv[1], (long long)(total / N), st);
+    else nf(c->d_bsk_coef, c->d_bsk, 2, c->d_psi_rev, c->d_psi_inv_rev, c->mont_ninv[0], c->mont_ninv[1], (long long)(total / N), st);
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(st));
     // the coefficient-domain copy is only a parity tap: keep it for toy sizes, drop it for real key sizes
@@ -232,7 +265,7 @@ extern "C" int fbs_ctx_destroy(fbs_ctx *c)
 {
     if (!c) return FBS_OK;
     cudaSetDevice(c->device);
-    void *ptrs[] = {c->d_kbt, c->d_s_lwe, c->d_s_big, c->d_ksk, c->d_colsum, c->d_bsk, c->d_bsk_coef, c->d_psi_rev, c->d_psi_inv_rev,
+    void *ptrs[] = {c->d_kbt, c->d_s_lwe, c->d_s_big, c->d_ksk, c->d_colsum, c->d_bsk, c->d_bsk_coef, c->d_psi_rev, c->d_psi_inv_rev, c->d_psi_pow,
                     c->d_gad_bsk, c->d_gad_ks, c->d_digits, c->d_body, c->d_ms, c->d_io, c->d_wires};
     for (void *p : ptrs) if (p) cudaFree(p);
     for (auto &e : c->ev) if (e) cudaEventDestroy(e);
@@ -246,7 +279,7 @@ extern "C" int fbs_ctx_info(const fbs_ctx *c, int32_t *sm_count, int64_t *bsk_by
     if (!c) return fail(FBS_ERR_ARG, "null ctx");
     const fbs_params &P = c->P;
     if (sm_count) *sm_count = c->sm_count;
-    if (bsk_bytes) *bsk_bytes = (int64_t)P.n * (P.k + 1) * P.bsk_l * (P.k + 1) * P.N * 8;
+    if (bsk_bytes) *bsk_bytes = (int64_t)c->n_ggsw * (P.k + 1) * P.bsk_l * (P.k + 1) * P.N * 8;
     if (ksk_bytes) *ksk_bytes = (int64_t)P.k * P.N * P.ks_l * (P.n + 1) * 8;
     if (br_smem_bytes) *br_smem_bytes = (int32_t)c->br_smem;
     return FBS_OK;
@@ -388,7 +421,7 @@ static int run_level_impl(fbs_ctx *c, fbs_prog *g, int level, int nb, int ne, in
     CK(cudaGetLastError());
     if (rec) CK(cudaEventRecord(E[2], st));
     BRArgs ba{};
-    ba.ms = c->d_ms; ba.bsk = c->d_bsk; ba.psi_rev = c->d_psi_rev; ba.psi_inv_rev = c->d_psi_inv_rev;
+    ba.ms = c->d_ms; ba.bsk = c->d_bsk; ba.psi_rev = c->d_psi_rev; ba.psi_inv_rev = c->d_psi_inv_rev; ba.psi_pow = c->d_psi_pow;
     ba.bs_lc = g->d_bs_lc; ba.bs_slot = g->d_bs_slot; ba.bs_tab_ptr = g->d_bs_tab_ptr; ba.bs_mode = g->d_bs_mode; ba.bs_tab = g->d_tab;
     ba.wires = wires; ba.tap_acc = tap_acc; ba.B = B; ba.jobs = (long long)(node1 - node0) * B; ba.node_begin = node0;
     ba.n_peers = c->n_peers;
@@ -631,7 +664,7 @@ extern "C" int fbs_debug_get_keys(fbs_ctx *c, uint8_t *s_lwe, uint8_t *s_big, ui
     if (ksk) CK(cudaMemcpy(ksk, c->d_ksk, (size_t)P.k * P.N * P.ks_l * (P.n + 1) * 8, cudaMemcpyDeviceToHost));
     if (bsk_coef) {
         if (!c->d_bsk_coef) return fail(FBS_ERR_STATE, "coefficient-domain BSK is only kept for key sizes <= 64 MiB");
-        CK(cudaMemcpy(bsk_coef, c->d_bsk_coef, (size_t)P.n * (P.k + 1) * P.bsk_l * (P.k + 1) * P.N * 8, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(bsk_coef, c->d_bsk_coef, (size_t)c->n_ggsw * (P.k + 1) * P.bsk_l * (P.k + 1) * P.N * 8, cudaMemcpyDeviceToHost));
     }
     return FBS_OK;
 }

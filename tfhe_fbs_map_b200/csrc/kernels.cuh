@@ -111,8 +111,16 @@ __global__ void k_gen_bsk_fill(u64 *bsk, int k, int N, u64 seed, u64 noise_scale
                      : fbs_rnd_noise(seed, DOM_BSK_NOISE, ir * (u64)N + q, noise_scale);
 }
 // body += sum_v A_v * S_v (negacyclic, S binary), then add s_lwe[i]*g_j to coefficient 0 of poly u
+// GGSW i encrypts s_lwe[i] (classic) or, key-unrolled, the bit products of key pair t = i / 3:
+// c = i % 3 = 0: s1 s2, 1: s1 (1 - s2), 2: (1 - s1) s2   (oracle/tfhe_ref.c: ggsw_bit)
+__device__ __forceinline__ int fbs_ggsw_bit(const u8 *__restrict__ s_lwe, int i, int unroll)
+{
+    if (unroll != 2) return s_lwe[i];
+    const int t = i / 3, c = i % 3, s1 = s_lwe[2 * t], s2 = s_lwe[2 * t + 1];
+    return c == 0 ? (s1 & s2) : c == 1 ? (s1 & (s2 ^ 1)) : ((s1 ^ 1) & s2);
+}
 __global__ void __launch_bounds__(256) k_bsk_body(u64 *bsk, int k, int N, int l, const u8 *__restrict__ s_lwe,
-                                                 const u8 *__restrict__ s_big, const u64 *__restrict__ gadgets)
+                                                 const u8 *__restrict__ s_big, const u64 *__restrict__ gadgets, int unroll)
 {
     extern __shared__ u64 sh_a[];                 // [N] mask poly, then [N] key bits as bytes
     u8 *sh_s = (u8 *)(sh_a + N);
@@ -134,7 +142,7 @@ __global__ void __launch_bounds__(256) k_bsk_body(u64 *bsk, int k, int N, int l,
         }
     }
     __syncthreads();
-    if (threadIdx.x == 0 && s_lwe[i]) row[(size_t)u * N] = fq_add(row[(size_t)u * N], gadgets[j]);
+    if (threadIdx.x == 0 && fbs_ggsw_bit(s_lwe, i, unroll)) row[(size_t)u * N] = fq_add(row[(size_t)u * N], gadgets[j]);
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -143,6 +151,9 @@ __global__ void __launch_bounds__(256) k_bsk_body(u64 *bsk, int k, int N, int l,
 //                       mode 2: BSK preprocessing: forward, residues times 2^32/N (Montgomery form with the inverse
 //                               transform's 1/N folded in), packed (mod p1 | mod p2 << 32), stored SWIZZLED for the
 //                               blind-rotate kernel
+//                       mode 3: key-unrolled BSK preprocessing: as mode 2 with the caller's scale 2^64/N (Montgomery form
+//                               twice: the key goes through two reductions), stored as [e][tau] so that k_blind_rotate2's
+//                               direct global loads coalesce
 // ------------------------------------------------------------------------------------------------------
 template <int LOGN>
 __global__ void __launch_bounds__(NttPlan<LOGN>::T) k_ntt(const u64 *__restrict__ in, u64 *__restrict__ out, int mode,
@@ -182,7 +193,8 @@ __global__ void __launch_bounds__(NttPlan<LOGN>::T) k_ntt(const u64 *__restrict_
             } else {                                                     // mode 2: residues * 2^32/N, packed, swizzled
                 v.a = (u32)((u64)v.a * scale1 % FQ_P1);
                 v.b = (u32)((u64)v.b * scale2 % FQ_P2);
-                dst[P::swz(id)] = rns_pack(v);
+                if (mode == 3) dst[e * P::T + tau] = rns_pack(v);          // id = 8*tau + e
+                else dst[P::swz(id)] = rns_pack(v);
             }
         }
     }
@@ -442,6 +454,7 @@ struct BRArgs {
     const u16 *ms;                      // [(lincomb - lc_begin) * B + inst][n+1]
     const u64 *bsk;
     const fq_tw *psi_rev, *psi_inv_rev;
+    const u64 *psi_pow;                 // [2N] packed psi^x mod (p1 | p2 << 32): evaluations of X^x (key-unrolled kernel)
     const int32_t *bs_lc, *bs_slot, *bs_tab_ptr, *bs_mode;
     const u8 *bs_tab;
     u64 *wires; u64 *tap_acc;
@@ -715,6 +728,224 @@ __global__ void __launch_bounds__((PB / TP) * (K + 1) * (1 << LOGN) / 8, 1) k_bl
         if (a.tap_acc) {
             u64 *t = a.tap_acc + (size_t)job[q] * G * N;
             for (int w = ptid; w < G * N; w += C::PT) t[w] = rns_to_int(rns_unpack(A[w]));
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// K2u: blind rotation with TWO key bits per step (key unrolling, params bsk_unroll = 2; L = 1).
+//   X^(a1 s1 + a2 s2) - 1 = (X^(a1+a2) - 1) s1 s2 + (X^a1 - 1) s1 (1 - s2) + (X^a2 - 1) (1 - s1) s2, so with GGSW ciphertexts
+//   G_0, G_1, G_2 of the three bit products:   ACC <- ACC + Dec(ACC) [x] ( sum_c (X^{e_c} - 1) G_c ),   e = (a1+a2, a1, a2).
+// One decomposition and one forward / inverse transform pair serve two key bits; the monomial factors are applied to the
+// KEY in the NTT domain, where X^e is the point-wise multiplication by psi^(e * (2 brev(i) + 1)) (table psi_pow), so the
+// accumulator is decomposed as it is: no rotated reads, ACC lives in registers for the whole blind rotation and shared
+// memory only holds the transpose scratch (32 KB per bootstrap at set A).  Per coefficient and prime the point-wise part is
+//   bundle_u = REDC( sum_c f_c * key_c[u][g] ),  out_g = REDC( sum_u D_u * bundle_u )       (key in Montgomery form twice)
+// i.e. 8 products + 3 reductions against 2 x (2 + 1) for two classic steps, against a whole saved step of transforms.
+// The key is read straight from L2 (coalesced 8-byte loads, layout [ggsw][u][v][e][tau]; it is shared by the bootstraps a
+// thread carries and by all CTAs) -- 1.5 x the classic key per blind rotation, but half as many steps.
+// ------------------------------------------------------------------------------------------------------
+template <int LOGN, int K, int PB, int TP>
+struct BR2Cfg {
+    static_assert(TP == 1 || TP == PB, "a thread carries one bootstrap or all of the CTA's");
+    static constexpr int N = 1 << LOGN, G = K + 1, T = N / 8, PT = G * T, THREADS = (PB / TP) * PT;
+    static constexpr size_t s_w = (size_t)G * N;                  // transpose scratch = digit spectra = final accumulator
+    __host__ __device__ static constexpr size_t ms_stride(int n) { return (((size_t)(n + 1) * 2 + 15) / 16) * 16; }
+    __host__ __device__ static constexpr size_t smem_bytes(int n) { return 8 * PB * s_w + PB * ms_stride(n); }
+};
+__device__ __forceinline__ u64 ldg_stream(const u64 *p)           // read-only, do not keep in L1 (the key streams through once)
+{
+    u64 v;
+    asm volatile("ld.global.nc.L1::no_allocate.b64 %0, [%1];" : "=l"(v) : "l"(p));
+    return v;
+}
+template <int LOGN, int K, int PB, int TP>
+__global__ void __launch_bounds__((PB / TP) * (K + 1) * (1 << LOGN) / 8, 1) k_blind_rotate2(BRArgs a)
+{
+    using C = BR2Cfg<LOGN, K, PB, TP>;
+    using P = NttPlan<LOGN>;
+    constexpr int N = C::N, G = C::G, T = C::T, L = 1;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int tid = threadIdx.x, pb0 = (TP == 1) ? tid / C::PT : 0, ptid = tid % C::PT, g = ptid / T, tau = ptid % T;
+    constexpr size_t PW = C::s_w, PWB = PW * 8;
+    u64 *S = (u64 *)smem_raw + (size_t)pb0 * PW;                 // bootstrap q of this thread: S + q*PW
+    const size_t ms_stride = C::ms_stride(a.n);
+    u16 *s_ms = (u16 *)(smem_raw + 8 * (size_t)PB * PW + (size_t)pb0 * ms_stride);
+    const int n = a.n, p = a.p;
+
+    bool live[TP]; int node[TP], tabL[TP], tab0[TP], mode[TP]; long long inst[TP], job[TP];
+#pragma unroll
+    for (int q = 0; q < TP; q++) {
+        job[q] = a.job_begin + (long long)blockIdx.x * PB + pb0 + q;
+        live[q] = job[q] < a.jobs;
+        if (!live[q]) job[q] = a.jobs - 1;
+        node[q] = a.node_begin + (int)(job[q] / a.B);
+        inst[q] = job[q] % a.B;
+        const u16 *ms = a.ms + ((size_t)(a.bs_lc[node[q]] - a.lc_begin) * a.B + inst[q]) * (size_t)(n + 1);
+        tab0[q] = a.bs_tab_ptr[node[q]]; tabL[q] = a.bs_tab_ptr[node[q] + 1] - tab0[q]; mode[q] = a.bs_mode[node[q]];
+        u16 *dst = (u16 *)((unsigned char *)s_ms + (size_t)q * ms_stride);
+        for (int i = ptid; i <= n; i += C::PT) dst[i] = ms[i];
+    }
+    __syncthreads();
+    // ---- accumulator init in registers: ACC = (0, .., 0, X^{-b~} * TV); this thread holds coefficients j = tau + e*T of polynomial g
+    rns2 av[TP][8];
+#pragma unroll
+    for (int q = 0; q < TP; q++) {
+        const u64 delta = fbs_delta(p), off = fq_mul((u64)mode[q], delta >> 1);
+        const int bt = ((const u16 *)((const unsigned char *)s_ms + (size_t)q * ms_stride))[n];
+#pragma unroll
+        for (int e = 0; e < 8; e++) {
+            const int j = tau + e * T;
+            u64 val = 0;
+            if (g == K) {
+                int src = j + bt;
+                bool neg = false;
+                if (src >= 2 * N) src -= 2 * N;
+                if (src >= N) { src -= N; neg = true; }
+                int x = (int)((2LL * src * p + N) / (2LL * N));
+                if (x >= p) { x -= p; neg = !neg; }
+                const u64 tvx = (x < tabL[q]) ? (u64)__ldg(a.bs_tab + tab0[q] + x) : 0;
+                const u64 F = fq_sub(fq_mul(tvx, delta), off);
+                val = neg ? fq_neg(F) : F;
+            }
+            av[q][e] = rns_from_int(val);
+        }
+    }
+    const int bar_g = 1 + pb0 * G + g, bar_p = 1 + PB * G + pb0;
+    auto gsync = [bar_g] { bar_sync_named(bar_g, T); };
+    auto psync = [bar_p] { if (TP == 1) bar_sync_named(bar_p, C::PT); else __syncthreads(); };
+    const int beta = a.beta;
+    const u64 rc = 1ULL << (62 - beta);
+    constexpr int SH = LOGN + 3;
+    unsigned char *Sb = (unsigned char *)S;
+    u32 bo[LOGN];
+#pragma unroll
+    for (int lb = 0; lb < LOGN; lb++) bo[lb] = P::tau_boff(tau, lb) | ((u32)g << SH);
+    // NTT output position 8*tau + e holds the evaluation at psi^(2 brev(8 tau + e) + 1) = psi^(odd0 + (brev3(e) << (LOGN-2)))
+    const u32 odd0 = 2u * (__brev((u32)tau) >> (32 - (LOGN - 3))) + 1u;
+    // key words of this thread: ggsw-relative index ((u*G + g)*N + e*T + tau), u = (g + og) mod G
+    const u64 *kbase[G];
+#pragma unroll
+    for (int og = 0; og < G; og++) { int gg = g + og; if (gg >= G) gg -= G; kbase[og] = a.bsk + ((size_t)gg * G + g) * N + tau; }
+    constexpr size_t GGSW_W = (size_t)G * G * N;                  // words per GGSW
+
+    for (int t = 0; t < n / 2; t++) {
+        // ---- decompose ACC_g itself: one balanced digit per coefficient (L = 1), lazy residues in (0, 2p)
+        rns2 dg[1][TP][8];
+#pragma unroll
+        for (int q = 0; q < TP; q++)
+#pragma unroll
+            for (int e = 0; e < 8; e++) {
+                const u32 tt = rns_crt_hi(av[q][e]);
+                const u32 d = (u32)fbs_digit1_t(tt, av[q][e].a, beta, rc);
+                dg[0][q][e].a = d + FQ_P1;
+                dg[0][q][e].b = d + FQ_P2;
+            }
+        ntt_fwd1_from<LOGN, 0, TP>(dg[0], tau, Sb, PWB, bo, a.psi_rev, gsync, true, a.zero);
+#pragma unroll
+        for (int e = 0; e < 8; e++) {
+            const u32 o = bo[0] ^ P::elem_boff(e, 0);
+#pragma unroll
+            for (int q = 0; q < TP; q++) {
+                dg[0][q][e].a = r32_fold(dg[0][q][e].a, 2 * FQ_P1);     // < 2p: keeps the sums below within 64 bits / the folds in range
+                dg[0][q][e].b = r32_fold(dg[0][q][e].b, 2 * FQ_P2);
+                *(u64 *)(Sb + q * PWB + o) = rns_pack(dg[0][q][e]);
+            }
+        }
+        // exponents of the three monomial factors, per bootstrap: E_c * odd0 and the per-element step E_c << (LOGN-2)
+        u32 eb[TP][3], es[TP][3];
+#pragma unroll
+        for (int q = 0; q < TP; q++) {
+            const u16 *msq = (const u16 *)((const unsigned char *)s_ms + (size_t)q * ms_stride);
+            const u32 a1 = msq[2 * t], a2 = msq[2 * t + 1];
+            const u32 E[3] = {a1 + a2, a1, a2};
+#pragma unroll
+            for (int c = 0; c < 3; c++) { eb[q][c] = E[c] * odd0; es[q][c] = E[c] << (LOGN - 2); }
+        }
+        psync();
+        // ---- point-wise part
+        rns2 x[TP][8];
+        const u64 *kt = nullptr;
+#pragma unroll
+        for (int e = 0; e < 8; e++) {
+            const u32 o = bo[0] ^ P::elem_boff(e, 0);
+            constexpr int BR3[8] = {0, 4, 2, 6, 1, 5, 3, 7};
+            rns2 kk[3][G];
+#pragma unroll
+            for (int c = 0; c < 3; c++)
+#pragma unroll
+                for (int og = 0; og < G; og++)
+                    kk[c][og] = rns_unpack(ldg_stream(kbase[og] + ((size_t)(3 * t + c)) * GGSW_W + (size_t)e * T));
+#pragma unroll
+            for (int q = 0; q < TP; q++) {
+                rns2 f[3];
+#pragma unroll
+                for (int c = 0; c < 3; c++) {
+                    const u32 xi = (eb[q][c] + (u32)BR3[e] * es[q][c]) & (2 * N - 1);
+                    f[c] = rns_unpack(__ldg(a.psi_pow + xi));
+                    f[c].a -= 1; f[c].b -= 1;                            // X^E - 1 at this point, canonical (psi^x >= 1)
+                }
+                u64 oa = 0, ob = 0;
+#pragma unroll
+                for (int og = 0; og < G; og++) {
+                    u64 pa = (u64)f[0].a * kk[0][og].a, pb2 = (u64)f[0].b * kk[0][og].b;
+                    pa += (u64)f[1].a * kk[1][og].a; pb2 += (u64)f[1].b * kk[1][og].b;
+                    pa += (u64)f[2].a * kk[2][og].a; pb2 += (u64)f[2].b * kk[2][og].b;           // < 3 p^2
+                    const u32 ba = r32_redc(pa, FQ_P1, FQ_P1_INVNEG), bb = r32_redc(pb2, FQ_P2, FQ_P2_INVNEG);   // < 1.75 p + 1
+                    rns2 d;
+                    if (og == 0) d = dg[0][q][e];
+                    else {
+                        int gg = g + og; if (gg >= G) gg -= G;
+                        const u32 xg = (G == 2) ? (1u << SH) : ((u32)(g ^ gg) << SH);
+                        d = rns_unpack(*(const u64 *)(Sb + q * PWB + (o ^ xg)));
+                    }
+                    if (og == 0) { oa = (u64)d.a * ba; ob = (u64)d.b * bb; }
+                    else { oa += (u64)d.a * ba; ob += (u64)d.b * bb; }                            // < G * 3.5 p^2
+                }
+                x[q][e].a = r32_fold(r32_redc(oa, FQ_P1, FQ_P1_INVNEG), 2 * FQ_P1);
+                x[q][e].b = r32_fold(r32_redc(ob, FQ_P2, FQ_P2_INVNEG), 2 * FQ_P2);
+            }
+        }
+        (void)kt;
+        auto after_pass0 = [&] { __syncthreads(); };             // nobody reads this step's digit spectra any more
+        ntt_inv1_from<LOGN, 0, TP>(x, tau, Sb, PWB, bo, a.psi_rev, after_pass0, gsync, a.zero);
+#pragma unroll
+        for (int e = 0; e < 8; e++)
+#pragma unroll
+            for (int q = 0; q < TP; q++) {
+                av[q][e].a = r32_csub(r32_fold(av[q][e].a + x[q][e].a + a.zero, 2 * FQ_P1), FQ_P1);
+                av[q][e].b = r32_csub(r32_fold(av[q][e].b + x[q][e].b + a.zero, 2 * FQ_P2), FQ_P2);
+            }
+    }
+    // ---- accumulator to shared memory (natural order), then K3 as in k_blind_rotate
+    gsync();                                             // the group's last transposed reads are done
+#pragma unroll
+    for (int q = 0; q < TP; q++)
+#pragma unroll
+        for (int e = 0; e < 8; e++) S[q * PW + (size_t)g * N + tau + e * T] = rns_pack(av[q][e]);
+    psync();
+#pragma unroll
+    for (int q = 0; q < TP; q++) {
+        if (!live[q]) continue;
+        const u64 *A = S + q * PW;
+        const size_t CT = (size_t)K * N + 1;
+        const size_t off = ((size_t)a.bs_slot[node[q]] * a.B + inst[q]) * CT;
+        u64 *out = a.wires + off;
+        for (int w = ptid; w < K * N; w += C::PT) {
+            const int u = w / N, j = w % N;
+            const rns2 v = rns_unpack(A[(size_t)u * N + (j == 0 ? 0 : N - j)]);
+            const u64 val = rns_to_int(j == 0 ? v : rns_neg(v));
+            out[w] = val;
+            for (int pr = 0; pr < a.n_peers; pr++) a.peer_wires[pr][off + w] = val;
+        }
+        if (ptid == 0) {
+            const u64 val = fq_add(rns_to_int(rns_unpack(A[(size_t)K * N])), fq_mul((u64)mode[q], fbs_delta(p) >> 1));
+            out[(size_t)K * N] = val;
+            for (int pr = 0; pr < a.n_peers; pr++) a.peer_wires[pr][off + (size_t)K * N] = val;
+        }
+        if (a.tap_acc) {
+            u64 *t2 = a.tap_acc + (size_t)job[q] * G * N;
+            for (int w = ptid; w < G * N; w += C::PT) t2[w] = rns_to_int(rns_unpack(A[w]));
         }
     }
 }

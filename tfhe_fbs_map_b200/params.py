@@ -34,6 +34,7 @@ class ParamSet:
     lwe_sigma: float  # std of small-LWE (KSK) noise, torus units
     glwe_sigma: float # std of GLWE (BSK, fresh input) noise, torus units
     secure: bool = True
+    bsk_unroll: int = 1  # 2 = two key bits per blind-rotation step (three GGSW per key pair, n/2 steps; n must be even)
 
     @property
     def big_dim(self) -> int:
@@ -52,8 +53,12 @@ class ParamSet:
         return max(0, int(round(self.glwe_sigma * GOLDILOCKS_P)))
 
     @property
+    def n_ggsw(self) -> int:
+        return 3 * (self.n // 2) if self.bsk_unroll == 2 else self.n
+
+    @property
     def bsk_bytes(self) -> int:
-        return self.n * (self.k + 1) ** 2 * self.bsk_l * self.N * 8
+        return self.n_ggsw * (self.k + 1) ** 2 * self.bsk_l * self.N * 8
 
     @property
     def ksk_bytes(self) -> int:
@@ -75,9 +80,14 @@ class ParamSet:
         B = 2.0 ** self.bsk_beta
         Bk = 2.0 ** self.ks_beta
         kN = self.k * self.N
-        v_step = (self.bsk_l * (self.k + 1) * self.N * (B * B + 2) / 12.0 * self.glwe_sigma ** 2
-                  + (1 + kN / 2.0) / (24.0 * B ** (2 * self.bsk_l)))
-        v_br = self.n * v_step
+        t_key = self.bsk_l * (self.k + 1) * self.N * (B * B + 2) / 12.0 * self.glwe_sigma ** 2     # GGSW noise through the digits
+        t_round = (1 + kN / 2.0) / (24.0 * B ** (2 * self.bsk_l))                                 # rounding error times a key bit (E m^2 = 1/2)
+        if self.bsk_unroll == 2:
+            # one external product per key PAIR with the bundle sum_c (X^{e_c} - 1) GGSW_c: three key-noise terms scaled by
+            # |X^e - 1|^2 = 2, and a plaintext X^e - 1 (norm^2 2, present with probability 3/4) instead of a bit
+            v_br = (self.n / 2.0) * (6.0 * t_key + 3.0 * t_round)
+        else:
+            v_br = self.n * (t_key + t_round)
         v_ks = kN * (self.ks_l * (Bk * Bk + 2) / 12.0 * self.lwe_sigma ** 2 + 1.0 / (24.0 * Bk ** (2 * self.ks_l)))
         v_ms = (1.0 / 12.0 + self.n / 24.0) / (2.0 * self.N) ** 2
         return dict(v_br=v_br, v_ks=v_ks, v_ms=v_ms, v_in=norm2 * v_br + v_ks + v_ms)
@@ -95,12 +105,12 @@ class CParams(ctypes.Structure):
     """Mirror of ``fbs_params`` in include/fbs_b200.h."""
     _fields_ = [("n", ctypes.c_int32), ("k", ctypes.c_int32), ("N", ctypes.c_int32),
                 ("bsk_l", ctypes.c_int32), ("bsk_beta", ctypes.c_int32),
-                ("ks_l", ctypes.c_int32), ("ks_beta", ctypes.c_int32), ("reserved", ctypes.c_int32),
+                ("ks_l", ctypes.c_int32), ("ks_beta", ctypes.c_int32), ("bsk_unroll", ctypes.c_int32),
                 ("lwe_noise", ctypes.c_uint64), ("glwe_noise", ctypes.c_uint64)]
 
 
 def to_c(ps: ParamSet) -> CParams:
-    return CParams(ps.n, ps.k, ps.N, ps.bsk_l, ps.bsk_beta, ps.ks_l, ps.ks_beta, 0,
+    return CParams(ps.n, ps.k, ps.N, ps.bsk_l, ps.bsk_beta, ps.ks_l, ps.ks_beta, ps.bsk_unroll,
                    ps.lwe_noise_scale, ps.glwe_noise_scale)
 
 
@@ -132,7 +142,17 @@ TOY_5 = ParamSet("toy5", n=10, k=1, N=2048, bsk_l=1, bsk_beta=23, ks_l=5, ks_bet
 TOY_6 = ParamSet("toy6", n=8, k=1, N=2048, bsk_l=2, bsk_beta=15, ks_l=6, ks_beta=3,
                  lwe_sigma=2.0 ** -30, glwe_sigma=2.0 ** -52, secure=False)
 
-PARAM_SETS = {ps.name: ps for ps in (SET_A, SET_C, SET_S, TOY_1, TOY_2, TOY_3, TOY_4, TOY_5, TOY_6)}
+
+def _unrolled(ps: ParamSet, name: str) -> ParamSet:
+    d = asdict(ps); d.update(name=name, bsk_unroll=2)
+    return ParamSet(**d)
+
+
+# key-unrolled twins (two key bits per blind-rotation step, 1.5x the bootstrapping key): same security and shape
+SET_A2 = _unrolled(SET_A, "A2")
+TOY_2U, TOY_3U, TOY_5U = _unrolled(TOY_2, "toy2u"), _unrolled(TOY_3, "toy3u"), _unrolled(TOY_5, "toy5u")
+
+PARAM_SETS = {ps.name: ps for ps in (SET_A, SET_A2, SET_C, SET_S, TOY_1, TOY_2, TOY_3, TOY_4, TOY_5, TOY_6, TOY_2U, TOY_3U, TOY_5U)}
 DEFAULT_SET = "A"
 
 
