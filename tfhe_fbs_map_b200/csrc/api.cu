@@ -72,11 +72,11 @@ static const BRVariant g_br_variants[] = {
     BRV2(9, 1, 2, 2), BRV2(8, 2, 2, 1),            // toy3u, toy2u
 };
 
-typedef void (*ntt_launch_fn)(const u64 *, u64 *, int, const fq_tw *, const fq_tw *, u32, u32, long long, cudaStream_t);
+typedef void (*ntt_launch_fn)(const u64 *, u64 *, int, const fq_tw *, const fq_tw *, u32, u32, long long, cudaStream_t, int);
 template <int LOGN>
-static void ntt_launch(const u64 *in, u64 *out, int mode, const fq_tw *pr, const fq_tw *pir, u32 s1, u32 s2, long long count, cudaStream_t st)
+static void ntt_launch(const u64 *in, u64 *out, int mode, const fq_tw *pr, const fq_tw *pir, u32 s1, u32 s2, long long count, cudaStream_t st, int g1)
 {
-    k_ntt<LOGN><<<(unsigned)count, NttPlan<LOGN>::T, 0, st>>>(in, out, mode, pr, pir, s1, s2);
+    k_ntt<LOGN><<<(unsigned)count, NttPlan<LOGN>::T, 0, st>>>(in, out, mode, pr, pir, s1, s2, g1);
 }
 static ntt_launch_fn ntt_for(int logN)
 {
@@ -251,8 +251,8 @@ extern "C" int fbs_keygen(fbs_ctx *c)
     k_bsk_body<<<c->n_ggsw * rows, 256, (size_t)N * 9, st>>>(c->d_bsk_coef, k, N, l, c->d_s_lwe, c->d_s_big, c->d_gad_bsk, c->unroll);
     ntt_launch_fn nf = ntt_for(c->logN);
     if (!nf) return fail(FBS_ERR_ARG, "no NTT kernel for this N");
-    if (c->unroll == 2) nf(c->d_bsk_coef, c->d_bsk, 3, c->d_psi_rev, c->d_psi_inv_rev, c->mont2_ninv[0], c->mont2_ninv[1], (long long)(total / N), st);
-    else nf(c->d_bsk_coef, c->d_bsk, 2, c->d_psi_rev, c->d_psi_inv_rev, c->mont_ninv[0], c->mont_ninv[1], (long long)(total / N), st);
+    if (c->unroll == 2) nf(c->d_bsk_coef, c->d_bsk, 3, c->d_psi_rev, c->d_psi_inv_rev, c->mont2_ninv[0], c->mont2_ninv[1], (long long)(total / N), st, k + 1);
+    else nf(c->d_bsk_coef, c->d_bsk, 2, c->d_psi_rev, c->d_psi_inv_rev, c->mont_ninv[0], c->mont_ninv[1], (long long)(total / N), st, k + 1);
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(st));
     // the coefficient-domain copy is only a parity tap: keep it for toy sizes, drop it for real key sizes
@@ -677,7 +677,7 @@ extern "C" int fbs_debug_ntt(fbs_ctx *c, uint64_t *polys, int64_t count, int32_t
     u64 *d_a = nullptr, *d_b = nullptr; const size_t words = (size_t)count * c->P.N;
     CKR(dev_alloc(&d_a, words)); CKR(dev_alloc(&d_b, words));
     CK(cudaMemcpy(d_a, polys, words * 8, cudaMemcpyHostToDevice));
-    nf(d_a, d_b, inverse ? 1 : 0, c->d_psi_rev, c->d_psi_inv_rev, c->ninv[0], c->ninv[1], count, c->stream);
+    nf(d_a, d_b, inverse ? 1 : 0, c->d_psi_rev, c->d_psi_inv_rev, c->ninv[0], c->ninv[1], count, c->stream, c->P.k + 1);
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(c->stream));
     CK(cudaMemcpy(polys, d_b, words * 8, cudaMemcpyDeviceToHost));

@@ -152,12 +152,12 @@ __global__ void __launch_bounds__(256) k_bsk_body(u64 *bsk, int k, int N, int l,
 //                               transform's 1/N folded in), packed (mod p1 | mod p2 << 32), stored SWIZZLED for the
 //                               blind-rotate kernel
 //                       mode 3: key-unrolled BSK preprocessing: as mode 2 with the caller's scale 2^64/N (Montgomery form
-//                               twice: the key goes through two reductions), stored as [e][tau] so that k_blind_rotate2's
-//                               direct global loads coalesce
+//                               twice: the key goes through two reductions), stored as [key pair][element e][c][u][v][tau]: the
+//                               words k_blind_rotate2 needs for one element are one contiguous slice (one bulk copy)
 // ------------------------------------------------------------------------------------------------------
 template <int LOGN>
 __global__ void __launch_bounds__(NttPlan<LOGN>::T) k_ntt(const u64 *__restrict__ in, u64 *__restrict__ out, int mode,
-                                                         const fq_tw *__restrict__ psi_rev, const fq_tw *__restrict__ psi_inv_rev, u32 scale1, u32 scale2)
+                                                         const fq_tw *__restrict__ psi_rev, const fq_tw *__restrict__ psi_inv_rev, u32 scale1, u32 scale2, int g1 /* k+1, mode 3 */)
 {
     using P = NttPlan<LOGN>;
     __shared__ u64 bufA[P::N];
@@ -193,7 +193,10 @@ __global__ void __launch_bounds__(NttPlan<LOGN>::T) k_ntt(const u64 *__restrict_
             } else {                                                     // mode 2: residues * 2^32/N, packed, swizzled
                 v.a = (u32)((u64)v.a * scale1 % FQ_P1);
                 v.b = (u32)((u64)v.b * scale2 % FQ_P2);
-                if (mode == 3) dst[e * P::T + tau] = rns_pack(v);          // id = 8*tau + e
+                if (mode == 3) {                                          // polynomial (ggsw = 3t + c, u, v); id = 8*tau + e
+                    const int pv = blockIdx.x % (g1 * g1), ggsw = blockIdx.x / (g1 * g1), t = ggsw / 3, c = ggsw % 3;
+                    out[(((size_t)t * 8 + e) * 3 + c) * g1 * g1 * P::T + (size_t)pv * P::T + tau] = rns_pack(v);
+                }
                 else dst[P::swz(id)] = rns_pack(v);
             }
         }
@@ -750,28 +753,34 @@ struct BR2Cfg {
     static_assert(TP == 1 || TP == PB, "a thread carries one bootstrap or all of the CTA's");
     static constexpr int N = 1 << LOGN, G = K + 1, T = N / 8, PT = G * T, THREADS = (PB / TP) * PT;
     static constexpr size_t s_w = (size_t)G * N;                  // transpose scratch = digit spectra = final accumulator
+    static constexpr size_t psi_w = 2 * (size_t)N;                // psi^x table
+    // Key slice = every key word the CTA needs for ONE of the 8 elements a thread holds: [c < 3][u < G][v < G][tau < T]; a step
+    // consumes 8 slices in element order.  HBM layout [key pair][element][c][u][v][tau]: one contiguous bulk copy per slice.
+    static constexpr size_t slice_w = 3 * (size_t)G * G * T;
+    static constexpr size_t fixed_b = 8 * (PB * s_w + psi_w) + PB * 2048 + 256;          // ms rows budgeted for n < 1024
+    static constexpr int R_fit = (int)((227 * 1024 - fixed_b) / (8 * slice_w));
+    static constexpr int R = R_fit > 8 ? 8 : R_fit;                                         // ring slots (prefetch distance)
+    static_assert(R >= 2, "key ring does not fit shared memory");
     __host__ __device__ static constexpr size_t ms_stride(int n) { return (((size_t)(n + 1) * 2 + 15) / 16) * 16; }
-    __host__ __device__ static constexpr size_t smem_bytes(int n) { return 8 * PB * s_w + PB * ms_stride(n); }
+    __host__ __device__ static constexpr size_t smem_bytes(int n) { return 8 * (PB * s_w + psi_w + R * slice_w + 2 * R) + PB * ms_stride(n); }
 };
-__device__ __forceinline__ u64 ldg_stream(const u64 *p)           // read-only, do not keep in L1 (the key streams through once)
-{
-    u64 v;
-    asm volatile("ld.global.nc.L1::no_allocate.b64 %0, [%1];" : "=l"(v) : "l"(p));
-    return v;
-}
 template <int LOGN, int K, int PB, int TP>
 __global__ void __launch_bounds__((PB / TP) * (K + 1) * (1 << LOGN) / 8, 1) k_blind_rotate2(BRArgs a)
 {
     using C = BR2Cfg<LOGN, K, PB, TP>;
     using P = NttPlan<LOGN>;
-    constexpr int N = C::N, G = C::G, T = C::T, L = 1;
+    constexpr int N = C::N, G = C::G, T = C::T, R = C::R;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int tid = threadIdx.x, pb0 = (TP == 1) ? tid / C::PT : 0, ptid = tid % C::PT, g = ptid / T, tau = ptid % T;
     constexpr size_t PW = C::s_w, PWB = PW * 8;
     u64 *S = (u64 *)smem_raw + (size_t)pb0 * PW;                 // bootstrap q of this thread: S + q*PW
+    u64 *PSI = (u64 *)smem_raw + (size_t)PB * PW;
+    u64 *RING = PSI + C::psi_w;
+    u64 *full = RING + (size_t)R * C::slice_w, *empty = full + R;  // mbarriers: slice landed / slice consumed by every warp
     const size_t ms_stride = C::ms_stride(a.n);
-    u16 *s_ms = (u16 *)(smem_raw + 8 * (size_t)PB * PW + (size_t)pb0 * ms_stride);
+    u16 *s_ms = (u16 *)((unsigned char *)(empty + R) + (size_t)pb0 * ms_stride);
     const int n = a.n, p = a.p;
+    const int n_slices = 8 * (n / 2);
 
     bool live[TP]; int node[TP], tabL[TP], tab0[TP], mode[TP]; long long inst[TP], job[TP];
 #pragma unroll
@@ -786,7 +795,21 @@ __global__ void __launch_bounds__((PB / TP) * (K + 1) * (1 << LOGN) / 8, 1) k_bl
         u16 *dst = (u16 *)((unsigned char *)s_ms + (size_t)q * ms_stride);
         for (int i = ptid; i <= n; i += C::PT) dst[i] = ms[i];
     }
+    // psi^x table, low index nibble XOR-folded with the next two: the lanes of a warp look up exponents that differ by
+    // multiples of 16 E (bit-reversed evaluation points), which would all fall into one bank pair otherwise
+    auto psw = [](u32 x) { return x ^ (((x >> 4) ^ (x >> 8)) & 15u); };
+    for (int i = tid; i < 2 * N; i += C::THREADS) PSI[psw((u32)i)] = a.psi_pow[i];
+    if (tid == 0) {
+        for (int r = 0; r < R; r++) { mbar_init(full + r, 1); mbar_init(empty + r, C::THREADS / 32); }
+    }
     __syncthreads();
+    if (tid == 0) {                                             // prologue: the first R slices
+        fence_proxy_async();
+        for (int sl = 0; sl < R && sl < n_slices; sl++) {
+            mbar_expect_tx(full + sl, (u32)(C::slice_w * 8));
+            tma_load_1d(RING + (size_t)sl * C::slice_w, a.bsk + (size_t)sl * C::slice_w, (u32)(C::slice_w * 8), full + sl);
+        }
+    }
     // ---- accumulator init in registers: ACC = (0, .., 0, X^{-b~} * TV); this thread holds coefficients j = tau + e*T of polynomial g
     rns2 av[TP][8];
 #pragma unroll
@@ -823,11 +846,11 @@ __global__ void __launch_bounds__((PB / TP) * (K + 1) * (1 << LOGN) / 8, 1) k_bl
     for (int lb = 0; lb < LOGN; lb++) bo[lb] = P::tau_boff(tau, lb) | ((u32)g << SH);
     // NTT output position 8*tau + e holds the evaluation at psi^(2 brev(8 tau + e) + 1) = psi^(odd0 + (brev3(e) << (LOGN-2)))
     const u32 odd0 = 2u * (__brev((u32)tau) >> (32 - (LOGN - 3))) + 1u;
-    // key words of this thread: ggsw-relative index ((u*G + g)*N + e*T + tau), u = (g + og) mod G
-    const u64 *kbase[G];
+    // key words of this thread inside a slice: ((c*G + u)*G + g)*T + tau, u = (g + og) mod G
+    u32 koff[G];
 #pragma unroll
-    for (int og = 0; og < G; og++) { int gg = g + og; if (gg >= G) gg -= G; kbase[og] = a.bsk + ((size_t)gg * G + g) * N + tau; }
-    constexpr size_t GGSW_W = (size_t)G * G * N;                  // words per GGSW
+    for (int og = 0; og < G; og++) { int gg = g + og; if (gg >= G) gg -= G; koff[og] = (u32)(((gg * G + g) * T + tau) * 8); }
+    int slot = 0; u32 par = 0;                                    // ring position of the next slice to consume
 
     for (int t = 0; t < n / 2; t++) {
         // ---- decompose ACC_g itself: one balanced digit per coefficient (L = 1), lazy residues in (0, 2p)
@@ -863,26 +886,26 @@ __global__ void __launch_bounds__((PB / TP) * (K + 1) * (1 << LOGN) / 8, 1) k_bl
             for (int c = 0; c < 3; c++) { eb[q][c] = E[c] * odd0; es[q][c] = E[c] << (LOGN - 2); }
         }
         psync();
-        // ---- point-wise part
+        // ---- point-wise part, one key slice per element
         rns2 x[TP][8];
-        const u64 *kt = nullptr;
 #pragma unroll
         for (int e = 0; e < 8; e++) {
             const u32 o = bo[0] ^ P::elem_boff(e, 0);
             constexpr int BR3[8] = {0, 4, 2, 6, 1, 5, 3, 7};
+            mbar_wait(full + slot, par);
+            const unsigned char *ks = (const unsigned char *)(RING + (size_t)slot * C::slice_w);
             rns2 kk[3][G];
 #pragma unroll
             for (int c = 0; c < 3; c++)
 #pragma unroll
-                for (int og = 0; og < G; og++)
-                    kk[c][og] = rns_unpack(ldg_stream(kbase[og] + ((size_t)(3 * t + c)) * GGSW_W + (size_t)e * T));
+                for (int og = 0; og < G; og++) kk[c][og] = rns_unpack(*(const u64 *)(ks + koff[og] + (size_t)c * G * G * T * 8));
 #pragma unroll
             for (int q = 0; q < TP; q++) {
                 rns2 f[3];
 #pragma unroll
                 for (int c = 0; c < 3; c++) {
                     const u32 xi = (eb[q][c] + (u32)BR3[e] * es[q][c]) & (2 * N - 1);
-                    f[c] = rns_unpack(__ldg(a.psi_pow + xi));
+                    f[c] = rns_unpack(PSI[psw(xi)]);
                     f[c].a -= 1; f[c].b -= 1;                            // X^E - 1 at this point, canonical (psi^x >= 1)
                 }
                 u64 oa = 0, ob = 0;
@@ -905,8 +928,21 @@ __global__ void __launch_bounds__((PB / TP) * (K + 1) * (1 << LOGN) / 8, 1) k_bl
                 x[q][e].a = r32_fold(r32_redc(oa, FQ_P1, FQ_P1_INVNEG), 2 * FQ_P1);
                 x[q][e].b = r32_fold(r32_redc(ob, FQ_P2, FQ_P2_INVNEG), 2 * FQ_P2);
             }
+            // slice consumed by this warp (its key words are in registers); when every warp is through, thread 0 refills
+            // the slot with the slice R ahead, so the copy overlaps R - 1 elements' worth of arithmetic or the transforms
+            __syncwarp();
+            if ((tid & 31) == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(empty + slot)) : "memory");
+            if (tid == 0) {
+                const int nxt = 8 * t + e + R;
+                if (nxt < n_slices) {
+                    mbar_wait(empty + slot, par);
+                    fence_proxy_async();
+                    mbar_expect_tx(full + slot, (u32)(C::slice_w * 8));
+                    tma_load_1d(RING + (size_t)slot * C::slice_w, a.bsk + (size_t)nxt * C::slice_w, (u32)(C::slice_w * 8), full + slot);
+                }
+            }
+            if (++slot == R) { slot = 0; par ^= 1; }
         }
-        (void)kt;
         auto after_pass0 = [&] { __syncthreads(); };             // nobody reads this step's digit spectra any more
         ntt_inv1_from<LOGN, 0, TP>(x, tau, Sb, PWB, bo, a.psi_rev, after_pass0, gsync, a.zero);
 #pragma unroll
