@@ -95,7 +95,7 @@ struct fbs_ctx {
     u8 *d_kbt = nullptr;                                       // byte-transposed KSK for the tensor-core key switch
     int n_peers = 0; u64 *peers[8] = {};                       // peer replicas of the wire buffer (fbs_set_peers)
     fq_tw *d_psi_rev = nullptr, *d_psi_inv_rev = nullptr;
-    u64 *d_psi_pow = nullptr;                                  // psi^x, x < 2N, packed residues (key-unrolled kernel)
+    u64 *d_psi_pow = nullptr;                                  // psi^x - 1, x < 2N, packed residues (key-unrolled kernel)
     int unroll = 1, n_ggsw = 0; u32 mont2_ninv[2] = {0, 0};    // 2^64/N per prime
     u64 *d_gad_bsk = nullptr, *d_gad_ks = nullptr;
     u32 ninv[2] = {0, 0}, mont_ninv[2] = {0, 0};     // 1/N and 2^32/N per prime
@@ -206,7 +206,7 @@ static int ctx_create_impl(const fbs_params *params, int device, uint64_t seed, 
         std::vector<u64> pp(2 * (size_t)N);
         const u64 ps1 = pow_mod_host(3, (FQ_P1 - 1) / (2ULL * N), FQ_P1), ps2 = pow_mod_host(3, (FQ_P2 - 1) / (2ULL * N), FQ_P2);
         u64 x1 = 1, x2 = 1;
-        for (int x = 0; x < 2 * N; x++) { pp[x] = x1 | (x2 << 32); x1 = x1 * ps1 % FQ_P1; x2 = x2 * ps2 % FQ_P2; }
+        for (int x = 0; x < 2 * N; x++) { pp[x] = (x1 - 1) | ((x2 - 1) << 32); x1 = x1 * ps1 % FQ_P1; x2 = x2 * ps2 % FQ_P2; }   // psi^x - 1 (psi^x >= 1)
         CKR(dev_alloc(&c->d_psi_pow, 2 * (size_t)N));
         CK(cudaMemcpy(c->d_psi_pow, pp.data(), 16 * (size_t)N, cudaMemcpyHostToDevice));
     }

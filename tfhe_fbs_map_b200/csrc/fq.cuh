@@ -153,6 +153,16 @@ FQ_HD u32 r32_csub(u32 x, u32 p)                       // x >= p ? x - p : x, wr
 struct rns2 { u32 a, b; };
 FQ_HD u64 rns_pack(rns2 v) { return (u64)v.a | ((u64)v.b << 32); }
 FQ_HD rns2 rns_unpack(u64 w) { rns2 v; v.a = (u32)w; v.b = (u32)(w >> 32); return v; }
+FQ_HD rns2 rns_split(u64 w)                             // rns_unpack with the halves as opaque 32-bit registers
+{
+    rns2 v;
+#if defined(__CUDA_ARCH__)
+    asm("mov.b64 {%0, %1}, %2;" : "=r"(v.a), "=r"(v.b) : "l"(w));
+#else
+    v.a = (u32)w; v.b = (u32)(w >> 32);
+#endif
+    return v;
+}
 FQ_HD rns2 rns_from_int(u64 x) { rns2 v; v.a = (u32)(x % FQ_P1); v.b = (u32)(x % FQ_P2); return v; }   // x < 2^64
 FQ_HD rns2 rns_from_small(int d)                      // |d| < 2^29
 {

@@ -457,7 +457,7 @@ struct BRArgs {
     const u16 *ms;                      // [(lincomb - lc_begin) * B + inst][n+1]
     const u64 *bsk;
     const fq_tw *psi_rev, *psi_inv_rev;
-    const u64 *psi_pow;                 // [2N] packed psi^x mod (p1 | p2 << 32): evaluations of X^x (key-unrolled kernel)
+    const u64 *psi_pow;                 // [2N] packed (psi^x - 1) mod (p1 | p2 << 32): evaluations of X^x - 1 (key-unrolled kernel)
     const int32_t *bs_lc, *bs_slot, *bs_tab_ptr, *bs_mode;
     const u8 *bs_tab;
     u64 *wires; u64 *tap_acc;
@@ -875,15 +875,26 @@ __global__ void __launch_bounds__((PB / TP) * (K + 1) * (1 << LOGN) / 8, 1) k_bl
                 *(u64 *)(Sb + q * PWB + o) = rns_pack(dg[0][q][e]);
             }
         }
-        // exponents of the three monomial factors, per bootstrap: E_c * odd0 and the per-element step E_c << (LOGN-2)
-        u32 eb[TP][3], es[TP][3];
+        // Exponents of the three monomial factors.  Element e evaluates X^E at psi^(E*odd0 + (brev3(e) << (LOGN-2)) * E): the
+        // low LOGN-2 bits of the table index are the same for the 8 elements, only the top three move (by brev3(e) * E mod 8).
+        // With the table's XOR fold (psw) that is: byte offset = lo8 ^ (h * HMUL), h = (hb + brev3(e)*E) & 7, where lo8 has the
+        // fold of the fixed bits applied and HMUL places h at bits LOGN-2.. and (its part of nibble 2) into the low nibble.
+        constexpr bool fast_psi = (LOGN - 2 >= 9) && (LOGN + 1 <= 12);        // top-3 bits lie inside nibble 2, nibble 1 is fixed
+        constexpr u32 HMUL = 8u * ((1u << (LOGN - 2)) | (fast_psi ? (1u << (LOGN - 2 - 8)) : 0u));
+        u32 lo8[TP][3], hb[TP][3], eb[TP][3], Ec[TP][3];
 #pragma unroll
         for (int q = 0; q < TP; q++) {
             const u16 *msq = (const u16 *)((const unsigned char *)s_ms + (size_t)q * ms_stride);
             const u32 a1 = msq[2 * t], a2 = msq[2 * t + 1];
             const u32 E[3] = {a1 + a2, a1, a2};
 #pragma unroll
-            for (int c = 0; c < 3; c++) { eb[q][c] = E[c] * odd0; es[q][c] = E[c] << (LOGN - 2); }
+            for (int c = 0; c < 3; c++) {
+                const u32 x0 = (E[c] * odd0) & (2 * N - 1);
+                Ec[q][c] = E[c]; eb[q][c] = x0;
+                hb[q][c] = x0 >> (LOGN - 2);
+                const u32 lo = x0 & ((1u << (LOGN - 2)) - 1);
+                lo8[q][c] = 8u * (lo ^ (((lo >> 4) ^ (lo >> 8)) & 15u));       // fold of the fixed bits (bits >= LOGN-2 excluded)
+            }
         }
         psync();
         // ---- point-wise part, one key slice per element
@@ -898,32 +909,34 @@ __global__ void __launch_bounds__((PB / TP) * (K + 1) * (1 << LOGN) / 8, 1) k_bl
 #pragma unroll
             for (int c = 0; c < 3; c++)
 #pragma unroll
-                for (int og = 0; og < G; og++) kk[c][og] = rns_unpack(*(const u64 *)(ks + koff[og] + (size_t)c * G * G * T * 8));
+                for (int og = 0; og < G; og++) kk[c][og] = rns_split(*(const u64 *)(ks + koff[og] + (size_t)c * G * G * T * 8));
 #pragma unroll
             for (int q = 0; q < TP; q++) {
                 rns2 f[3];
 #pragma unroll
                 for (int c = 0; c < 3; c++) {
-                    const u32 xi = (eb[q][c] + (u32)BR3[e] * es[q][c]) & (2 * N - 1);
-                    f[c] = rns_unpack(PSI[psw(xi)]);
-                    f[c].a -= 1; f[c].b -= 1;                            // X^E - 1 at this point, canonical (psi^x >= 1)
+                    if constexpr (fast_psi) {
+                        const u32 h = (hb[q][c] + (u32)BR3[e] * Ec[q][c]) & 7u;
+                        f[c] = rns_split(*(const u64 *)((const unsigned char *)PSI + (lo8[q][c] ^ (h * HMUL))));
+                    } else {
+                        const u32 xi = (eb[q][c] + (((u32)BR3[e] * Ec[q][c]) << (LOGN - 2))) & (2 * N - 1);
+                        f[c] = rns_split(PSI[psw(xi)]);
+                    }
                 }
                 u64 oa = 0, ob = 0;
 #pragma unroll
                 for (int og = 0; og < G; og++) {
-                    u64 pa = (u64)f[0].a * kk[0][og].a, pb2 = (u64)f[0].b * kk[0][og].b;
-                    pa += (u64)f[1].a * kk[1][og].a; pb2 += (u64)f[1].b * kk[1][og].b;
-                    pa += (u64)f[2].a * kk[2][og].a; pb2 += (u64)f[2].b * kk[2][og].b;           // < 3 p^2
+                    u64 pa = r32_mulwide(f[0].a, kk[0][og].a), pb2 = r32_mulwide(f[0].b, kk[0][og].b);
+                    pa = r32_madwide(f[1].a, kk[1][og].a, pa); pb2 = r32_madwide(f[1].b, kk[1][og].b, pb2);
+                    pa = r32_madwide(f[2].a, kk[2][og].a, pa); pb2 = r32_madwide(f[2].b, kk[2][og].b, pb2);       // < 3 p^2
                     const u32 ba = r32_redc(pa, FQ_P1, FQ_P1_INVNEG), bb = r32_redc(pb2, FQ_P2, FQ_P2_INVNEG);   // < 1.75 p + 1
-                    rns2 d;
-                    if (og == 0) d = dg[0][q][e];
-                    else {
-                        int gg = g + og; if (gg >= G) gg -= G;
-                        const u32 xg = (G == 2) ? (1u << SH) : ((u32)(g ^ gg) << SH);
-                        d = rns_unpack(*(const u64 *)(Sb + q * PWB + (o ^ xg)));
-                    }
-                    if (og == 0) { oa = (u64)d.a * ba; ob = (u64)d.b * bb; }
-                    else { oa += (u64)d.a * ba; ob += (u64)d.b * bb; }                            // < G * 3.5 p^2
+                    // digit spectra from shared memory, the thread's own too: keeping them in registers across the
+                    // point-wise part costs more in spills than the 8 extra loads
+                    int gg = g + og; if (gg >= G) gg -= G;
+                    const u32 xg = (og == 0) ? 0u : (G == 2) ? (1u << SH) : ((u32)(g ^ gg) << SH);
+                    const rns2 d = rns_split(*(const u64 *)(Sb + q * PWB + (o ^ xg)));
+                    if (og == 0) { oa = r32_mulwide(d.a, ba); ob = r32_mulwide(d.b, bb); }
+                    else { oa = r32_madwide(d.a, ba, oa); ob = r32_madwide(d.b, bb, ob); }                      // < G * 3.5 p^2
                 }
                 x[q][e].a = r32_fold(r32_redc(oa, FQ_P1, FQ_P1_INVNEG), 2 * FQ_P1);
                 x[q][e].b = r32_fold(r32_redc(ob, FQ_P2, FQ_P2_INVNEG), 2 * FQ_P2);
