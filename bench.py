@@ -209,7 +209,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="adder128_p15", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=None, help="encrypted instances per GPU per step (default 296; 16 for aes128_p11)")
-    ap.add_argument("--param-set", default="A")
+    ap.add_argument("--param-set", default="A2", help="A2 = set A with two key bits per blind-rotation step (default); A = classic")
     ap.add_argument("--seed", type=int, default=20241018)
     ap.add_argument("--shard", default="instances", choices=["instances", "nodes"],
                     help="instances: batch split across GPUs, no collective (weak scaling); nodes: one circuit, each level's "

@@ -11,10 +11,10 @@ from tfhe_fbs_map_b200 import levelize, params
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(scope="module")
-def be():
+@pytest.fixture(scope="module", params=["A", "A2"])     # A2: same shape, two key bits per blind-rotation step
+def be(request):
     from tfhe_fbs_map_b200.backend import B200Backend
-    b = B200Backend("A", device=0, seed=20241018)
+    b = B200Backend(request.param, device=0, seed=20241018)
     yield b
     b.close()
 
@@ -36,7 +36,7 @@ def test_pbs_sweep_exhaustive_tables(be, p):
 
 
 def test_one_pbs_bit_exact_against_cpu_oracle(be):
-    ref = RefTFHE(params.get("A"), seed=20241018)
+    ref = RefTFHE(be.params, seed=20241018)
     p = 17
     tab = [0, 1, 1, 0, 1, 0, 0, 1, 1, 1, 0, 0, 1, 0, 1, 1, 0]
     tab2 = tab + [1 - x for x in tab]

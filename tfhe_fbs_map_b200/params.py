@@ -68,8 +68,10 @@ class ParamSet:
     def modmul_per_pbs(self) -> int:
         """64-bit modular multiplies of one blind rotation, canonical radix-2 count."""
         k1, l, N = self.k + 1, self.bsk_l, self.N
-        per_step = (k1 * l + k1) * (N // 2) * int(math.log2(N)) + k1 * k1 * l * N
-        return self.n * per_step
+        ntt = (k1 * l + k1) * (N // 2) * int(math.log2(N))
+        if self.bsk_unroll == 2:      # per key PAIR: one transform set, 3 factor x key products + 1 digit x bundle product per key word
+            return (self.n // 2) * (ntt + 4 * k1 * k1 * l * N)
+        return self.n * (ntt + k1 * k1 * l * N)
 
     def mul32_per_pbs(self) -> int:
         """32x32->64 multiplies: 4 per modmul + 2 per key-switch MAC."""
@@ -153,7 +155,7 @@ SET_A2 = _unrolled(SET_A, "A2")
 TOY_2U, TOY_3U, TOY_5U = _unrolled(TOY_2, "toy2u"), _unrolled(TOY_3, "toy3u"), _unrolled(TOY_5, "toy5u")
 
 PARAM_SETS = {ps.name: ps for ps in (SET_A, SET_A2, SET_C, SET_S, TOY_1, TOY_2, TOY_3, TOY_4, TOY_5, TOY_6, TOY_2U, TOY_3U, TOY_5U)}
-DEFAULT_SET = "A"
+DEFAULT_SET = "A2"
 
 
 def get(name: str | ParamSet) -> ParamSet:
@@ -162,7 +164,7 @@ def get(name: str | ParamSet) -> ParamSet:
     return PARAM_SETS[name]
 
 
-def estimate(p: int, norm2: float, sets=("S", "A", "C")) -> dict:
+def estimate(p: int, norm2: float, sets=("S", "A2", "C")) -> dict:
     """Replacement for ``optimizer --precision=p --sq-norm2=norm2`` (reference add_exec_estimates.py:14):
     first shipped set whose failure probability meets concrete's default target 4 sigma ~ 6.3e-5
     (reference concrete.patch:101-102); returns its shape, p_fail and the algorithmic cost in modmuls."""
