@@ -337,15 +337,16 @@ def main():
             metric="PBS/sec", value=value, unit="PBS/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
             ms_per_step=ms_res / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
             dtype="u64 (q = p1*p2, two 30-bit NTT primes; RNS u32x2 in the NTT)", data="synthetic",
-            config=dict(workload=args.workload, desc=wl["desc"], param_set=ps.name, n=ps.n, k=ps.k, N=ps.N, bsk_l=ps.bsk_l, ks_l=ps.ks_l,
+            config=dict(workload=args.workload, desc=wl["desc"], param_set=ps.name, n=ps.n, k=ps.k, N=ps.N, bsk_l=ps.bsk_l, ks_l=ps.ks_l, bsk_unroll=ps.bsk_unroll,
                         fbs_size=wl["p"], instances_per_gpu=B, pbs_per_instance=prog.n_boots, levels=prog.n_levels,
                         p_fail_per_pbs=ps.p_fail(wl["p"], env.stats()["norm2_linprod"]), sharding="instances, keys replicated, no collective",
                         l2="wire buffer %.2f GB per GPU > 126 MB L2; BSK+KSK (%.0f MB) are re-streamed every level" % (wires.numel() * 8 / 1e9, (info["bsk_bytes"] + info["ksk_bytes"]) / 1e6)),
             evals_per_s=world * B * args.steps / (ms_res * 1e-3), mismatches=mism_res,
             phase_ms_per_step=dict(lincomb=st.ms_lincomb / args.steps, keyswitch=st.ms_keyswitch / args.steps, blind_rotate=st.ms_blind_rotate / args.steps),
             roofline=dict(bound="hbm", achieved=achieved, peak=peaks.get("hbm_gbs"), unit="GB/s", frac=achieved / peaks.get("hbm_gbs"),
-                          traffic=61.95e6 / 1e9, traffic_note="GB per launch: dram__bytes_read+write of a 592-PBS launch, profiles/r1_v5_hot_kernels_summary.txt",
-                          kernel="k_blind_rotate", launch_ms=br_ms_avg, peak_source=peak_kind,
+                          traffic=(155.58e6 if ps.bsk_unroll == 2 else 61.95e6) / 1e9,
+                          traffic_note="GB per launch: dram__bytes_read+write of a 592-PBS launch (two waves), profiles/" + ("r1_v9_hot_kernels_summary.txt; the 73 MB key-unrolled BSK does not stay L2-resident between waves and is re-read from HBM once per wave" if ps.bsk_unroll == 2 else "r1_v5_hot_kernels_summary.txt"),
+                          kernel="k_blind_rotate2" if ps.bsk_unroll == 2 else "k_blind_rotate", launch_ms=br_ms_avg, peak_source=peak_kind,
                           note="kernel is integer-issue bound by design (accumulator on chip, keys L2-resident); see roofline_int"),
             roofline_int=dict(bound="int32-multiply", achieved=mul32 / 1e12, peak=int_peak / 1e12, unit="T mul32/s", frac=mul32 / int_peak,
                               mul32_per_pbs=ps.mul32_per_pbs(), modmul_per_pbs=ps.modmul_per_pbs(), peak_source="measured (fbs_measure_int_peak: mad.wide.u32 chains)"),
