@@ -114,6 +114,17 @@ template <int LOGN> int run() {
             if (k < N) sb[k] = fq_add(sb[k], pr); else sb[k - N] = fq_sub(sb[k - N], pr); }
         for (int i = 0; i < N; i++) { rns2 v = canon4(rns_unpack(prod[i])); if (rns_to_int(v) != sb[i]) bad++; }
     }
+    // the inverse pass reading the FORWARD table mirrored (blind-rotate kernels) gives the same residues
+    for (int tau = 0; tau < P::T; tau++) {
+        rns2 x1[1][8], x2[1][8];
+        for (int el = 0; el < 8; el++) { rns2 v = canon4(rns_unpack(e2[(tau * 8 + el) % N])); v.a += FQ_P1 * (el & 1); x1[0][el] = x2[0][el] = v; }
+        ntt_inv_pass_n<LOGN, 1, 1, false>(x1, tau, t.psi_inv_rev.data());
+        ntt_inv_pass_n<LOGN, 1, 1, true>(x2, tau, t.psi_rev.data());
+        for (int el = 0; el < 8; el++) if (x1[0][el].a % FQ_P1 != x2[0][el].a % FQ_P1 || x1[0][el].b % FQ_P2 != x2[0][el].b % FQ_P2 || x2[0][el].a >= 2 * FQ_P1 || x2[0][el].b >= 2 * FQ_P2) bad++;
+    }
+    // GF(2)-linear addressing used by the kernels
+    for (int tau = 0; tau < P::T; tau++) for (int el = 0; el < 8; el++) for (int p = 0; p < P::NPASS; p++) for (int lb : {P::fwd_lb(p), P::inv_lb(p)})
+        if (8u * (u32)P::swz(P::idx(tau, el, lb)) != (P::tau_boff(tau, lb) ^ P::elem_boff(el, lb))) bad++;
     printf("LOGN=%d bad=%d\n", LOGN, bad);
     return bad;
 }
@@ -158,6 +169,16 @@ int main() {
         // 32-bit Shoup: any y, result in [0,2p) and congruent
         u32 y = (u32)fbs_rnd64(5, 6, i), w = (u32)(a % FQ_P2), sh = r32_mul_shoup(y, w, shoup32_host(w, FQ_P2), FQ_P2);
         if (sh >= 2 * FQ_P2 || sh % FQ_P2 != (u32)((u64)w * (y % FQ_P2) % FQ_P2)) bad++;
+        // one-level digit (fbs_digit1_t, the blind-rotation kernels' fast path) == rounding + balanced digit of the spec,
+        // r32_csub == conditional subtraction, borrow-free REDC == acc * 2^-32 mod p within (0, hi + p]
+        for (int beta : {8, 12, 22, 23, 24}) {
+            const u32 t = rns_crt_hi(r);
+            int dref[1]; fbs_balanced_digits<1>(fbs_round_top_t(t, r.a, beta), beta, dref);
+            if (fbs_digit1_t(t, r.a, beta, 1ULL << (62 - beta)) != dref[0]) bad++;
+        }
+        { const u32 xx = (u32)fbs_rnd64(13, 14, i); if (r32_csub(xx, FQ_P1) != (xx >= FQ_P1 ? xx - FQ_P1 : xx)) bad++; }
+        { const u64 acc = fbs_rnd64(15, 16, i) >> 1; const u32 rr = r32_redc(acc, FQ_P2, 0xAFFF3FFFu);
+          if (rr % FQ_P2 != (u32)((u128)(acc % FQ_P2) * pow_mod_host((1ULL << 32) % FQ_P2, FQ_P2 - 2, FQ_P2) % FQ_P2) || rr > (u32)(acc >> 32) + FQ_P2) bad++; }
         // rounding: both definitions stay within one unit of the exact quotient
         for (int bits : {12, 15, 23, 24, 30}) {
             u64 yq = fbs_round_top(a, bits);

@@ -742,11 +742,12 @@ __global__ void __launch_bounds__((PB / TP) * (K + 1) * (1 << LOGN) / 8, 1) k_bl
 // One decomposition and one forward / inverse transform pair serve two key bits; the monomial factors are applied to the
 // KEY in the NTT domain, where X^e is the point-wise multiplication by psi^(e * (2 brev(i) + 1)) (table psi_pow), so the
 // accumulator is decomposed as it is: no rotated reads, ACC lives in registers for the whole blind rotation and shared
-// memory only holds the transpose scratch (32 KB per bootstrap at set A).  Per coefficient and prime the point-wise part is
+// memory only holds the transpose scratch (32 KB per bootstrap at set A2).  Per coefficient and prime the point-wise part is
 //   bundle_u = REDC( sum_c f_c * key_c[u][g] ),  out_g = REDC( sum_u D_u * bundle_u )       (key in Montgomery form twice)
 // i.e. 8 products + 3 reductions against 2 x (2 + 1) for two classic steps, against a whole saved step of transforms.
-// The key is read straight from L2 (coalesced 8-byte loads, layout [ggsw][u][v][e][tau]; it is shared by the bootstraps a
-// thread carries and by all CTAs) -- 1.5 x the classic key per blind rotation, but half as many steps.
+// The key (1.5 x the classic one, half as many steps) is streamed by TMA in per-element slices through a shared-memory ring
+// (BR2Cfg, full/empty mbarriers); a key word is read from shared memory once per thread and used for every bootstrap the
+// thread carries.  The table psi_pow (psi^x - 1) sits in shared memory too, index nibble XOR-folded against bank conflicts.
 // ------------------------------------------------------------------------------------------------------
 template <int LOGN, int K, int PB, int TP>
 struct BR2Cfg {
