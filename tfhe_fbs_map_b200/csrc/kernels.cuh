@@ -760,7 +760,10 @@ struct BR2Cfg {
     static constexpr size_t slice_w = 3 * (size_t)G * G * T;
     static constexpr size_t fixed_b = 8 * (PB * s_w + psi_w) + PB * 2048 + 256;          // ms rows budgeted for n < 1024
     static constexpr int R_fit = (int)((227 * 1024 - fixed_b) / (8 * slice_w));
-    static constexpr int R = R_fit > 8 ? 8 : R_fit;                                         // ring slots (prefetch distance)
+#ifndef FBS_RING_MAX
+#define FBS_RING_MAX 3      /* measured at set A2: 2 slots 45.8 k, 3 slots 46.3 k, 4 45.8 k, 5 45.1 k PBS/s -- deeper rings only take L1 from the twiddles */
+#endif
+    static constexpr int R = R_fit > FBS_RING_MAX ? FBS_RING_MAX : R_fit;                   // ring slots (prefetch distance)
     static_assert(R >= 2, "key ring does not fit shared memory");
     __host__ __device__ static constexpr size_t ms_stride(int n) { return (((size_t)(n + 1) * 2 + 15) / 16) * 16; }
     __host__ __device__ static constexpr size_t smem_bytes(int n) { return 8 * (PB * s_w + psi_w + R * slice_w + 2 * R) + PB * ms_stride(n); }
