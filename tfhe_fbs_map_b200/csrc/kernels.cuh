@@ -755,10 +755,15 @@ struct BR2Cfg {
     static constexpr int N = 1 << LOGN, G = K + 1, T = N / 8, PT = G * T, THREADS = (PB / TP) * PT;
     static constexpr size_t s_w = (size_t)G * N;                  // transpose scratch = digit spectra = final accumulator
     static constexpr size_t psi_w = 2 * (size_t)N;                // psi^x table
+#ifndef FBS_TW_SMEM
+#define FBS_TW_SMEM 1
+#endif
+    static constexpr bool TWS = FBS_TW_SMEM != 0;                 // NTT twiddle table in shared memory (16 B per entry)
+    static constexpr size_t tw_w = TWS ? 2 * (size_t)N : 0;
     // Key slice = every key word the CTA needs for ONE of the 8 elements a thread holds: [c < 3][u < G][v < G][tau < T]; a step
     // consumes 8 slices in element order.  HBM layout [key pair][element][c][u][v][tau]: one contiguous bulk copy per slice.
     static constexpr size_t slice_w = 3 * (size_t)G * G * T;
-    static constexpr size_t fixed_b = 8 * (PB * s_w + psi_w) + PB * 2048 + 256;          // ms rows budgeted for n < 1024
+    static constexpr size_t fixed_b = 8 * (PB * s_w + psi_w + tw_w) + PB * 2048 + 256;   // ms rows budgeted for n < 1024
     static constexpr int R_fit = (int)((227 * 1024 - fixed_b) / (8 * slice_w));
 #ifndef FBS_RING_MAX
 #define FBS_RING_MAX 3      /* measured at set A2: 2 slots 45.8 k, 3 slots 46.3 k, 4 45.8 k, 5 45.1 k PBS/s -- deeper rings only take L1 from the twiddles */
@@ -766,7 +771,7 @@ struct BR2Cfg {
     static constexpr int R = R_fit > FBS_RING_MAX ? FBS_RING_MAX : R_fit;                   // ring slots (prefetch distance)
     static_assert(R >= 2, "key ring does not fit shared memory");
     __host__ __device__ static constexpr size_t ms_stride(int n) { return (((size_t)(n + 1) * 2 + 15) / 16) * 16; }
-    __host__ __device__ static constexpr size_t smem_bytes(int n) { return 8 * (PB * s_w + psi_w + R * slice_w + 2 * R) + PB * ms_stride(n); }
+    __host__ __device__ static constexpr size_t smem_bytes(int n) { return 8 * (PB * s_w + psi_w + tw_w + R * slice_w + 2 * R) + PB * ms_stride(n); }
 };
 template <int LOGN, int K, int PB, int TP>
 __global__ void __launch_bounds__((PB / TP) * (K + 1) * (1 << LOGN) / 8, 1) k_blind_rotate2(BRArgs a)
@@ -779,7 +784,8 @@ __global__ void __launch_bounds__((PB / TP) * (K + 1) * (1 << LOGN) / 8, 1) k_bl
     constexpr size_t PW = C::s_w, PWB = PW * 8;
     u64 *S = (u64 *)smem_raw + (size_t)pb0 * PW;                 // bootstrap q of this thread: S + q*PW
     u64 *PSI = (u64 *)smem_raw + (size_t)PB * PW;
-    u64 *RING = PSI + C::psi_w;
+    u64 *TW = PSI + C::psi_w;                                    // twiddles (when C::TWS)
+    u64 *RING = TW + C::tw_w;
     u64 *full = RING + (size_t)R * C::slice_w, *empty = full + R;  // mbarriers: slice landed / slice consumed by every warp
     const size_t ms_stride = C::ms_stride(a.n);
     u16 *s_ms = (u16 *)((unsigned char *)(empty + R) + (size_t)pb0 * ms_stride);
@@ -803,6 +809,8 @@ __global__ void __launch_bounds__((PB / TP) * (K + 1) * (1 << LOGN) / 8, 1) k_bl
     // multiples of 16 E (bit-reversed evaluation points), which would all fall into one bank pair otherwise
     auto psw = [](u32 x) { return x ^ (((x >> 4) ^ (x >> 8)) & 15u); };
     for (int i = tid; i < 2 * N; i += C::THREADS) PSI[psw((u32)i)] = a.psi_pow[i];
+    if (C::TWS) for (int i = tid; i < 2 * N; i += C::THREADS) TW[i] = ((const u64 *)a.psi_rev)[i];
+    const fq_tw *twp = C::TWS ? (const fq_tw *)TW : a.psi_rev;
     if (tid == 0) {
         for (int r = 0; r < R; r++) { mbar_init(full + r, 1); mbar_init(empty + r, C::THREADS / 32); }
     }
@@ -868,7 +876,7 @@ __global__ void __launch_bounds__((PB / TP) * (K + 1) * (1 << LOGN) / 8, 1) k_bl
                 dg[0][q][e].a = d + FQ_P1;
                 dg[0][q][e].b = d + FQ_P2;
             }
-        ntt_fwd1_from<LOGN, 0, TP>(dg[0], tau, Sb, PWB, bo, a.psi_rev, gsync, true, a.zero);
+        ntt_fwd1_from<LOGN, 0, TP, decltype(gsync), C::TWS>(dg[0], tau, Sb, PWB, bo, twp, gsync, true, a.zero);
 #pragma unroll
         for (int e = 0; e < 8; e++) {
             const u32 o = bo[0] ^ P::elem_boff(e, 0);
@@ -961,7 +969,7 @@ __global__ void __launch_bounds__((PB / TP) * (K + 1) * (1 << LOGN) / 8, 1) k_bl
             if (++slot == R) { slot = 0; par ^= 1; }
         }
         auto after_pass0 = [&] { __syncthreads(); };             // nobody reads this step's digit spectra any more
-        ntt_inv1_from<LOGN, 0, TP>(x, tau, Sb, PWB, bo, a.psi_rev, after_pass0, gsync, a.zero);
+        ntt_inv1_from<LOGN, 0, TP, decltype(after_pass0), decltype(gsync), C::TWS>(x, tau, Sb, PWB, bo, twp, after_pass0, gsync, a.zero);
 #pragma unroll
         for (int e = 0; e < 8; e++)
 #pragma unroll

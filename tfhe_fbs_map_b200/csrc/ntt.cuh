@@ -49,11 +49,18 @@ static_assert(NttPlan<10>::swz(NttPlan<10>::idx(97, 3, 4)) * 8 == (NttPlan<10>::
 
 // ---- one forward pass on registers -------------------------------------------------------------------
 struct alignas(16) fq_tw { u32 w1, ws1, w2, ws2; };      // twiddle + Shoup companion for both primes: one 128-bit load
+template <bool TWS = false>                              // TWS: the table lives in shared memory
 FQ_HD fq_tw fq_tw_load(const fq_tw *p)
 {
 #if defined(__CUDA_ARCH__)
-    const uint4 v = __ldg(reinterpret_cast<const uint4 *>(p));
-    return fq_tw{v.x, v.y, v.z, v.w};
+    if constexpr (TWS) {
+        uint4 v;
+        asm("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"((u32)__cvta_generic_to_shared(p)));
+        return fq_tw{v.x, v.y, v.z, v.w};
+    } else {
+        const uint4 v = __ldg(reinterpret_cast<const uint4 *>(p));
+        return fq_tw{v.x, v.y, v.z, v.w};
+    }
 #else
     return *p;
 #endif
@@ -64,7 +71,7 @@ FQ_HD fq_tw fq_tw_load(const fq_tw *p)
 // time (a kernel argument) makes the add 3-input, which only IADD3 can do, and pins it to the ALU pipe.
 struct NttZero { u32 z; };
 // NB = bootstraps per thread: the NB butterflies at one position share the twiddle load and the index arithmetic
-template <int LOGN, int PASS, int NB>
+template <int LOGN, int PASS, int NB, bool TWS = false>
 FQ_HD void ntt_fwd_pass_n(rns2 (&x)[NB][8], int tau, const fq_tw *__restrict__ psi_rev, u32 z = 0)
 {
     using P = NttPlan<LOGN>;
@@ -78,7 +85,7 @@ FQ_HD void ntt_fwd_pass_n(rns2 (&x)[NB][8], int tau, const fq_tw *__restrict__ p
         for (int e0 = 0; e0 < 8; e0++) {
             if (e0 & (1 << q)) continue;
             const int e1 = e0 | (1 << q);
-            const fq_tw w = fq_tw_load(psi_rev + m + ((th << (2 - q)) | (e0 >> (q + 1))));
+            const fq_tw w = fq_tw_load<TWS>(psi_rev + m + ((th << (2 - q)) | (e0 >> (q + 1))));
 #pragma unroll
             for (int b = 0; b < NB; b++) {
                 const u32 ua = r32_fold(x[b][e0].a, 2 * FQ_P1), va = r32_mul_shoup(x[b][e1].a, w.w1, w.ws1, FQ_P1);
@@ -97,7 +104,7 @@ FQ_HD void ntt_fwd_pass(rns2 (&x)[8], int tau, const fq_tw *__restrict__ psi_rev
 // ---- one inverse pass on registers ---------------------------------------------------------------------
 // MIRROR: psi^-bitrev(m+i) = -psi^bitrev(2m-1-i), so the inverse can read the FORWARD table mirrored within each block
 // [m, 2m) and swap the operands of its subtraction; the blind-rotate kernel does, which halves the twiddle footprint in L1.
-template <int LOGN, int PASS, int NB, bool MIRROR = false>
+template <int LOGN, int PASS, int NB, bool MIRROR = false, bool TWS = false>
 FQ_HD void ntt_inv_pass_n(rns2 (&x)[NB][8], int tau, const fq_tw *__restrict__ psi_inv_rev, u32 z = 0)
 {
     using P = NttPlan<LOGN>;
@@ -112,7 +119,7 @@ FQ_HD void ntt_inv_pass_n(rns2 (&x)[NB][8], int tau, const fq_tw *__restrict__ p
             if (e0 & (1 << q)) continue;
             const int e1 = e0 | (1 << q);
             const int ti = (th << (2 - q)) | (e0 >> (q + 1));
-            const fq_tw w = fq_tw_load(psi_inv_rev + (MIRROR ? 2 * m - 1 - ti : m + ti));
+            const fq_tw w = fq_tw_load<TWS>(psi_inv_rev + (MIRROR ? 2 * m - 1 - ti : m + ti));
 #pragma unroll
             for (int b = 0; b < NB; b++) {
                 const u32 ua = x[b][e0].a, va = x[b][e1].a, ub = x[b][e0].b, vb = x[b][e1].b;
@@ -164,11 +171,11 @@ __device__ __forceinline__ void ntt_forward(rns2 (&x)[8], int tau, u64 *bufA, u6
 // first write needs the caller's guarantee (`buf_free`) that the previous users of the scratch are done.
 // Addressing: `bo[lb]` = NttPlan::tau_boff(tau, lb) (+ any higher-order offset that selects the polynomial) for every
 // layout lb, `buf` a byte pointer, `stride` the byte distance between the scratch polynomials of the NB bootstraps.
-template <int LOGN, int PASS, int NB, class Sync>
+template <int LOGN, int PASS, int NB, class Sync, bool TWS = false>
 __device__ __forceinline__ void ntt_fwd1_from(rns2 (&x)[NB][8], int tau, unsigned char *buf, size_t stride, const u32 (&bo)[LOGN], const fq_tw *psi_rev, Sync sync, bool buf_free, u32 z = 0)
 {
     using P = NttPlan<LOGN>;
-    ntt_fwd_pass_n<LOGN, PASS, NB>(x, tau, psi_rev, z);
+    ntt_fwd_pass_n<LOGN, PASS, NB, TWS>(x, tau, psi_rev, z);
     if constexpr (PASS + 1 < P::NPASS) {
         constexpr int lb0 = P::fwd_lb(PASS), lb1 = P::fwd_lb(PASS + 1);
         if (!buf_free) sync();                          // earlier readers of buf (other threads) are done
@@ -185,16 +192,16 @@ __device__ __forceinline__ void ntt_fwd1_from(rns2 (&x)[NB][8], int tau, unsigne
 #pragma unroll
             for (int b = 0; b < NB; b++) x[b][e] = rns_unpack(*(const u64 *)(buf + b * stride + o));
         }
-        ntt_fwd1_from<LOGN, PASS + 1, NB>(x, tau, buf, stride, bo, psi_rev, sync, true, z);
+        ntt_fwd1_from<LOGN, PASS + 1, NB, Sync, TWS>(x, tau, buf, stride, bo, psi_rev, sync, true, z);
     }
 }
 // inverse: `after_pass0` runs between pass 0 and the first write to buf
 // `psi_rev` is the FORWARD table (read mirrored, see ntt_inv_pass_n)
-template <int LOGN, int PASS, int NB, class Sync0, class Sync>
+template <int LOGN, int PASS, int NB, class Sync0, class Sync, bool TWS = false>
 __device__ __forceinline__ void ntt_inv1_from(rns2 (&x)[NB][8], int tau, unsigned char *buf, size_t stride, const u32 (&bo)[LOGN], const fq_tw *psi_rev, Sync0 after_pass0, Sync sync, u32 z = 0)
 {
     using P = NttPlan<LOGN>;
-    ntt_inv_pass_n<LOGN, PASS, NB, true>(x, tau, psi_rev, z);
+    ntt_inv_pass_n<LOGN, PASS, NB, true, TWS>(x, tau, psi_rev, z);
     if constexpr (PASS == 0) after_pass0();             // later passes write the words they read themselves: no barrier
     if constexpr (PASS + 1 < P::NPASS) {
         constexpr int lb0 = P::inv_lb(PASS), lb1 = P::inv_lb(PASS + 1);
@@ -211,7 +218,7 @@ __device__ __forceinline__ void ntt_inv1_from(rns2 (&x)[NB][8], int tau, unsigne
 #pragma unroll
             for (int b = 0; b < NB; b++) x[b][e] = rns_unpack(*(const u64 *)(buf + b * stride + o));
         }
-        ntt_inv1_from<LOGN, PASS + 1, NB>(x, tau, buf, stride, bo, psi_rev, sync, sync, z);
+        ntt_inv1_from<LOGN, PASS + 1, NB, Sync, Sync, TWS>(x, tau, buf, stride, bo, psi_rev, sync, sync, z);
     }
 }
 
