@@ -381,7 +381,12 @@ extern "C" int fbs_encrypt_inputs(fbs_ctx *c, fbs_prog *g, const uint8_t *in_dev
     return FBS_OK;
 }
 
-template <int LK> static void launch_lc(const LCArgs &a, long long tiles, cudaStream_t st) { k_lincomb_decomp<LK><<<(unsigned)tiles, 256, 0, st>>>(a); }
+template <int LK> static void launch_lc(const LCArgs &a, long long tiles, cudaStream_t st)
+{
+    // column chunks so that even a level with few ciphertexts puts about two CTAs on every SM (148 SMs on B200)
+    int ny = (int)std::min<long long>(std::max<long long>(1, (2 * 148 + tiles - 1) / tiles), (a.D + 1 + 255) / 256);
+    k_lincomb_decomp<LK><<<dim3((unsigned)tiles, (unsigned)ny), 256, 0, st>>>(a);
+}
 
 static int run_level_impl(fbs_ctx *c, fbs_prog *g, int level, int nb, int ne, int64_t B, u64 *wires, cudaStream_t st,
                           fbs_run_stats *stats, u64 *tap_ks, u64 *tap_acc, bool timed, cudaEvent_t *evq = nullptr)

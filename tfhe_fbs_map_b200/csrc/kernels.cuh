@@ -313,7 +313,9 @@ __global__ void __launch_bounds__(256) k_lincomb_decomp(LCArgs a)
     const size_t CT = (size_t)a.D + 1;
     const size_t R = (size_t)a.D * LK;
     const int halfB = 1 << (a.ks_beta - 1);
-    for (int i = threadIdx.x; i <= a.D; i += 256) {
+    // gridDim.y column chunks: a level of a narrow circuit has only a few tiles of 16 ciphertexts, too few to fill the SMs
+    const int chunk = ((a.D + 1 + (int)gridDim.y - 1) / (int)gridDim.y + 255) / 256 * 256, i_end = min(a.D + 1, ((int)blockIdx.y + 1) * chunk);
+    for (int i = blockIdx.y * chunk + threadIdx.x; i < i_end; i += 256) {
 #pragma unroll
         for (int mm = 0; mm < 16; mm++) {
             const int lc = s_lc[mm];
