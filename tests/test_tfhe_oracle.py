@@ -91,3 +91,14 @@ def test_encrypted_program_equals_cleartext(circuit, p):
     want = unpack_outputs(e, batch=B)
     for nm in prog.output_names:
         assert np.array_equal(got[prog.out_index[nm]], want[str(nm)]), nm
+
+
+def test_unrolled_parameter_model():
+    """Key-unrolled twins: three GGSW per key pair, same shape otherwise; the failure probability moves by a hair only
+    (key-switch and modulus-switch noise dominate), the canonical multiply count drops."""
+    a, a2 = params.get("A"), params.get("A2")
+    assert a2.n_ggsw == 3 * a.n // 2 and a2.bsk_bytes * 2 == 3 * a.bsk_bytes
+    assert a2.modmul_per_pbs() < 0.75 * a.modmul_per_pbs()
+    for p, norm2 in ((15, 70), (17, 202), (11, 155)):
+        assert a.p_fail(p, norm2) <= a2.p_fail(p, norm2) < 1.5 * a.p_fail(p, norm2)
+    assert params.estimate(15, 70)["param_set"] == "A2"
