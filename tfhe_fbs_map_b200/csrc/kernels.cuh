@@ -346,7 +346,7 @@ __global__ void __launch_bounds__(256) k_lincomb_decomp(LCArgs a)
 // exact u8 x u8 -> s32 GEMM (7 * 255 * kN*l_ks < 2^31), run as mma.sync.m16n8k32; the 8 byte sums of a column are
 // recombined as sum_b C_b * 2^(8b) mod q in the epilogue and the digit offset B/2 is removed with (B/2)*colsum[c].
 // This is the one GEMM-shaped step of the path: 8x more MACs than the integer-pipe version
-// (2 IMAD.WIDE per MAC), but on a unit that is otherwise idle -- measured 436 -> see profiles/ ms per adder128 step.
+// (2 IMAD.WIDE per MAC), but on a unit that is otherwise idle -- measured 18.3 -> 1.3 ms per 4736 ciphertexts (profiles/README.md).
 // KbT[(c*8+b)][r] is the byte-transposed key (k-contiguous "col" operand), CTA tile 64 ciphertexts x 8 columns x 128 rows,
 // cp.async double buffering, 144-byte padded rows (bank-conflict-free 32-bit fragment loads).
 // ------------------------------------------------------------------------------------------------------

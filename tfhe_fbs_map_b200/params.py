@@ -46,11 +46,11 @@ class ParamSet:
 
     @property
     def lwe_noise_scale(self) -> int:
-        return max(0, int(round(self.lwe_sigma * GOLDILOCKS_P)))
+        return max(0, int(round(self.lwe_sigma * FBS_Q)))
 
     @property
     def glwe_noise_scale(self) -> int:
-        return max(0, int(round(self.glwe_sigma * GOLDILOCKS_P)))
+        return max(0, int(round(self.glwe_sigma * FBS_Q)))
 
     @property
     def n_ggsw(self) -> int:
