@@ -100,8 +100,20 @@ def cpu_baseline(ps, sample_fn, p, seed, threads, instances=None):
     from tfhe_fbs_map_b200 import levelize
     env = load_env(sample_fn)
     prog = levelize(env, p)
+    if getattr(ps, "bsk_unroll", 1) == 2:
+        # the CPU runs the classic one-bit-per-step blind rotation of the same shape: the oracle's literal key-unrolled
+        # restatement does three external products per key pair and would make the CPU look slower than it is
+        from dataclasses import asdict
+        from tfhe_fbs_map_b200.params import ParamSet
+        d = asdict(ps); d.update(bsk_unroll=1, name=ps.name + " shape, classic blind rotation")
+        ps = ParamSet(**d)
     L = lib()
-    cores = threads or L.ref_max_threads()
+    if not threads:
+        try:
+            threads = len(os.sched_getaffinity(0))
+        except AttributeError:
+            threads = L.ref_max_threads()
+    cores = threads
     B = instances or cores
     ref = RefTFHE(ps, seed=seed)
     rng = np.random.default_rng(1)
@@ -126,7 +138,11 @@ def run_reference(args, wl, ps, rank, world):
     if rank != 0:
         return
     from oracle.tfhe_ref import lib
-    cores = lib().ref_max_threads()
+    # every host thread this process may use: torchrun exports OMP_NUM_THREADS=1, which ref_max_threads() would obey
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except AttributeError:
+        cores = os.cpu_count() or lib().ref_max_threads()
     vals = []
     for step in range(args.warmup + args.steps):
         cb = cpu_baseline(ps, wl["cpu_sample"], wl["p"], args.seed, cores, instances=max(1, cores // 2) if step < args.warmup else cores)
