@@ -26,6 +26,9 @@ template <int V> __global__ void __launch_bounds__(1024) k(u32 *x, const uint4 *
             if (V == 0 || V == 2 || V == 4) v = tw * y[j] - __umulhi(tws, y[j]) * P1;
             if (V == 1) { u64 T = (u64)y[j] * tw; u32 m = (u32)T * pinv; u64 R = (u64)m * P1 + T; v = (u32)(R >> 32); z = (u32)R; }
             if (V == 3) { u64 T = (u64)y[j] * tws; v = tw * y[j] - (u32)(T >> 32) * P1; z = (u32)T; }
+            if (V == 6) { u64 T = (u64)y[j] * tws; u32 lo = (u32)T; asm volatile("" :: "r"(lo)); v = tw * y[j] - (u32)(T >> 32) * P1; }
+            if (V == 7) { v = tw * y[j] - (u32)__mulhi((int)tws, (int)y[j]) * P1; }
+            if (V == 8) { u32 q; asm("mul.hi.u32 %0, %1, %2;" : "=r"(q) : "r"(y[j]), "r"(tws)); v = tw * y[j] - q * P1; }
             if (V == 4) { y[j] = v; continue; }
             const u32 u = (V == 2) ? y[i] : fold(y[i]);
             y[i] = u + v + z; y[j] = u - v + 2 * P1;
@@ -50,6 +53,6 @@ template <int V> void run(const char *name, int warps)
 }
 int main()
 {
-    for (int w : {4, 8}) { run<0>("Shoup", w); run<1>("Montgomery", w); run<2>("Shoup, no fold", w); run<3>("Shoup, quotient via WIDE", w); run<4>("multiplies only", w); run<5>("adds only", w); }
+    for (int w : {4}) { run<0>("Shoup", w); run<1>("Montgomery", w); run<2>("Shoup, no fold", w); run<3>("Shoup, quotient via WIDE", w); run<4>("multiplies only", w); run<5>("adds only", w); run<6>("quotient WIDE, lo kept alive", w); run<7>("signed mulhi", w); run<8>("mulhi operands swapped", w); }
     return 0;
 }
