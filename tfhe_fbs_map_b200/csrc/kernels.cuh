@@ -851,6 +851,12 @@ __global__ void __launch_bounds__((PB / TP) * (K + 1) * (1 << LOGN) / 8, 1) k_bl
     const int bar_g = 1 + pb0 * G + g, bar_p = 1 + PB * G + pb0;
     auto gsync = [bar_g] { bar_sync_named(bar_g, T); };
     auto psync = [bar_p] { if (TP == 1) bar_sync_named(bar_p, C::PT); else __syncthreads(); };
+    // Digit spectra are exchanged between the G threads that hold the SAME spectrum positions (same tau, one per group):
+    // a named barrier over those G warps replaces a CTA-wide one, so the groups only couple warp by warp.
+    constexpr int BAR_X0 = 1 + PB * G + PB;                       // after the group (bar_g) and bootstrap (bar_p) barrier ids
+    static_assert(BAR_X0 + (PB / TP) * (T / 32) <= 16, "named barriers");
+    const int bar_x = BAR_X0 + pb0 * (T / 32) + (tau >> 5);
+    auto xsync = [bar_x] { bar_sync_named(bar_x, G * 32); };
     const int beta = a.beta;
     const u64 rc = 1ULL << (62 - beta);
     constexpr int SH = LOGN + 3;
@@ -910,7 +916,7 @@ __global__ void __launch_bounds__((PB / TP) * (K + 1) * (1 << LOGN) / 8, 1) k_bl
                 lo8[q][c] = 8u * (lo ^ (((lo >> 4) ^ (lo >> 8)) & 15u));       // fold of the fixed bits (bits >= LOGN-2 excluded)
             }
         }
-        psync();
+        xsync();                                                 // the partner warps' spectra are in shared memory
         // ---- point-wise part, one key slice per element
         rns2 x[TP][8];
 #pragma unroll
@@ -970,7 +976,7 @@ __global__ void __launch_bounds__((PB / TP) * (K + 1) * (1 << LOGN) / 8, 1) k_bl
             }
             if (++slot == R) { slot = 0; par ^= 1; }
         }
-        auto after_pass0 = [&] { __syncthreads(); };             // nobody reads this step's digit spectra any more
+        auto after_pass0 = [&] { xsync(); };                     // the partner warps have read this step's digit spectra
         ntt_inv1_from<LOGN, 0, TP, decltype(after_pass0), decltype(gsync), C::TWS>(x, tau, Sb, PWB, bo, twp, after_pass0, gsync, a.zero);
 #pragma unroll
         for (int e = 0; e < 8; e++)
