@@ -41,6 +41,14 @@ struct NttPlan {
     }
     // swz and idx are GF(2)-linear in (tau, e): swz(idx(tau, e, lb)) = swz(idx(tau, 0, lb)) ^ swz(idx(0, e, lb)).  The kernels keep
     // the thread part as a BYTE offset in a register (one per layout) and XOR the compile-time element part into it.
+    // thread that holds logical index i in layout lb, and whether a transpose lb0 -> lb1 only moves words between threads of
+    // the same warp (then __syncwarp() orders it, no block-level barrier needed)
+    FQ_HDM static constexpr int owner(int i, int lb) { return ((i >> (lb + 3)) << lb) | (i & ((1 << lb) - 1)); }
+    FQ_HDM static constexpr bool intra_warp(int lb0, int lb1)
+    {
+        for (int i = 0; i < N; i++) if ((owner(i, lb0) >> 5) != (owner(i, lb1) >> 5)) return false;
+        return true;
+    }
     FQ_HDM static constexpr u32 tau_boff(int tau, int lb) { return 8u * (u32)swz(idx(tau, 0, lb)); }
     FQ_HDM static constexpr u32 elem_boff(int e, int lb) { return 8u * (u32)swz(idx(0, e, lb)); }
 };
@@ -168,7 +176,8 @@ __device__ __forceinline__ void ntt_forward(rns2 (&x)[8], int tau, u64 *bufA, u6
 // NB bootstraps: their scratch polynomials are `stride` words apart and are transposed under the same barriers.
 // ONE barrier per transpose suffices: a word's address depends only on its logical index, so the words a thread writes
 // for transpose t+1 are exactly the words it read itself in transpose t (nobody else reads them in between).  Only the
-// first write needs the caller's guarantee (`buf_free`) that the previous users of the scratch are done.
+// first write needs the caller's guarantee (`buf_free`) that the previous users of the scratch are done.  Transposes that
+// stay inside a warp (NttPlan::intra_warp: 2 of the 3 forward and 1 of the 3 inverse ones at N = 2048) only need __syncwarp().
 // Addressing: `bo[lb]` = NttPlan::tau_boff(tau, lb) (+ any higher-order offset that selects the polynomial) for every
 // layout lb, `buf` a byte pointer, `stride` the byte distance between the scratch polynomials of the NB bootstraps.
 template <int LOGN, int PASS, int NB, class Sync, bool TWS = false>
@@ -185,7 +194,7 @@ __device__ __forceinline__ void ntt_fwd1_from(rns2 (&x)[NB][8], int tau, unsigne
 #pragma unroll
             for (int b = 0; b < NB; b++) *(u64 *)(buf + b * stride + o) = rns_pack(x[b][e]);
         }
-        sync();
+        if constexpr (P::intra_warp(lb0, lb1)) __syncwarp(); else sync();
 #pragma unroll
         for (int e = 0; e < 8; e++) {
             const u32 o = bo[lb1] ^ P::elem_boff(e, lb1);
@@ -211,7 +220,7 @@ __device__ __forceinline__ void ntt_inv1_from(rns2 (&x)[NB][8], int tau, unsigne
 #pragma unroll
             for (int b = 0; b < NB; b++) *(u64 *)(buf + b * stride + o) = rns_pack(x[b][e]);
         }
-        sync();
+        if constexpr (P::intra_warp(lb0, lb1)) __syncwarp(); else sync();
 #pragma unroll
         for (int e = 0; e < 8; e++) {
             const u32 o = bo[lb1] ^ P::elem_boff(e, lb1);
