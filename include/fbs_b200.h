@@ -36,7 +36,7 @@ typedef struct fbs_params {
     int32_t bsk_beta;   /* log2 blind-rotate base                      */
     int32_t ks_l;       /* key-switch levels                           */
     int32_t ks_beta;    /* log2 key-switch base (<= 8)                 */
-    int32_t bsk_unroll; /* 0/1: one key bit per blind-rotation step; 2: two (three GGSW per key pair, n even, bsk_l = 1) */
+    int32_t bsk_unroll; /* 0/1: one key bit per blind-rotation step; 2: two (three GGSW per key pair, bsk_l = 1) */
     uint64_t lwe_noise; /* round(sigma_lwe  * Q)                       */
     uint64_t glwe_noise;/* round(sigma_glwe * Q)                       */
 } fbs_params;

@@ -220,11 +220,11 @@ void ref_ctx_destroy(ref_ctx *c)
  *   (X^(a1+a2) - 1) s1 s2 + (X^a1 - 1) s1 (1 - s2) + (X^a2 - 1) (1 - s1) s2,
  * so pair t of the key gets three GGSW ciphertexts, of the bits m_0 = s1 s2, m_1 = s1 (1-s2), m_2 = (1-s1) s2 (GGSW index 3t + c).
  * Classic: GGSW i encrypts s_i. */
-static int n_ggsw(const ref_params *P) { return P->bsk_unroll == 2 ? 3 * (P->n / 2) : P->n; }
+static int n_ggsw(const ref_params *P) { return P->bsk_unroll == 2 ? 3 * ((P->n + 1) / 2) : P->n; }   /* odd n: last pair padded with a zero key bit */
 static int ggsw_bit(const ref_ctx *c, int g)
 {
     if (c->P.bsk_unroll != 2) return c->s_lwe[g];
-    int t = g / 3, cc = g % 3, s1 = c->s_lwe[2 * t], s2 = c->s_lwe[2 * t + 1];
+    int t = g / 3, cc = g % 3, s1 = c->s_lwe[2 * t], s2 = (2 * t + 1 < c->P.n) ? c->s_lwe[2 * t + 1] : 0;
     return cc == 0 ? (s1 & s2) : cc == 1 ? (s1 & !s2) : (!s1 & s2);
 }
 void ref_keygen(ref_ctx *c)
@@ -401,8 +401,8 @@ void ref_blind_rotate(const ref_ctx *c, const uint16_t *ms, const u64 *tv, u64 *
     if (P->bsk_unroll == 2) {
         /* ACC <- ACC + sum_c (X^{e_c} - 1) * (Dec(ACC) [x] GGSW_{3t+c}),  e = (a1 + a2, a1, a2): one decomposition per key pair */
         u64 *delta = malloc((size_t)(k + 1) * N * 8);
-        for (int t = 0; t < n / 2; t++) {
-            const int a1 = ms[2 * t], a2 = ms[2 * t + 1], e[3] = {(a1 + a2) % (2 * N), a1, a2};
+        for (int t = 0; t < (n + 1) / 2; t++) {
+            const int a1 = ms[2 * t], a2 = (2 * t + 1 < n) ? ms[2 * t + 1] : 0, e[3] = {(a1 + a2) % (2 * N), a1, a2};
             decompose_ntt(c, acc, -1, dig);
             memset(delta, 0, (size_t)(k + 1) * N * 8);
             for (int cc = 0; cc < 3; cc++) {

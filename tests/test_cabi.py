@@ -54,8 +54,8 @@ def test_parameter_validation_needs_no_gpu(libpath):
     from tfhe_fbs_map_b200 import params
     lib = backend.load_library(libpath)
     out = ctypes.c_void_p()
-    for bad, msg in ((dict(bsk_unroll=3), b"bsk_unroll"), (dict(bsk_unroll=2, n=741), b"even"),
-                     (dict(bsk_unroll=2, bsk_l=2, bsk_beta=12), b"even"), (dict(N=1000), b"power of two"),
+    for bad, msg in ((dict(bsk_unroll=3), b"bsk_unroll"),
+                     (dict(bsk_unroll=2, bsk_l=2, bsk_beta=12), b"bsk_l = 1"), (dict(N=1000), b"power of two"),
                      (dict(bsk_l=1, bsk_beta=26), b"bsk_beta")):
         d = params.get("A").as_dict(); d.update(bad); d["name"] = "bad"
         cp = params.to_c(params.ParamSet(**d))

@@ -163,7 +163,7 @@ static int ctx_create_impl(const fbs_params *params, int device, uint64_t seed, 
     const BRVariant *br = nullptr, *br1 = nullptr;
     const int unroll = P.bsk_unroll == 2 ? 2 : 1;
     if (P.bsk_unroll < 0 || P.bsk_unroll > 2) return fail(FBS_ERR_ARG, "bsk_unroll must be 0, 1 or 2");
-    if (unroll == 2 && ((P.n & 1) || P.bsk_l != 1)) return fail(FBS_ERR_ARG, "bsk_unroll = 2 needs an even n and bsk_l = 1");
+    if (unroll == 2 && P.bsk_l != 1) return fail(FBS_ERR_ARG, "bsk_unroll = 2 needs bsk_l = 1");
     for (const BRVariant &v : g_br_variants) if (v.logN == logN && v.k == P.k && v.l == P.bsk_l && v.unr == unroll) {
         if (!br || v.pb > br->pb) br = &v;
         if (v.pb == 1) br1 = &v;
@@ -176,16 +176,18 @@ static int ctx_create_impl(const fbs_params *params, int device, uint64_t seed, 
     fbs_ctx *c = new fbs_ctx();
     *partial = c;
     c->P = P; c->device = device; c->seed = seed; c->logN = logN; c->br = br; c->br1 = br1 ? br1 : br;
-    c->unroll = unroll; c->n_ggsw = unroll == 2 ? 3 * (P.n / 2) : P.n;
+    c->unroll = unroll; c->n_ggsw = unroll == 2 ? 3 * ((P.n + 1) / 2) : P.n;
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, device));
     c->sm_count = prop.multiProcessorCount;
     c->br_smem = br->smem(P.n);
     if (c->br_smem > (size_t)prop.sharedMemPerBlockOptin)
         return fail(FBS_ERR_ARG, "blind-rotate kernel needs " + std::to_string(c->br_smem) + " B shared memory, device offers " + std::to_string(prop.sharedMemPerBlockOptin));
-    CK(br->prepare(c->br_smem));
+    // the attribute belongs to the FUNCTION, not to this context: contexts with different n share a kernel instantiation,
+    // so it is raised to the device limit once instead of to this context's need (a later, smaller context would lower it)
+    CK(br->prepare((size_t)prop.sharedMemPerBlockOptin));
     c->br1_smem = c->br1->smem(P.n);
-    if (c->br1 != c->br) CK(c->br1->prepare(c->br1_smem));
+    if (c->br1 != c->br) CK(c->br1->prepare((size_t)prop.sharedMemPerBlockOptin));
     CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     for (auto &e : c->ev) CK(cudaEventCreate(&e));
     // twiddles psi^bitrev(i): 7 generates Z_P^*
@@ -248,7 +250,7 @@ extern "C" int fbs_keygen(fbs_ctx *c)
     const size_t total = (size_t)c->n_ggsw * rows * (k + 1) * N;
     if (!c->d_bsk) { CKR(dev_alloc(&c->d_bsk, total)); CKR(dev_alloc(&c->d_bsk_coef, total)); }
     k_gen_bsk_fill<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(c->d_bsk_coef, k, N, c->seed, P.glwe_noise, total);
-    k_bsk_body<<<c->n_ggsw * rows, 256, (size_t)N * 9, st>>>(c->d_bsk_coef, k, N, l, c->d_s_lwe, c->d_s_big, c->d_gad_bsk, c->unroll);
+    k_bsk_body<<<c->n_ggsw * rows, 256, (size_t)N * 9, st>>>(c->d_bsk_coef, k, N, l, c->d_s_lwe, c->d_s_big, c->d_gad_bsk, c->unroll, n);
     ntt_launch_fn nf = ntt_for(c->logN);
     if (!nf) return fail(FBS_ERR_ARG, "no NTT kernel for this N");
     if (c->unroll == 2) nf(c->d_bsk_coef, c->d_bsk, 3, c->d_psi_rev, c->d_psi_inv_rev, c->mont2_ninv[0], c->mont2_ninv[1], (long long)(total / N), st, k + 1);

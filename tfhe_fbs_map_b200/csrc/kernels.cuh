@@ -113,14 +113,14 @@ __global__ void k_gen_bsk_fill(u64 *bsk, int k, int N, u64 seed, u64 noise_scale
 // body += sum_v A_v * S_v (negacyclic, S binary), then add s_lwe[i]*g_j to coefficient 0 of poly u
 // GGSW i encrypts s_lwe[i] (classic) or, key-unrolled, the bit products of key pair t = i / 3:
 // c = i % 3 = 0: s1 s2, 1: s1 (1 - s2), 2: (1 - s1) s2   (oracle/tfhe_ref.c: ggsw_bit)
-__device__ __forceinline__ int fbs_ggsw_bit(const u8 *__restrict__ s_lwe, int i, int unroll)
+__device__ __forceinline__ int fbs_ggsw_bit(const u8 *__restrict__ s_lwe, int i, int unroll, int n)
 {
     if (unroll != 2) return s_lwe[i];
-    const int t = i / 3, c = i % 3, s1 = s_lwe[2 * t], s2 = s_lwe[2 * t + 1];
+    const int t = i / 3, c = i % 3, s1 = s_lwe[2 * t], s2 = (2 * t + 1 < n) ? s_lwe[2 * t + 1] : 0;     // odd n: zero pad
     return c == 0 ? (s1 & s2) : c == 1 ? (s1 & (s2 ^ 1)) : ((s1 ^ 1) & s2);
 }
 __global__ void __launch_bounds__(256) k_bsk_body(u64 *bsk, int k, int N, int l, const u8 *__restrict__ s_lwe,
-                                                 const u8 *__restrict__ s_big, const u64 *__restrict__ gadgets, int unroll)
+                                                 const u8 *__restrict__ s_big, const u64 *__restrict__ gadgets, int unroll, int n)
 {
     extern __shared__ u64 sh_a[];                 // [N] mask poly, then [N] key bits as bytes
     u8 *sh_s = (u8 *)(sh_a + N);
@@ -142,7 +142,7 @@ __global__ void __launch_bounds__(256) k_bsk_body(u64 *bsk, int k, int N, int l,
         }
     }
     __syncthreads();
-    if (threadIdx.x == 0 && fbs_ggsw_bit(s_lwe, i, unroll)) row[(size_t)u * N] = fq_add(row[(size_t)u * N], gadgets[j]);
+    if (threadIdx.x == 0 && fbs_ggsw_bit(s_lwe, i, unroll, n)) row[(size_t)u * N] = fq_add(row[(size_t)u * N], gadgets[j]);
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -792,7 +792,7 @@ __global__ void __launch_bounds__((PB / TP) * (K + 1) * (1 << LOGN) / 8, 1) k_bl
     const size_t ms_stride = C::ms_stride(a.n);
     u16 *s_ms = (u16 *)((unsigned char *)(empty + R) + (size_t)pb0 * ms_stride);
     const int n = a.n, p = a.p;
-    const int n_slices = 8 * (n / 2);
+    const int n_pairs = (n + 1) / 2, n_slices = 8 * n_pairs;      // odd n: the last pair has a zero second key bit (a2 = 0)
 
     bool live[TP]; int node[TP], tabL[TP], tab0[TP], mode[TP]; long long inst[TP], job[TP];
 #pragma unroll
@@ -872,7 +872,7 @@ __global__ void __launch_bounds__((PB / TP) * (K + 1) * (1 << LOGN) / 8, 1) k_bl
     for (int og = 0; og < G; og++) { int gg = g + og; if (gg >= G) gg -= G; koff[og] = (u32)(((gg * G + g) * T + tau) * 8); }
     int slot = 0; u32 par = 0;                                    // ring position of the next slice to consume
 
-    for (int t = 0; t < n / 2; t++) {
+    for (int t = 0; t < n_pairs; t++) {
         // ---- decompose ACC_g itself: one balanced digit per coefficient (L = 1), lazy residues in (0, 2p)
         rns2 dg[1][TP][8];
 #pragma unroll
@@ -905,7 +905,7 @@ __global__ void __launch_bounds__((PB / TP) * (K + 1) * (1 << LOGN) / 8, 1) k_bl
 #pragma unroll
         for (int q = 0; q < TP; q++) {
             const u16 *msq = (const u16 *)((const unsigned char *)s_ms + (size_t)q * ms_stride);
-            const u32 a1 = msq[2 * t], a2 = msq[2 * t + 1];
+            const u32 a1 = msq[2 * t], a2 = (2 * t + 1 < n) ? msq[2 * t + 1] : 0u;      // msq[n] is the body, not a mask element
             const u32 E[3] = {a1 + a2, a1, a2};
 #pragma unroll
             for (int c = 0; c < 3; c++) {

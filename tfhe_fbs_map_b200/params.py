@@ -34,7 +34,7 @@ class ParamSet:
     lwe_sigma: float  # std of small-LWE (KSK) noise, torus units
     glwe_sigma: float # std of GLWE (BSK, fresh input) noise, torus units
     secure: bool = True
-    bsk_unroll: int = 1  # 2 = two key bits per blind-rotation step (three GGSW per key pair, n/2 steps; n must be even)
+    bsk_unroll: int = 1  # 2 = two key bits per blind-rotation step (three GGSW per key pair, ceil(n/2) steps; needs bsk_l = 1)
 
     @property
     def big_dim(self) -> int:
@@ -54,7 +54,7 @@ class ParamSet:
 
     @property
     def n_ggsw(self) -> int:
-        return 3 * (self.n // 2) if self.bsk_unroll == 2 else self.n
+        return 3 * ((self.n + 1) // 2) if self.bsk_unroll == 2 else self.n      # odd n: last pair padded with a zero key bit
 
     @property
     def bsk_bytes(self) -> int:
@@ -70,7 +70,7 @@ class ParamSet:
         k1, l, N = self.k + 1, self.bsk_l, self.N
         ntt = (k1 * l + k1) * (N // 2) * int(math.log2(N))
         if self.bsk_unroll == 2:      # per key PAIR: one transform set, 3 factor x key products + 1 digit x bundle product per key word
-            return (self.n // 2) * (ntt + 4 * k1 * k1 * l * N)
+            return ((self.n + 1) // 2) * (ntt + 4 * k1 * k1 * l * N)
         return self.n * (ntt + k1 * k1 * l * N)
 
     def mul32_per_pbs(self) -> int:
@@ -153,8 +153,10 @@ def _unrolled(ps: ParamSet, name: str) -> ParamSet:
 # key-unrolled twins (two key bits per blind-rotation step, 1.5x the bootstrapping key): same security and shape
 SET_A2 = _unrolled(SET_A, "A2")
 TOY_2U, TOY_3U, TOY_5U = _unrolled(TOY_2, "toy2u"), _unrolled(TOY_3, "toy3u"), _unrolled(TOY_5, "toy5u")
+_d7 = asdict(TOY_3); _d7.update(name="toy7u", n=15, bsk_unroll=2)      # odd n: the last key pair is padded with a zero bit
+TOY_7U = ParamSet(**_d7)
 
-PARAM_SETS = {ps.name: ps for ps in (SET_A, SET_A2, SET_C, SET_S, TOY_1, TOY_2, TOY_3, TOY_4, TOY_5, TOY_6, TOY_2U, TOY_3U, TOY_5U)}
+PARAM_SETS = {ps.name: ps for ps in (SET_A, SET_A2, SET_C, SET_S, TOY_1, TOY_2, TOY_3, TOY_4, TOY_5, TOY_6, TOY_2U, TOY_3U, TOY_5U, TOY_7U)}
 DEFAULT_SET = "A2"
 
 
