@@ -89,7 +89,7 @@ enum { DOM_SLWE = 1, DOM_SGLWE = 2, DOM_BSK_MASK = 3, DOM_BSK_NOISE = 4, DOM_KSK
 
 /* ---------------- parameters / context ---------------- */
 typedef struct {
-    int32_t n, k, N, bsk_l, bsk_beta, ks_l, ks_beta, bsk_unroll;   /* bsk_unroll: 0/1 classic, 2 = two key bits per step */
+    int32_t n, k, N, bsk_l, bsk_beta, ks_l, ks_beta, bsk_unroll;   /* bsk_unroll: 0/1 classic, 2 / 3 = that many key bits per step */
     u64 lwe_noise, glwe_noise;   /* round(sigma * P) */
 } ref_params;
 
@@ -216,16 +216,26 @@ void ref_ctx_destroy(ref_ctx *c)
     free(c->s_lwe); free(c->s_big); free(c->ksk); free(c->bsk_coef); free(c->bsk_ntt); free(c->psi_rev); free(c->psi_inv_rev); free(c);
 }
 
-/* Key unrolling (two key bits per blind-rotation step): X^(a1 s1 + a2 s2) - 1 =
- *   (X^(a1+a2) - 1) s1 s2 + (X^a1 - 1) s1 (1 - s2) + (X^a2 - 1) (1 - s1) s2,
- * so pair t of the key gets three GGSW ciphertexts, of the bits m_0 = s1 s2, m_1 = s1 (1-s2), m_2 = (1-s1) s2 (GGSW index 3t + c).
- * Classic: GGSW i encrypts s_i. */
-static int n_ggsw(const ref_params *P) { return P->bsk_unroll == 2 ? 3 * ((P->n + 1) / 2) : P->n; }   /* odd n: last pair padded with a zero key bit */
+/* Key unrolling (m = bsk_unroll key bits per blind-rotation step, m = 2 or 3):
+ *   X^(sum_i a_i s_i) - 1 = sum over the non-empty subsets T of the m key bits of (X^(sum_{i in T} a_i) - 1) * [key bits == T],
+ * so group t of the key gets 2^m - 1 GGSW ciphertexts, of the indicator bits prod_{i in T} s_i * prod_{i not in T} (1 - s_i)
+ * (GGSW index (2^m - 1) t + c, subset mask_of(m, c); bit i of the mask stands for key bit m t + i).  For m = 2:
+ *   X^(a1 s1 + a2 s2) - 1 = (X^(a1+a2) - 1) s1 s2 + (X^a1 - 1) s1 (1 - s2) + (X^a2 - 1) (1 - s1) s2.
+ * n is padded with zero key bits (and a_i = 0) to a multiple of m.  Classic (m <= 1): GGSW i encrypts s_i. */
+static int unroll_m(const ref_params *P) { return P->bsk_unroll == 2 || P->bsk_unroll == 3 ? P->bsk_unroll : 1; }
+static int n_groups(const ref_params *P) { int m = unroll_m(P); return (P->n + m - 1) / m; }
+static int n_sub(const ref_params *P) { return (1 << unroll_m(P)) - 1; }
+static int mask_of(int m, int c) { static const int m2[3] = {3, 1, 2}; return m == 2 ? m2[c] : c + 1; }
+static int n_ggsw(const ref_params *P) { return unroll_m(P) == 1 ? P->n : n_sub(P) * n_groups(P); }
+static int key_bit(const ref_ctx *c, int i) { return i < c->P.n ? c->s_lwe[i] : 0; }
 static int ggsw_bit(const ref_ctx *c, int g)
 {
-    if (c->P.bsk_unroll != 2) return c->s_lwe[g];
-    int t = g / 3, cc = g % 3, s1 = c->s_lwe[2 * t], s2 = (2 * t + 1 < c->P.n) ? c->s_lwe[2 * t + 1] : 0;
-    return cc == 0 ? (s1 & s2) : cc == 1 ? (s1 & !s2) : (!s1 & s2);
+    const int m = unroll_m(&c->P);
+    if (m == 1) return c->s_lwe[g];
+    const int ns = n_sub(&c->P), t = g / ns, mask = mask_of(m, g % ns);
+    int bit = 1;
+    for (int i = 0; i < m; i++) bit &= ((mask >> i) & 1) ? key_bit(c, m * t + i) : !key_bit(c, m * t + i);
+    return bit;
 }
 void ref_keygen(ref_ctx *c)
 {
@@ -398,18 +408,21 @@ void ref_blind_rotate(const ref_ctx *c, const uint16_t *ms, const u64 *tv, u64 *
     int bt = ms[n];
     for (int j = 0; j < N; j++) acc[(size_t)k * N + j] = rot_coef(tv, N, j, (2 * N - bt) % (2 * N));
     u64 *dig = malloc((size_t)rows * N * 8), *outp = malloc((size_t)(k + 1) * N * 8);
-    if (P->bsk_unroll == 2) {
-        /* ACC <- ACC + sum_c (X^{e_c} - 1) * (Dec(ACC) [x] GGSW_{3t+c}),  e = (a1 + a2, a1, a2): one decomposition per key pair */
+    if (unroll_m(P) > 1) {
+        /* ACC <- ACC + sum_c (X^{e_c} - 1) * (Dec(ACC) [x] GGSW_{ns t + c}),  e_c = sum of the a_i in subset c: one decomposition per key group */
+        const int m = unroll_m(P), ns = n_sub(P);
         u64 *delta = malloc((size_t)(k + 1) * N * 8);
-        for (int t = 0; t < (n + 1) / 2; t++) {
-            const int a1 = ms[2 * t], a2 = (2 * t + 1 < n) ? ms[2 * t + 1] : 0, e[3] = {(a1 + a2) % (2 * N), a1, a2};
+        for (int t = 0; t < n_groups(P); t++) {
             decompose_ntt(c, acc, -1, dig);
             memset(delta, 0, (size_t)(k + 1) * N * 8);
-            for (int cc = 0; cc < 3; cc++) {
-                ext_product(c, dig, 3 * t + cc, outp);
+            for (int cc = 0; cc < ns; cc++) {
+                int e = 0;
+                for (int i = 0; i < m; i++) if (((mask_of(m, cc) >> i) & 1) && m * t + i < n) e += ms[m * t + i];
+                e %= 2 * N;
+                ext_product(c, dig, ns * t + cc, outp);
                 for (int v = 0; v <= k; v++) for (int j = 0; j < N; j++) {
                     const u64 *o = outp + (size_t)v * N;
-                    delta[(size_t)v * N + j] = f_add(delta[(size_t)v * N + j], f_sub(rot_coef(o, N, j, e[cc]), o[j]));
+                    delta[(size_t)v * N + j] = f_add(delta[(size_t)v * N + j], f_sub(rot_coef(o, N, j, e), o[j]));
                 }
             }
             for (size_t w = 0; w < (size_t)(k + 1) * N; w++) acc[w] = f_add(acc[w], delta[w]);

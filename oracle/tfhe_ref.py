@@ -121,7 +121,7 @@ class RefTFHE:
         s_lwe = np.zeros(ps.n, np.uint8)
         s_big = np.zeros(ps.k * ps.N, np.uint8)
         ksk = np.zeros((ps.k * ps.N * ps.ks_l, ps.n + 1), np.uint64)
-        n_ggsw = 3 * ((ps.n + 1) // 2) if getattr(ps, "bsk_unroll", 1) == 2 else ps.n
+        n_ggsw = ps.n_ggsw if hasattr(ps, "n_ggsw") else ps.n
         bsk = np.zeros((n_ggsw, (ps.k + 1) * ps.bsk_l, ps.k + 1, ps.N), np.uint64)
         self.L.ref_get_keys(self.ctx, _p(s_lwe), _p(s_big), _p(ksk), _p(bsk))
         return s_lwe, s_big, ksk, bsk

@@ -44,7 +44,7 @@ def test_library_is_sm100a_with_tma(libpath):
     assert "UBLKCP" in sass          # cp.async.bulk = TMA bulk copy streams the bootstrapping key
     assert "IMAD.WIDE" in sass       # the arithmetic runs on the integer pipes
     # the default (key-unrolled) kernel: TMA key ring with mbarriers, no global load inside the step loop's transforms
-    sass2 = subprocess.run(["cuobjdump", "-sass", "-fun", "_Z15k_blind_rotate2ILi11ELi1ELi2ELi2EEv6BRArgs", libpath],
+    sass2 = subprocess.run(["cuobjdump", "-sass", "-fun", "_Z15k_blind_rotate2ILi11ELi1ELi2ELi2ELi2EEv6BRArgs", libpath],
                            capture_output=True, text=True).stdout
     assert "UBLKCP" in sass2 and "SYNCS.ARRIVE" in sass2 and "IMAD.HI.U32" in sass2
 
@@ -54,8 +54,8 @@ def test_parameter_validation_needs_no_gpu(libpath):
     from tfhe_fbs_map_b200 import params
     lib = backend.load_library(libpath)
     out = ctypes.c_void_p()
-    for bad, msg in ((dict(bsk_unroll=3), b"bsk_unroll"),
-                     (dict(bsk_unroll=2, bsk_l=2, bsk_beta=12), b"bsk_l = 1"), (dict(N=1000), b"power of two"),
+    for bad, msg in ((dict(bsk_unroll=4), b"bsk_unroll"),
+                     (dict(bsk_unroll=2, bsk_l=2, bsk_beta=12), b"bsk_l = 1"), (dict(bsk_unroll=3, bsk_l=2, bsk_beta=12), b"bsk_l = 1"), (dict(N=1000), b"power of two"),
                      (dict(bsk_l=1, bsk_beta=26), b"bsk_beta")):
         d = params.get("A").as_dict(); d.update(bad); d["name"] = "bad"
         cp = params.to_c(params.ParamSet(**d))

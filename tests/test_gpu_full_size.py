@@ -11,7 +11,7 @@ from tfhe_fbs_map_b200 import levelize, params
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(scope="module", params=["A", "A2"])     # A2: same shape, two key bits per blind-rotation step
+@pytest.fixture(scope="module", params=["A", "A2", "A3"])     # A2 / A3: same shape, two / three key bits per blind-rotation step
 def be(request):
     from tfhe_fbs_map_b200.backend import B200Backend
     b = B200Backend(request.param, device=0, seed=20241018)

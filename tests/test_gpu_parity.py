@@ -11,7 +11,7 @@ from tfhe_fbs_map_b200 import levelize, params
 from tfhe_fbs_map_b200.formats import read_lbf
 
 pytestmark = pytest.mark.gpu
-TOYS = ["toy1", "toy2", "toy3", "toy4", "toy5", "toy6", "toy2u", "toy3u", "toy5u", "toy7u"]     # *u: two key bits per blind-rotation step (toy7u: odd n)
+TOYS = ["toy1", "toy2", "toy3", "toy4", "toy5", "toy6", "toy2u", "toy3u", "toy5u", "toy7u", "toy3v", "toy5v"]     # *u / *v: two / three key bits per blind-rotation step (toy7u: odd n)
 SEED = 777
 
 

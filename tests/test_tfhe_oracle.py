@@ -13,7 +13,7 @@ from tfhe_fbs_map_b200.formats import read_lbf
 P = GOLDILOCKS_P
 
 
-@pytest.fixture(scope="module", params=["toy1", "toy2", "toy3", "toy2u", "toy3u", "toy7u"])   # *u: key-unrolled blind rotation
+@pytest.fixture(scope="module", params=["toy1", "toy2", "toy3", "toy2u", "toy3u", "toy7u", "toy3v"])   # *u: key-unrolled blind rotation
 def ref(request):
     return RefTFHE(params.get(request.param), seed=2024)
 

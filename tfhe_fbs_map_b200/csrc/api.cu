@@ -44,21 +44,21 @@ static cudaError_t br_prepare(size_t smem)
 }
 template <int LOGN, int K, int L, bool SM, int PB, int TP> static size_t br_smem(int n) { return BRCfg<LOGN, K, L, SM, PB, TP>::smem_bytes(n); }
 #define BRV(LOGN, K, L, SM, PB, TP) { LOGN, K, L, SM, PB, TP, BRCfg<LOGN, K, L, SM, PB, TP>::THREADS, br_smem<LOGN, K, L, SM, PB, TP>, br_launch<LOGN, K, L, SM, PB, TP>, br_prepare<LOGN, K, L, SM, PB, TP>, 1 }
-// key-unrolled kernels (bsk_unroll = 2, one decomposition level)
-template <int LOGN, int K, int PB, int TP>
+// key-unrolled kernels (bsk_unroll = M = 2 or 3 key bits per step, one decomposition level)
+template <int LOGN, int K, int PB, int TP, int M>
 static cudaError_t br2_launch(const BRArgs &a, long long jobs, size_t smem, cudaStream_t st)
 {
     const long long grid = (jobs - a.job_begin + PB - 1) / PB;
-    k_blind_rotate2<LOGN, K, PB, TP><<<(unsigned)grid, BR2Cfg<LOGN, K, PB, TP>::THREADS, smem, st>>>(a);
+    k_blind_rotate2<LOGN, K, PB, TP, M><<<(unsigned)grid, BR2Cfg<LOGN, K, PB, TP, M>::THREADS, smem, st>>>(a);
     return cudaGetLastError();
 }
-template <int LOGN, int K, int PB, int TP>
+template <int LOGN, int K, int PB, int TP, int M>
 static cudaError_t br2_prepare(size_t smem)
 {
-    return cudaFuncSetAttribute(k_blind_rotate2<LOGN, K, PB, TP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    return cudaFuncSetAttribute(k_blind_rotate2<LOGN, K, PB, TP, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 }
-template <int LOGN, int K, int PB, int TP> static size_t br2_smem(int n) { return BR2Cfg<LOGN, K, PB, TP>::smem_bytes(n); }
-#define BRV2(LOGN, K, PB, TP) { LOGN, K, 1, false, PB, TP, BR2Cfg<LOGN, K, PB, TP>::THREADS, br2_smem<LOGN, K, PB, TP>, br2_launch<LOGN, K, PB, TP>, br2_prepare<LOGN, K, PB, TP>, 2 }
+template <int LOGN, int K, int PB, int TP, int M> static size_t br2_smem(int n) { return BR2Cfg<LOGN, K, PB, TP, M>::smem_bytes(n); }
+#define BRV2(LOGN, K, PB, TP, M) { LOGN, K, 1, false, PB, TP, BR2Cfg<LOGN, K, PB, TP, M>::THREADS, br2_smem<LOGN, K, PB, TP, M>, br2_launch<LOGN, K, PB, TP, M>, br2_prepare<LOGN, K, PB, TP, M>, M }
 #ifndef FBS_SETA_TP
 #define FBS_SETA_TP 2     /* bootstraps per thread in the set-A kernel: 2 = every thread carries both bootstraps of its CTA */
 #endif
@@ -68,8 +68,10 @@ static const BRVariant g_br_variants[] = {
     BRV(11, 1, 2, false, 1, 1),            // set C (row does not fit shared memory next to the accumulator: BSK read from L2)
     BRV(10, 2, 1, true, 1, 1),             // set S
     BRV(8, 1, 2, true, 2, 2), BRV(8, 2, 1, true, 2, 1), BRV(9, 1, 1, true, 2, 2), BRV(10, 1, 3, true, 1, 1),   // toy sets (tests)
-    BRV2(11, 1, 2, 2), BRV2(11, 1, 1, 1),          // set A2 (two key bits per step)
-    BRV2(9, 1, 2, 2), BRV2(8, 2, 2, 1),            // toy3u, toy2u
+    BRV2(11, 1, 2, 2, 2), BRV2(11, 1, 1, 1, 2),    // set A2 (two key bits per step)
+    BRV2(9, 1, 2, 2, 2), BRV2(8, 2, 2, 1, 2),      // toy3u / toy7u, toy2u
+    BRV2(11, 1, 2, 2, 3), BRV2(11, 1, 1, 1, 3),    // set A3 (three key bits per step)
+    BRV2(9, 1, 2, 2, 3),                           // toy3v
 };
 
 typedef void (*ntt_launch_fn)(const u64 *, u64 *, int, const fq_tw *, const fq_tw *, u32, u32, long long, cudaStream_t, int);
@@ -161,9 +163,9 @@ static int ctx_create_impl(const fbs_params *params, int device, uint64_t seed, 
     if (P.bsk_l == 1 && P.bsk_beta > 24) return fail(FBS_ERR_ARG, "one-level blind-rotate decomposition needs bsk_beta <= 24");
     if (P.n < 1 || P.n > 4095) return fail(FBS_ERR_ARG, "n out of range");
     const BRVariant *br = nullptr, *br1 = nullptr;
-    const int unroll = P.bsk_unroll == 2 ? 2 : 1;
-    if (P.bsk_unroll < 0 || P.bsk_unroll > 2) return fail(FBS_ERR_ARG, "bsk_unroll must be 0, 1 or 2");
-    if (unroll == 2 && P.bsk_l != 1) return fail(FBS_ERR_ARG, "bsk_unroll = 2 needs bsk_l = 1");
+    const int unroll = (P.bsk_unroll == 2 || P.bsk_unroll == 3) ? P.bsk_unroll : 1;
+    if (P.bsk_unroll < 0 || P.bsk_unroll > 3) return fail(FBS_ERR_ARG, "bsk_unroll must be 0, 1, 2 or 3");
+    if (unroll > 1 && P.bsk_l != 1) return fail(FBS_ERR_ARG, "bsk_unroll > 1 needs bsk_l = 1");
     for (const BRVariant &v : g_br_variants) if (v.logN == logN && v.k == P.k && v.l == P.bsk_l && v.unr == unroll) {
         if (!br || v.pb > br->pb) br = &v;
         if (v.pb == 1) br1 = &v;
@@ -176,7 +178,7 @@ static int ctx_create_impl(const fbs_params *params, int device, uint64_t seed, 
     fbs_ctx *c = new fbs_ctx();
     *partial = c;
     c->P = P; c->device = device; c->seed = seed; c->logN = logN; c->br = br; c->br1 = br1 ? br1 : br;
-    c->unroll = unroll; c->n_ggsw = unroll == 2 ? 3 * ((P.n + 1) / 2) : P.n;
+    c->unroll = unroll; c->n_ggsw = unroll > 1 ? ((1 << unroll) - 1) * ((P.n + unroll - 1) / unroll) : P.n;
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, device));
     c->sm_count = prop.multiProcessorCount;
@@ -253,7 +255,7 @@ extern "C" int fbs_keygen(fbs_ctx *c)
     k_bsk_body<<<c->n_ggsw * rows, 256, (size_t)N * 9, st>>>(c->d_bsk_coef, k, N, l, c->d_s_lwe, c->d_s_big, c->d_gad_bsk, c->unroll, n);
     ntt_launch_fn nf = ntt_for(c->logN);
     if (!nf) return fail(FBS_ERR_ARG, "no NTT kernel for this N");
-    if (c->unroll == 2) nf(c->d_bsk_coef, c->d_bsk, 3, c->d_psi_rev, c->d_psi_inv_rev, c->mont2_ninv[0], c->mont2_ninv[1], (long long)(total / N), st, k + 1);
+    if (c->unroll > 1) nf(c->d_bsk_coef, c->d_bsk, 3, c->d_psi_rev, c->d_psi_inv_rev, c->mont2_ninv[0], c->mont2_ninv[1], (long long)(total / N), st, (k + 1) | (((1 << c->unroll) - 1) << 8));
     else nf(c->d_bsk_coef, c->d_bsk, 2, c->d_psi_rev, c->d_psi_inv_rev, c->mont_ninv[0], c->mont_ninv[1], (long long)(total / N), st, k + 1);
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(st));

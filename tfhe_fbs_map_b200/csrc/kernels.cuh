@@ -111,13 +111,20 @@ __global__ void k_gen_bsk_fill(u64 *bsk, int k, int N, u64 seed, u64 noise_scale
                      : fbs_rnd_noise(seed, DOM_BSK_NOISE, ir * (u64)N + q, noise_scale);
 }
 // body += sum_v A_v * S_v (negacyclic, S binary), then add s_lwe[i]*g_j to coefficient 0 of poly u
-// GGSW i encrypts s_lwe[i] (classic) or, key-unrolled, the bit products of key pair t = i / 3:
-// c = i % 3 = 0: s1 s2, 1: s1 (1 - s2), 2: (1 - s1) s2   (oracle/tfhe_ref.c: ggsw_bit)
+// GGSW i encrypts s_lwe[i] (classic) or, key-unrolled by m = 2 or 3, the indicator bit of subset c = i % (2^m - 1) of key
+// group t = i / (2^m - 1): prod_{j in mask} s_j * prod_{j not in mask} (1 - s_j) with zero padding beyond n
+// (oracle/tfhe_ref.c: ggsw_bit, mask_of).
+__host__ __device__ __forceinline__ int fbs_unroll_mask(int m, int c) { return m == 2 ? (c == 0 ? 3 : c) : c + 1; }
 __device__ __forceinline__ int fbs_ggsw_bit(const u8 *__restrict__ s_lwe, int i, int unroll, int n)
 {
-    if (unroll != 2) return s_lwe[i];
-    const int t = i / 3, c = i % 3, s1 = s_lwe[2 * t], s2 = (2 * t + 1 < n) ? s_lwe[2 * t + 1] : 0;     // odd n: zero pad
-    return c == 0 ? (s1 & s2) : c == 1 ? (s1 & (s2 ^ 1)) : ((s1 ^ 1) & s2);
+    if (unroll != 2 && unroll != 3) return s_lwe[i];
+    const int ns = (1 << unroll) - 1, t = i / ns, mask = fbs_unroll_mask(unroll, i % ns);
+    int bit = 1;
+    for (int j = 0; j < unroll; j++) {
+        const int kb = (unroll * t + j < n) ? s_lwe[unroll * t + j] : 0;
+        bit &= ((mask >> j) & 1) ? kb : (kb ^ 1);
+    }
+    return bit;
 }
 __global__ void __launch_bounds__(256) k_bsk_body(u64 *bsk, int k, int N, int l, const u8 *__restrict__ s_lwe,
                                                  const u8 *__restrict__ s_big, const u64 *__restrict__ gadgets, int unroll, int n)
@@ -157,7 +164,7 @@ __global__ void __launch_bounds__(256) k_bsk_body(u64 *bsk, int k, int N, int l,
 // ------------------------------------------------------------------------------------------------------
 template <int LOGN>
 __global__ void __launch_bounds__(NttPlan<LOGN>::T) k_ntt(const u64 *__restrict__ in, u64 *__restrict__ out, int mode,
-                                                         const fq_tw *__restrict__ psi_rev, const fq_tw *__restrict__ psi_inv_rev, u32 scale1, u32 scale2, int g1 /* k+1, mode 3 */)
+                                                         const fq_tw *__restrict__ psi_rev, const fq_tw *__restrict__ psi_inv_rev, u32 scale1, u32 scale2, int g1 /* mode 3: (k+1) | GGSW-per-group << 8 */)
 {
     using P = NttPlan<LOGN>;
     __shared__ u64 bufA[P::N];
@@ -194,8 +201,9 @@ __global__ void __launch_bounds__(NttPlan<LOGN>::T) k_ntt(const u64 *__restrict_
                 v.a = (u32)((u64)v.a * scale1 % FQ_P1);
                 v.b = (u32)((u64)v.b * scale2 % FQ_P2);
                 if (mode == 3) {                                          // polynomial (ggsw = 3t + c, u, v); id = 8*tau + e
-                    const int pv = blockIdx.x % (g1 * g1), ggsw = blockIdx.x / (g1 * g1), t = ggsw / 3, c = ggsw % 3;
-                    out[(((size_t)t * 8 + e) * 3 + c) * g1 * g1 * P::T + (size_t)pv * P::T + tau] = rns_pack(v);
+                    const int G1 = g1 & 0xFF, ns = g1 >> 8;              // k+1 and GGSW per key group (3 or 7), packed by the host
+                    const int pv = blockIdx.x % (G1 * G1), ggsw = blockIdx.x / (G1 * G1), t = ggsw / ns, c = ggsw % ns;
+                    out[(((size_t)t * 8 + e) * ns + c) * G1 * G1 * P::T + (size_t)pv * P::T + tau] = rns_pack(v);
                 }
                 else dst[P::swz(id)] = rns_pack(v);
             }
@@ -751,8 +759,10 @@ __global__ void __launch_bounds__((PB / TP) * (K + 1) * (1 << LOGN) / 8, 1) k_bl
 // (BR2Cfg, full/empty mbarriers); a key word is read from shared memory once per thread and used for every bootstrap the
 // thread carries.  The table psi_pow (psi^x - 1) sits in shared memory too, index nibble XOR-folded against bank conflicts.
 // ------------------------------------------------------------------------------------------------------
-template <int LOGN, int K, int PB, int TP>
+template <int LOGN, int K, int PB, int TP, int M = 2>
 struct BR2Cfg {
+    static_assert(M == 2 || M == 3, "two or three key bits per step");
+    static constexpr int NC = (1 << M) - 1;                       // GGSW ciphertexts (monomial factors) per key group
     static_assert(TP == 1 || TP == PB, "a thread carries one bootstrap or all of the CTA's");
     static constexpr int N = 1 << LOGN, G = K + 1, T = N / 8, PT = G * T, THREADS = (PB / TP) * PT;
     static constexpr size_t s_w = (size_t)G * N;                  // transpose scratch = digit spectra = final accumulator
@@ -760,11 +770,11 @@ struct BR2Cfg {
 #ifndef FBS_TW_SMEM
 #define FBS_TW_SMEM 1
 #endif
-    static constexpr bool TWS = FBS_TW_SMEM != 0;                 // NTT twiddle table in shared memory (16 B per entry)
+    static constexpr bool TWS = FBS_TW_SMEM != 0 && M == 2;       // NTT twiddle table in shared memory (16 B per entry); no room at M = 3
     static constexpr size_t tw_w = TWS ? 2 * (size_t)N : 0;
-    // Key slice = every key word the CTA needs for ONE of the 8 elements a thread holds: [c < 3][u < G][v < G][tau < T]; a step
+    // Key slice = every key word the CTA needs for ONE of the 8 elements a thread holds: [c < NC][u < G][v < G][tau < T]; a step
     // consumes 8 slices in element order.  HBM layout [key pair][element][c][u][v][tau]: one contiguous bulk copy per slice.
-    static constexpr size_t slice_w = 3 * (size_t)G * G * T;
+    static constexpr size_t slice_w = NC * (size_t)G * G * T;
     static constexpr size_t fixed_b = 8 * (PB * s_w + psi_w + tw_w) + PB * 2048 + 256;   // ms rows budgeted for n < 1024
     static constexpr int R_fit = (int)((227 * 1024 - fixed_b) / (8 * slice_w));
 #ifndef FBS_RING_MAX
@@ -775,10 +785,11 @@ struct BR2Cfg {
     __host__ __device__ static constexpr size_t ms_stride(int n) { return (((size_t)(n + 1) * 2 + 15) / 16) * 16; }
     __host__ __device__ static constexpr size_t smem_bytes(int n) { return 8 * (PB * s_w + psi_w + tw_w + R * slice_w + 2 * R) + PB * ms_stride(n); }
 };
-template <int LOGN, int K, int PB, int TP>
+template <int LOGN, int K, int PB, int TP, int M>
 __global__ void __launch_bounds__((PB / TP) * (K + 1) * (1 << LOGN) / 8, 1) k_blind_rotate2(BRArgs a)
 {
-    using C = BR2Cfg<LOGN, K, PB, TP>;
+    using C = BR2Cfg<LOGN, K, PB, TP, M>;
+    constexpr int NC = C::NC;
     using P = NttPlan<LOGN>;
     constexpr int N = C::N, G = C::G, T = C::T, R = C::R;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -792,7 +803,7 @@ __global__ void __launch_bounds__((PB / TP) * (K + 1) * (1 << LOGN) / 8, 1) k_bl
     const size_t ms_stride = C::ms_stride(a.n);
     u16 *s_ms = (u16 *)((unsigned char *)(empty + R) + (size_t)pb0 * ms_stride);
     const int n = a.n, p = a.p;
-    const int n_pairs = (n + 1) / 2, n_slices = 8 * n_pairs;      // odd n: the last pair has a zero second key bit (a2 = 0)
+    const int n_pairs = (n + M - 1) / M, n_slices = 8 * n_pairs;  // key groups; n is padded with zero key bits (a_i = 0) to a multiple of M
 
     bool live[TP]; int node[TP], tabL[TP], tab0[TP], mode[TP]; long long inst[TP], job[TP];
 #pragma unroll
@@ -895,74 +906,10 @@ __global__ void __launch_bounds__((PB / TP) * (K + 1) * (1 << LOGN) / 8, 1) k_bl
                 *(u64 *)(Sb + q * PWB + o) = rns_pack(dg[0][q][e]);
             }
         }
-        // Exponents of the three monomial factors.  Element e evaluates X^E at psi^(E*odd0 + (brev3(e) << (LOGN-2)) * E): the
-        // low LOGN-2 bits of the table index are the same for the 8 elements, only the top three move (by brev3(e) * E mod 8).
-        // With the table's XOR fold (psw) that is: byte offset = lo8 ^ (h * HMUL), h = (hb + brev3(e)*E) & 7, where lo8 has the
-        // fold of the fixed bits applied and HMUL places h at bits LOGN-2.. and (its part of nibble 2) into the low nibble.
-        constexpr bool fast_psi = (LOGN - 2 >= 9) && (LOGN + 1 <= 12);        // top-3 bits lie inside nibble 2, nibble 1 is fixed
-        constexpr u32 HMUL = 8u * ((1u << (LOGN - 2)) | (fast_psi ? (1u << (LOGN - 2 - 8)) : 0u));
-        u32 lo8[TP][3], hb[TP][3], eb[TP][3], Ec[TP][3];
-#pragma unroll
-        for (int q = 0; q < TP; q++) {
-            const u16 *msq = (const u16 *)((const unsigned char *)s_ms + (size_t)q * ms_stride);
-            const u32 a1 = msq[2 * t], a2 = (2 * t + 1 < n) ? msq[2 * t + 1] : 0u;      // msq[n] is the body, not a mask element
-            const u32 E[3] = {a1 + a2, a1, a2};
-#pragma unroll
-            for (int c = 0; c < 3; c++) {
-                const u32 x0 = (E[c] * odd0) & (2 * N - 1);
-                Ec[q][c] = E[c]; eb[q][c] = x0;
-                hb[q][c] = x0 >> (LOGN - 2);
-                const u32 lo = x0 & ((1u << (LOGN - 2)) - 1);
-                lo8[q][c] = 8u * (lo ^ (((lo >> 4) ^ (lo >> 8)) & 15u));       // fold of the fixed bits (bits >= LOGN-2 excluded)
-            }
-        }
-        xsync();                                                 // the partner warps' spectra are in shared memory
-        // ---- point-wise part, one key slice per element
         rns2 x[TP][8];
-#pragma unroll
-        for (int e = 0; e < 8; e++) {
-            const u32 o = bo[0] ^ P::elem_boff(e, 0);
-            constexpr int BR3[8] = {0, 4, 2, 6, 1, 5, 3, 7};
-            mbar_wait(full + slot, par);
-            const unsigned char *ks = (const unsigned char *)(RING + (size_t)slot * C::slice_w);
-            rns2 kk[3][G];
-#pragma unroll
-            for (int c = 0; c < 3; c++)
-#pragma unroll
-                for (int og = 0; og < G; og++) kk[c][og] = rns_split(*(const u64 *)(ks + koff[og] + (size_t)c * G * G * T * 8));
-#pragma unroll
-            for (int q = 0; q < TP; q++) {
-                rns2 f[3];
-#pragma unroll
-                for (int c = 0; c < 3; c++) {
-                    if constexpr (fast_psi) {
-                        const u32 h = (hb[q][c] + (u32)BR3[e] * Ec[q][c]) & 7u;
-                        f[c] = rns_split(*(const u64 *)((const unsigned char *)PSI + (lo8[q][c] ^ (h * HMUL))));
-                    } else {
-                        const u32 xi = (eb[q][c] + (((u32)BR3[e] * Ec[q][c]) << (LOGN - 2))) & (2 * N - 1);
-                        f[c] = rns_split(PSI[psw(xi)]);
-                    }
-                }
-                u64 oa = 0, ob = 0;
-#pragma unroll
-                for (int og = 0; og < G; og++) {
-                    u64 pa = r32_mulwide(f[0].a, kk[0][og].a), pb2 = r32_mulwide(f[0].b, kk[0][og].b);
-                    pa = r32_madwide(f[1].a, kk[1][og].a, pa); pb2 = r32_madwide(f[1].b, kk[1][og].b, pb2);
-                    pa = r32_madwide(f[2].a, kk[2][og].a, pa); pb2 = r32_madwide(f[2].b, kk[2][og].b, pb2);       // < 3 p^2
-                    const u32 ba = r32_redc(pa, FQ_P1, FQ_P1_INVNEG), bb = r32_redc(pb2, FQ_P2, FQ_P2_INVNEG);   // < 1.75 p + 1
-                    // digit spectra from shared memory, the thread's own too: keeping them in registers across the
-                    // point-wise part costs more in spills than the 8 extra loads
-                    int gg = g + og; if (gg >= G) gg -= G;
-                    const u32 xg = (og == 0) ? 0u : (G == 2) ? (1u << SH) : ((u32)(g ^ gg) << SH);
-                    const rns2 d = rns_split(*(const u64 *)(Sb + q * PWB + (o ^ xg)));
-                    if (og == 0) { oa = r32_mulwide(d.a, ba); ob = r32_mulwide(d.b, bb); }
-                    else { oa = r32_madwide(d.a, ba, oa); ob = r32_madwide(d.b, bb, ob); }                      // < G * 3.5 p^2
-                }
-                x[q][e].a = r32_fold(r32_redc(oa, FQ_P1, FQ_P1_INVNEG), 2 * FQ_P1);
-                x[q][e].b = r32_fold(r32_redc(ob, FQ_P2, FQ_P2_INVNEG), 2 * FQ_P2);
-            }
-            // slice consumed by this warp (its key words are in registers); when every warp is through, thread 0 refills
-            // the slot with the slice R ahead, so the copy overlaps R - 1 elements' worth of arithmetic or the transforms
+        // slice consumed by this warp (its key words are in registers); when every warp is through, thread 0 refills the
+        // slot with the slice R ahead, so the copy overlaps the other elements' arithmetic or the transforms
+        auto release_slot = [&](int e) {
             __syncwarp();
             if ((tid & 31) == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(empty + slot)) : "memory");
             if (tid == 0) {
@@ -975,6 +922,153 @@ __global__ void __launch_bounds__((PB / TP) * (K + 1) * (1 << LOGN) / 8, 1) k_bl
                 }
             }
             if (++slot == R) { slot = 0; par ^= 1; }
+
+        };
+        if constexpr (M == 2) {
+            // Exponents of the three monomial factors.  Element e evaluates X^E at psi^(E*odd0 + (brev3(e) << (LOGN-2)) * E): the
+            // low LOGN-2 bits of the table index are the same for the 8 elements, only the top three move (by brev3(e) * E mod 8).
+            // With the table's XOR fold (psw) that is: byte offset = lo8 ^ (h * HMUL), h = (hb + brev3(e)*E) & 7, where lo8 has the
+            // fold of the fixed bits applied and HMUL places h at bits LOGN-2.. and (its part of nibble 2) into the low nibble.
+            constexpr bool fast_psi = (LOGN - 2 >= 9) && (LOGN + 1 <= 12);        // top-3 bits lie inside nibble 2, nibble 1 is fixed
+            constexpr u32 HMUL = 8u * ((1u << (LOGN - 2)) | (fast_psi ? (1u << (LOGN - 2 - 8)) : 0u));
+            u32 lo8[TP][3], hb[TP][3], eb[TP][3], Ec[TP][3];
+#pragma unroll
+            for (int q = 0; q < TP; q++) {
+                const u16 *msq = (const u16 *)((const unsigned char *)s_ms + (size_t)q * ms_stride);
+                const u32 a1 = msq[2 * t], a2 = (2 * t + 1 < n) ? msq[2 * t + 1] : 0u;      // msq[n] is the body, not a mask element
+                const u32 E[3] = {a1 + a2, a1, a2};
+#pragma unroll
+                for (int c = 0; c < 3; c++) {
+                    const u32 x0 = (E[c] * odd0) & (2 * N - 1);
+                    Ec[q][c] = E[c]; eb[q][c] = x0;
+                    hb[q][c] = x0 >> (LOGN - 2);
+                    const u32 lo = x0 & ((1u << (LOGN - 2)) - 1);
+                    lo8[q][c] = 8u * (lo ^ (((lo >> 4) ^ (lo >> 8)) & 15u));       // fold of the fixed bits (bits >= LOGN-2 excluded)
+                }
+            }
+            xsync();                                                 // the partner warps' spectra are in shared memory
+            // ---- point-wise part, one key slice per element
+#pragma unroll
+            for (int e = 0; e < 8; e++) {
+                const u32 o = bo[0] ^ P::elem_boff(e, 0);
+                constexpr int BR3[8] = {0, 4, 2, 6, 1, 5, 3, 7};
+                mbar_wait(full + slot, par);
+                const unsigned char *ks = (const unsigned char *)(RING + (size_t)slot * C::slice_w);
+                rns2 kk[3][G];
+#pragma unroll
+                for (int c = 0; c < 3; c++)
+#pragma unroll
+                    for (int og = 0; og < G; og++) kk[c][og] = rns_split(*(const u64 *)(ks + koff[og] + (size_t)c * G * G * T * 8));
+#pragma unroll
+                for (int q = 0; q < TP; q++) {
+                    rns2 f[3];
+#pragma unroll
+                    for (int c = 0; c < 3; c++) {
+                        if constexpr (fast_psi) {
+                            const u32 h = (hb[q][c] + (u32)BR3[e] * Ec[q][c]) & 7u;
+                            f[c] = rns_split(*(const u64 *)((const unsigned char *)PSI + (lo8[q][c] ^ (h * HMUL))));
+                        } else {
+                            const u32 xi = (eb[q][c] + (((u32)BR3[e] * Ec[q][c]) << (LOGN - 2))) & (2 * N - 1);
+                            f[c] = rns_split(PSI[psw(xi)]);
+                        }
+                    }
+                    u64 oa = 0, ob = 0;
+#pragma unroll
+                    for (int og = 0; og < G; og++) {
+                        u64 pa = r32_mulwide(f[0].a, kk[0][og].a), pb2 = r32_mulwide(f[0].b, kk[0][og].b);
+                        pa = r32_madwide(f[1].a, kk[1][og].a, pa); pb2 = r32_madwide(f[1].b, kk[1][og].b, pb2);
+                        pa = r32_madwide(f[2].a, kk[2][og].a, pa); pb2 = r32_madwide(f[2].b, kk[2][og].b, pb2);       // < 3 p^2
+                        const u32 ba = r32_redc(pa, FQ_P1, FQ_P1_INVNEG), bb = r32_redc(pb2, FQ_P2, FQ_P2_INVNEG);   // < 1.75 p + 1
+                        // digit spectra from shared memory, the thread's own too: keeping them in registers across the
+                        // point-wise part costs more in spills than the 8 extra loads
+                        int gg = g + og; if (gg >= G) gg -= G;
+                        const u32 xg = (og == 0) ? 0u : (G == 2) ? (1u << SH) : ((u32)(g ^ gg) << SH);
+                        const rns2 d = rns_split(*(const u64 *)(Sb + q * PWB + (o ^ xg)));
+                        if (og == 0) { oa = r32_mulwide(d.a, ba); ob = r32_mulwide(d.b, bb); }
+                        else { oa = r32_madwide(d.a, ba, oa); ob = r32_madwide(d.b, bb, ob); }                      // < G * 3.5 p^2
+                    }
+                    x[q][e].a = r32_fold(r32_redc(oa, FQ_P1, FQ_P1_INVNEG), 2 * FQ_P1);
+                    x[q][e].b = r32_fold(r32_redc(ob, FQ_P2, FQ_P2_INVNEG), 2 * FQ_P2);
+                }
+                release_slot(e);
+            }
+        } else {
+            static_assert(M == 2 || G == 2, "the M = 3 sums are sized for k = 1");
+            // Generic factor count (M = 3: seven factors).  One packed word per (bootstrap, factor): fast path
+            // lo8 | hb << 16 | (E & 7) << 20, generic x0 | (E & 7) << 20 (see the M == 2 branch for the index arithmetic).
+            constexpr bool fast_psi = (LOGN - 2 >= 9) && (LOGN + 1 <= 12);
+            constexpr u32 HMUL = 8u * ((1u << (LOGN - 2)) | (fast_psi ? (1u << (LOGN - 2 - 8)) : 0u));
+            u32 PK[TP][NC];
+#pragma unroll
+            for (int q = 0; q < TP; q++) {
+                const u16 *msq = (const u16 *)((const unsigned char *)s_ms + (size_t)q * ms_stride);
+                u32 ai[M];
+#pragma unroll
+                for (int i = 0; i < M; i++) ai[i] = (M * t + i < n) ? msq[M * t + i] : 0u;   // msq[n] is the body, not a mask element
+#pragma unroll
+                for (int c = 0; c < NC; c++) {
+                    u32 E = 0;
+#pragma unroll
+                    for (int i = 0; i < M; i++) if ((fbs_unroll_mask(M, c) >> i) & 1) E += ai[i];
+                    const u32 x0 = (E * odd0) & (2 * N - 1);
+                    if constexpr (fast_psi) {
+                        const u32 lo = x0 & ((1u << (LOGN - 2)) - 1);
+                        PK[q][c] = (8u * (lo ^ (((lo >> 4) ^ (lo >> 8)) & 15u))) | ((x0 >> (LOGN - 2)) << 16) | ((E & 7u) << 20);
+                    } else PK[q][c] = x0 | ((E & 7u) << 20);
+                }
+            }
+            xsync();                                             // the partner warps' spectra are in shared memory
+#pragma unroll
+            for (int e = 0; e < 8; e++) {
+                const u32 o = bo[0] ^ P::elem_boff(e, 0);
+                constexpr int BR3[8] = {0, 4, 2, 6, 1, 5, 3, 7};
+                mbar_wait(full + slot, par);
+                const unsigned char *ks = (const unsigned char *)(RING + (size_t)slot * C::slice_w);
+                auto factor = [&](int q, int c) -> rns2 {        // X^{E_c} - 1 at this thread's element e
+                    const u32 pk = PK[q][c];
+                    if constexpr (fast_psi) {
+                        const u32 h = ((pk >> 16) + (u32)BR3[e] * (pk >> 20)) & 7u;
+                        return rns_split(*(const u64 *)((const unsigned char *)PSI + ((pk & 0xFFFFu) ^ (h * HMUL))));
+                    } else {
+                        const u32 xi = ((pk & 0xFFFFu) + (((u32)BR3[e] * (pk >> 20)) << (LOGN - 2))) & (2 * N - 1);
+                        return rns_split(PSI[psw(xi)]);
+                    }
+                };
+                // bundle_u = REDC(sum_c f_c * key_c[u][g]); factors outermost so that one key word (shared by the bootstraps
+                // the thread carries) and one factor are live at a time next to the 64-bit accumulators
+                u64 pa[TP][G], pb2[TP][G];
+#pragma unroll
+                for (int c = 0; c < NC; c++) {
+                    rns2 kk[G];
+#pragma unroll
+                    for (int og = 0; og < G; og++) kk[og] = rns_split(*(const u64 *)(ks + koff[og] + (size_t)c * G * G * T * 8));
+#pragma unroll
+                    for (int q = 0; q < TP; q++) {
+                        const rns2 f = factor(q, c);
+#pragma unroll
+                        for (int og = 0; og < G; og++) {
+                            if (c == 0) { pa[q][og] = r32_mulwide(f.a, kk[og].a); pb2[q][og] = r32_mulwide(f.b, kk[og].b); }
+                            else { pa[q][og] = r32_madwide(f.a, kk[og].a, pa[q][og]); pb2[q][og] = r32_madwide(f.b, kk[og].b, pb2[q][og]); }
+                        }                                                                    // < NC p^2 <= 7 p^2 < 2^63
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < TP; q++) {
+                    u64 oa = 0, ob = 0;
+#pragma unroll
+                    for (int og = 0; og < G; og++) {
+                        const u32 ba = r32_redc(pa[q][og], FQ_P1, FQ_P1_INVNEG), bb = r32_redc(pb2[q][og], FQ_P2, FQ_P2_INVNEG);   // < 2.75 p + 1
+                        int gg = g + og; if (gg >= G) gg -= G;
+                        const u32 xg = (og == 0) ? 0u : (G == 2) ? (1u << SH) : ((u32)(g ^ gg) << SH);
+                        const rns2 d = rns_split(*(const u64 *)(Sb + q * PWB + (o ^ xg)));            // digit spectrum, < 2p
+                        if (og == 0) { oa = r32_mulwide(d.a, ba); ob = r32_mulwide(d.b, bb); }
+                        else { oa = r32_madwide(d.a, ba, oa); ob = r32_madwide(d.b, bb, ob); }        // < G * 5.5 p^2 < 2^64 (G <= 2)
+                    }
+                    x[q][e].a = r32_fold(r32_redc(oa, FQ_P1, FQ_P1_INVNEG), 2 * FQ_P1);               // < 3.75 p before the fold
+                    x[q][e].b = r32_fold(r32_redc(ob, FQ_P2, FQ_P2_INVNEG), 2 * FQ_P2);
+                }
+                release_slot(e);
+            }
         }
         auto after_pass0 = [&] { xsync(); };                     // the partner warps have read this step's digit spectra
         ntt_inv1_from<LOGN, 0, TP, decltype(after_pass0), decltype(gsync), C::TWS>(x, tau, Sb, PWB, bo, twp, after_pass0, gsync, a.zero);

@@ -34,7 +34,7 @@ class ParamSet:
     lwe_sigma: float  # std of small-LWE (KSK) noise, torus units
     glwe_sigma: float # std of GLWE (BSK, fresh input) noise, torus units
     secure: bool = True
-    bsk_unroll: int = 1  # 2 = two key bits per blind-rotation step (three GGSW per key pair, ceil(n/2) steps; needs bsk_l = 1)
+    bsk_unroll: int = 1  # m = 2 or 3 key bits per blind-rotation step (2^m - 1 GGSW per key group, ceil(n/m) steps; needs bsk_l = 1)
 
     @property
     def big_dim(self) -> int:
@@ -54,7 +54,8 @@ class ParamSet:
 
     @property
     def n_ggsw(self) -> int:
-        return 3 * ((self.n + 1) // 2) if self.bsk_unroll == 2 else self.n      # odd n: last pair padded with a zero key bit
+        m = self.bsk_unroll if self.bsk_unroll in (2, 3) else 1      # key bits per step; n padded with zero bits to a multiple
+        return self.n if m == 1 else ((1 << m) - 1) * ((self.n + m - 1) // m)
 
     @property
     def bsk_bytes(self) -> int:
@@ -69,8 +70,9 @@ class ParamSet:
         """64-bit modular multiplies of one blind rotation, canonical radix-2 count."""
         k1, l, N = self.k + 1, self.bsk_l, self.N
         ntt = (k1 * l + k1) * (N // 2) * int(math.log2(N))
-        if self.bsk_unroll == 2:      # per key PAIR: one transform set, 3 factor x key products + 1 digit x bundle product per key word
-            return ((self.n + 1) // 2) * (ntt + 4 * k1 * k1 * l * N)
+        if self.bsk_unroll in (2, 3): # per key group: one transform set, 2^m - 1 factor x key products + 1 digit x bundle product per key word
+            m = self.bsk_unroll
+            return ((self.n + m - 1) // m) * (ntt + (1 << m) * k1 * k1 * l * N)
         return self.n * (ntt + k1 * k1 * l * N)
 
     def mul32_per_pbs(self) -> int:
@@ -84,10 +86,12 @@ class ParamSet:
         kN = self.k * self.N
         t_key = self.bsk_l * (self.k + 1) * self.N * (B * B + 2) / 12.0 * self.glwe_sigma ** 2     # GGSW noise through the digits
         t_round = (1 + kN / 2.0) / (24.0 * B ** (2 * self.bsk_l))                                 # rounding error times a key bit (E m^2 = 1/2)
-        if self.bsk_unroll == 2:
-            # one external product per key PAIR with the bundle sum_c (X^{e_c} - 1) GGSW_c: three key-noise terms scaled by
-            # |X^e - 1|^2 = 2, and a plaintext X^e - 1 (norm^2 2, present with probability 3/4) instead of a bit
-            v_br = (self.n / 2.0) * (6.0 * t_key + 3.0 * t_round)
+        if self.bsk_unroll in (2, 3):
+            # one external product per key group with the bundle sum_c (X^{e_c} - 1) GGSW_c: 2^m - 1 key-noise terms scaled by
+            # |X^e - 1|^2 = 2, and a plaintext X^e - 1 (norm^2 2, present with probability 1 - 2^-m) instead of a bit
+            # (t_round carries E m^2 = 1/2 of a bit: the factor is 2 * 2 * (1 - 2^-m))
+            m = self.bsk_unroll
+            v_br = (self.n / float(m)) * (2.0 * ((1 << m) - 1) * t_key + 4.0 * (1.0 - 2.0 ** -m) * t_round)
         else:
             v_br = self.n * (t_key + t_round)
         v_ks = kN * (self.ks_l * (Bk * Bk + 2) / 12.0 * self.lwe_sigma ** 2 + 1.0 / (24.0 * Bk ** (2 * self.ks_l)))
@@ -145,8 +149,8 @@ TOY_6 = ParamSet("toy6", n=8, k=1, N=2048, bsk_l=2, bsk_beta=15, ks_l=6, ks_beta
                  lwe_sigma=2.0 ** -30, glwe_sigma=2.0 ** -52, secure=False)
 
 
-def _unrolled(ps: ParamSet, name: str) -> ParamSet:
-    d = asdict(ps); d.update(name=name, bsk_unroll=2)
+def _unrolled(ps: ParamSet, name: str, m: int = 2) -> ParamSet:
+    d = asdict(ps); d.update(name=name, bsk_unroll=m)
     return ParamSet(**d)
 
 
@@ -155,8 +159,11 @@ SET_A2 = _unrolled(SET_A, "A2")
 TOY_2U, TOY_3U, TOY_5U = _unrolled(TOY_2, "toy2u"), _unrolled(TOY_3, "toy3u"), _unrolled(TOY_5, "toy5u")
 _d7 = asdict(TOY_3); _d7.update(name="toy7u", n=15, bsk_unroll=2)      # odd n: the last key pair is padded with a zero bit
 TOY_7U = ParamSet(**_d7)
+# three key bits per step (seven GGSW per key triple)
+SET_A3 = _unrolled(SET_A, "A3", 3)
+TOY_3V, TOY_5V = _unrolled(TOY_3, "toy3v", 3), _unrolled(TOY_5, "toy5v", 3)
 
-PARAM_SETS = {ps.name: ps for ps in (SET_A, SET_A2, SET_C, SET_S, TOY_1, TOY_2, TOY_3, TOY_4, TOY_5, TOY_6, TOY_2U, TOY_3U, TOY_5U, TOY_7U)}
+PARAM_SETS = {ps.name: ps for ps in (SET_A, SET_A2, SET_C, SET_S, TOY_1, TOY_2, TOY_3, TOY_4, TOY_5, TOY_6, TOY_2U, TOY_3U, TOY_5U, TOY_7U, SET_A3, TOY_3V, TOY_5V)}
 DEFAULT_SET = "A2"
 
 
