@@ -100,9 +100,9 @@ def cpu_baseline(ps, sample_fn, p, seed, threads, instances=None):
     from tfhe_fbs_map_b200 import levelize
     env = load_env(sample_fn)
     prog = levelize(env, p)
-    if getattr(ps, "bsk_unroll", 1) == 2:
+    if getattr(ps, "bsk_unroll", 1) > 1:
         # the CPU runs the classic one-bit-per-step blind rotation of the same shape: the oracle's literal key-unrolled
-        # restatement does three external products per key pair and would make the CPU look slower than it is
+        # restatement does 2^m - 1 external products per key group and would make the CPU look slower than it is
         from dataclasses import asdict
         from tfhe_fbs_map_b200.params import ParamSet
         d = asdict(ps); d.update(bsk_unroll=1, name=ps.name + " shape, classic blind rotation")
@@ -225,7 +225,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="adder128_p15", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=None, help="encrypted instances per GPU per step (default 296; 16 for aes128_p11)")
-    ap.add_argument("--param-set", default="A2", help="A2 = set A with two key bits per blind-rotation step (default); A = classic")
+    ap.add_argument("--param-set", default="A3", help="A3 / A2 = set A with three (default) / two key bits per blind-rotation step; A = classic")
     ap.add_argument("--seed", type=int, default=20241018)
     ap.add_argument("--shard", default="instances", choices=["instances", "nodes"],
                     help="instances: batch split across GPUs, no collective (weak scaling); nodes: one circuit, each level's "
@@ -360,9 +360,9 @@ def main():
             evals_per_s=world * B * args.steps / (ms_res * 1e-3), mismatches=mism_res,
             phase_ms_per_step=dict(lincomb=st.ms_lincomb / args.steps, keyswitch=st.ms_keyswitch / args.steps, blind_rotate=st.ms_blind_rotate / args.steps),
             roofline=dict(bound="hbm", achieved=achieved, peak=peaks.get("hbm_gbs"), unit="GB/s", frac=achieved / peaks.get("hbm_gbs"),
-                          traffic=(154.63e6 if ps.bsk_unroll == 2 else 61.95e6) / 1e9,
-                          traffic_note="GB per launch: dram__bytes_read+write of a 592-PBS launch (two waves), profiles/" + ("r1_v11_hot_kernels_summary.txt; the 73 MB key-unrolled BSK does not stay L2-resident between waves and is re-read from HBM once per wave" if ps.bsk_unroll == 2 else "r1_v5_hot_kernels_summary.txt"),
-                          kernel="k_blind_rotate2" if ps.bsk_unroll == 2 else "k_blind_rotate", launch_ms=br_ms_avg, peak_source=peak_kind,
+                          traffic={3: 119.20e6 * 2, 2: 154.63e6}.get(ps.bsk_unroll, 61.95e6) / 1e9,
+                          traffic_note="GB per launch: dram__bytes_read+write of a 592-PBS launch (two waves), profiles/" + ("r1_v12_hot_kernels_summary.txt; the key-unrolled BSK (114 MB at 3 bits per step) does not stay L2-resident between waves and is re-read from HBM once per wave" if ps.bsk_unroll > 1 else "r1_v5_hot_kernels_summary.txt"),
+                          kernel="k_blind_rotate2" if ps.bsk_unroll > 1 else "k_blind_rotate", launch_ms=br_ms_avg, peak_source=peak_kind,
                           note="kernel is integer-issue bound by design (accumulator on chip, keys L2-resident); see roofline_int"),
             roofline_int=dict(bound="int32-multiply", achieved=mul32 / 1e12, peak=int_peak / 1e12, unit="T mul32/s", frac=mul32 / int_peak,
                               mul32_per_pbs=ps.mul32_per_pbs(), modmul_per_pbs=ps.modmul_per_pbs(), peak_source="measured (fbs_measure_int_peak: mad.wide.u32 chains)"),

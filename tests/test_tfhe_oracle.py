@@ -96,9 +96,11 @@ def test_encrypted_program_equals_cleartext(circuit, p):
 def test_unrolled_parameter_model():
     """Key-unrolled twins: three GGSW per key pair, same shape otherwise; the failure probability moves by a hair only
     (key-switch and modulus-switch noise dominate), the canonical multiply count drops."""
-    a, a2 = params.get("A"), params.get("A2")
+    a, a2, a3 = params.get("A"), params.get("A2"), params.get("A3")
     assert a2.n_ggsw == 3 * a.n // 2 and a2.bsk_bytes * 2 == 3 * a.bsk_bytes
-    assert a2.modmul_per_pbs() < 0.75 * a.modmul_per_pbs()
+    assert a3.n_ggsw == 7 * ((a.n + 2) // 3)                       # 742 key bits -> 248 triples (two zero bits of padding)
+    assert a3.modmul_per_pbs() < a2.modmul_per_pbs() < 0.75 * a.modmul_per_pbs()
     for p, norm2 in ((15, 70), (17, 202), (11, 155)):
-        assert a.p_fail(p, norm2) <= a2.p_fail(p, norm2) < 1.5 * a.p_fail(p, norm2)
-    assert params.estimate(15, 70)["param_set"] == "A2"
+        for u in (a2, a3):
+            assert a.p_fail(p, norm2) <= u.p_fail(p, norm2) < 1.5 * a.p_fail(p, norm2)
+    assert params.estimate(15, 70)["param_set"] == params.DEFAULT_SET == "A3"

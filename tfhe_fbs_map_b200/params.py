@@ -164,7 +164,7 @@ SET_A3 = _unrolled(SET_A, "A3", 3)
 TOY_3V, TOY_5V = _unrolled(TOY_3, "toy3v", 3), _unrolled(TOY_5, "toy5v", 3)
 
 PARAM_SETS = {ps.name: ps for ps in (SET_A, SET_A2, SET_C, SET_S, TOY_1, TOY_2, TOY_3, TOY_4, TOY_5, TOY_6, TOY_2U, TOY_3U, TOY_5U, TOY_7U, SET_A3, TOY_3V, TOY_5V)}
-DEFAULT_SET = "A2"
+DEFAULT_SET = "A3"
 
 
 def get(name: str | ParamSet) -> ParamSet:
@@ -173,7 +173,7 @@ def get(name: str | ParamSet) -> ParamSet:
     return PARAM_SETS[name]
 
 
-def estimate(p: int, norm2: float, sets=("S", "A2", "C")) -> dict:
+def estimate(p: int, norm2: float, sets=("S", "A3", "C")) -> dict:
     """Replacement for ``optimizer --precision=p --sq-norm2=norm2`` (reference add_exec_estimates.py:14):
     first shipped set whose failure probability meets concrete's default target 4 sigma ~ 6.3e-5
     (reference concrete.patch:101-102); returns its shape, p_fail and the algorithmic cost in modmuls."""
