@@ -6,7 +6,7 @@ sys.path.insert(0, ".")
 from tfhe_fbs_map_b200.backend import B200Backend
 from tfhe_fbs_map_b200 import params
 
-name = sys.argv[1] if len(sys.argv) > 1 else params.DEFAULT_SET
+name = (sys.argv[1] if len(sys.argv) > 1 else "") or params.DEFAULT_SET
 batches = [int(x) for x in sys.argv[2].split(",")] if len(sys.argv) > 2 else [1, 64, 148, 296, 1184, 4736, 16384, 65536]
 ps = params.get(name)
 be = B200Backend(name, device=0, seed=5)

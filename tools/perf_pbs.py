@@ -4,7 +4,7 @@ import numpy as np
 sys.path.insert(0, ".")
 from tfhe_fbs_map_b200.backend import B200Backend
 from tfhe_fbs_map_b200 import params
-name = sys.argv[1] if len(sys.argv) > 1 else params.DEFAULT_SET
+name = (sys.argv[1] if len(sys.argv) > 1 else "") or params.DEFAULT_SET
 counts = [int(x) for x in sys.argv[2].split(",")] if len(sys.argv) > 2 else [148, 296, 1184]
 t = time.time(); be = B200Backend(name, device=0, seed=1); print("keygen s", round(time.time() - t, 2), be.info())
 p = 17; rng = np.random.default_rng(0)
