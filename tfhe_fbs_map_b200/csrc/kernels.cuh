@@ -924,151 +924,85 @@ __global__ void __launch_bounds__((PB / TP) * (K + 1) * (1 << LOGN) / 8, 1) k_bl
             if (++slot == R) { slot = 0; par ^= 1; }
 
         };
-        if constexpr (M == 2) {
-            // Exponents of the three monomial factors.  Element e evaluates X^E at psi^(E*odd0 + (brev3(e) << (LOGN-2)) * E): the
-            // low LOGN-2 bits of the table index are the same for the 8 elements, only the top three move (by brev3(e) * E mod 8).
-            // With the table's XOR fold (psw) that is: byte offset = lo8 ^ (h * HMUL), h = (hb + brev3(e)*E) & 7, where lo8 has the
-            // fold of the fixed bits applied and HMUL places h at bits LOGN-2.. and (its part of nibble 2) into the low nibble.
-            constexpr bool fast_psi = (LOGN - 2 >= 9) && (LOGN + 1 <= 12);        // top-3 bits lie inside nibble 2, nibble 1 is fixed
-            constexpr u32 HMUL = 8u * ((1u << (LOGN - 2)) | (fast_psi ? (1u << (LOGN - 2 - 8)) : 0u));
-            u32 lo8[TP][3], hb[TP][3], eb[TP][3], Ec[TP][3];
+        static_assert(M == 2 || G == 2, "the M = 3 sums are sized for k = 1");
+        // Exponents of the NC monomial factors, E_c = sum of the a_i in subset c.  Element e evaluates X^E at
+        // psi^(E*odd0 + (brev3(e) << (LOGN-2)) * E): the low LOGN-2 bits of the table index are the same for the 8 elements,
+        // only the top three move (by brev3(e) * E mod 8).  With the table's XOR fold (psw) that is: byte offset =
+        // lo8 ^ (h * HMUL), h = (hb + brev3(e)*E) & 7, where lo8 has the fold of the fixed bits applied and HMUL places h at
+        // bits LOGN-2.. and (its part of nibble 2) into the low nibble.  One packed word per (bootstrap, factor): fast path
+        // lo8 | hb << 16 | (E & 7) << 20, generic x0 | (E & 7) << 20.
+        constexpr bool fast_psi = (LOGN - 2 >= 9) && (LOGN + 1 <= 12);
+        constexpr u32 HMUL = 8u * ((1u << (LOGN - 2)) | (fast_psi ? (1u << (LOGN - 2 - 8)) : 0u));
+        u32 PK[TP][NC];
 #pragma unroll
-            for (int q = 0; q < TP; q++) {
-                const u16 *msq = (const u16 *)((const unsigned char *)s_ms + (size_t)q * ms_stride);
-                const u32 a1 = msq[2 * t], a2 = (2 * t + 1 < n) ? msq[2 * t + 1] : 0u;      // msq[n] is the body, not a mask element
-                const u32 E[3] = {a1 + a2, a1, a2};
+        for (int q = 0; q < TP; q++) {
+            const u16 *msq = (const u16 *)((const unsigned char *)s_ms + (size_t)q * ms_stride);
+            u32 ai[M];
 #pragma unroll
-                for (int c = 0; c < 3; c++) {
-                    const u32 x0 = (E[c] * odd0) & (2 * N - 1);
-                    Ec[q][c] = E[c]; eb[q][c] = x0;
-                    hb[q][c] = x0 >> (LOGN - 2);
+            for (int i = 0; i < M; i++) ai[i] = (M * t + i < n) ? msq[M * t + i] : 0u;   // msq[n] is the body, not a mask element
+#pragma unroll
+            for (int c = 0; c < NC; c++) {
+                u32 E = 0;
+#pragma unroll
+                for (int i = 0; i < M; i++) if ((fbs_unroll_mask(M, c) >> i) & 1) E += ai[i];
+                const u32 x0 = (E * odd0) & (2 * N - 1);
+                if constexpr (fast_psi) {
                     const u32 lo = x0 & ((1u << (LOGN - 2)) - 1);
-                    lo8[q][c] = 8u * (lo ^ (((lo >> 4) ^ (lo >> 8)) & 15u));       // fold of the fixed bits (bits >= LOGN-2 excluded)
-                }
+                    PK[q][c] = (8u * (lo ^ (((lo >> 4) ^ (lo >> 8)) & 15u))) | ((x0 >> (LOGN - 2)) << 16) | ((E & 7u) << 20);
+                } else PK[q][c] = x0 | ((E & 7u) << 20);
             }
-            xsync();                                                 // the partner warps' spectra are in shared memory
-            // ---- point-wise part, one key slice per element
+        }
+        xsync();                                             // the partner warps' spectra are in shared memory
 #pragma unroll
-            for (int e = 0; e < 8; e++) {
-                const u32 o = bo[0] ^ P::elem_boff(e, 0);
-                constexpr int BR3[8] = {0, 4, 2, 6, 1, 5, 3, 7};
-                mbar_wait(full + slot, par);
-                const unsigned char *ks = (const unsigned char *)(RING + (size_t)slot * C::slice_w);
-                rns2 kk[3][G];
+        for (int e = 0; e < 8; e++) {
+            const u32 o = bo[0] ^ P::elem_boff(e, 0);
+            constexpr int BR3[8] = {0, 4, 2, 6, 1, 5, 3, 7};
+            mbar_wait(full + slot, par);
+            const unsigned char *ks = (const unsigned char *)(RING + (size_t)slot * C::slice_w);
+            auto factor = [&](int q, int c) -> rns2 {        // X^{E_c} - 1 at this thread's element e
+                const u32 pk = PK[q][c];
+                if constexpr (fast_psi) {
+                    const u32 h = ((pk >> 16) + (u32)BR3[e] * (pk >> 20)) & 7u;
+                    return rns_split(*(const u64 *)((const unsigned char *)PSI + ((pk & 0xFFFFu) ^ (h * HMUL))));
+                } else {
+                    const u32 xi = ((pk & 0xFFFFu) + (((u32)BR3[e] * (pk >> 20)) << (LOGN - 2))) & (2 * N - 1);
+                    return rns_split(PSI[psw(xi)]);
+                }
+            };
+            // bundle_u = REDC(sum_c f_c * key_c[u][g]); factors outermost so that one key word (shared by the bootstraps
+            // the thread carries) and one factor are live at a time next to the 64-bit accumulators
+            u64 pa[TP][G], pb2[TP][G];
 #pragma unroll
-                for (int c = 0; c < 3; c++)
+            for (int c = 0; c < NC; c++) {
+                rns2 kk[G];
 #pragma unroll
-                    for (int og = 0; og < G; og++) kk[c][og] = rns_split(*(const u64 *)(ks + koff[og] + (size_t)c * G * G * T * 8));
+                for (int og = 0; og < G; og++) kk[og] = rns_split(*(const u64 *)(ks + koff[og] + (size_t)c * G * G * T * 8));
 #pragma unroll
                 for (int q = 0; q < TP; q++) {
-                    rns2 f[3];
-#pragma unroll
-                    for (int c = 0; c < 3; c++) {
-                        if constexpr (fast_psi) {
-                            const u32 h = (hb[q][c] + (u32)BR3[e] * Ec[q][c]) & 7u;
-                            f[c] = rns_split(*(const u64 *)((const unsigned char *)PSI + (lo8[q][c] ^ (h * HMUL))));
-                        } else {
-                            const u32 xi = (eb[q][c] + (((u32)BR3[e] * Ec[q][c]) << (LOGN - 2))) & (2 * N - 1);
-                            f[c] = rns_split(PSI[psw(xi)]);
-                        }
-                    }
-                    u64 oa = 0, ob = 0;
+                    const rns2 f = factor(q, c);
 #pragma unroll
                     for (int og = 0; og < G; og++) {
-                        u64 pa = r32_mulwide(f[0].a, kk[0][og].a), pb2 = r32_mulwide(f[0].b, kk[0][og].b);
-                        pa = r32_madwide(f[1].a, kk[1][og].a, pa); pb2 = r32_madwide(f[1].b, kk[1][og].b, pb2);
-                        pa = r32_madwide(f[2].a, kk[2][og].a, pa); pb2 = r32_madwide(f[2].b, kk[2][og].b, pb2);       // < 3 p^2
-                        const u32 ba = r32_redc(pa, FQ_P1, FQ_P1_INVNEG), bb = r32_redc(pb2, FQ_P2, FQ_P2_INVNEG);   // < 1.75 p + 1
-                        // digit spectra from shared memory, the thread's own too: keeping them in registers across the
-                        // point-wise part costs more in spills than the 8 extra loads
-                        int gg = g + og; if (gg >= G) gg -= G;
-                        const u32 xg = (og == 0) ? 0u : (G == 2) ? (1u << SH) : ((u32)(g ^ gg) << SH);
-                        const rns2 d = rns_split(*(const u64 *)(Sb + q * PWB + (o ^ xg)));
-                        if (og == 0) { oa = r32_mulwide(d.a, ba); ob = r32_mulwide(d.b, bb); }
-                        else { oa = r32_madwide(d.a, ba, oa); ob = r32_madwide(d.b, bb, ob); }                      // < G * 3.5 p^2
-                    }
-                    x[q][e].a = r32_fold(r32_redc(oa, FQ_P1, FQ_P1_INVNEG), 2 * FQ_P1);
-                    x[q][e].b = r32_fold(r32_redc(ob, FQ_P2, FQ_P2_INVNEG), 2 * FQ_P2);
+                        if (c == 0) { pa[q][og] = r32_mulwide(f.a, kk[og].a); pb2[q][og] = r32_mulwide(f.b, kk[og].b); }
+                        else { pa[q][og] = r32_madwide(f.a, kk[og].a, pa[q][og]); pb2[q][og] = r32_madwide(f.b, kk[og].b, pb2[q][og]); }
+                    }                                                                    // < NC p^2 <= 7 p^2 < 2^63
                 }
-                release_slot(e);
             }
-        } else {
-            static_assert(M == 2 || G == 2, "the M = 3 sums are sized for k = 1");
-            // Generic factor count (M = 3: seven factors).  One packed word per (bootstrap, factor): fast path
-            // lo8 | hb << 16 | (E & 7) << 20, generic x0 | (E & 7) << 20 (see the M == 2 branch for the index arithmetic).
-            constexpr bool fast_psi = (LOGN - 2 >= 9) && (LOGN + 1 <= 12);
-            constexpr u32 HMUL = 8u * ((1u << (LOGN - 2)) | (fast_psi ? (1u << (LOGN - 2 - 8)) : 0u));
-            u32 PK[TP][NC];
 #pragma unroll
             for (int q = 0; q < TP; q++) {
-                const u16 *msq = (const u16 *)((const unsigned char *)s_ms + (size_t)q * ms_stride);
-                u32 ai[M];
+                u64 oa = 0, ob = 0;
 #pragma unroll
-                for (int i = 0; i < M; i++) ai[i] = (M * t + i < n) ? msq[M * t + i] : 0u;   // msq[n] is the body, not a mask element
-#pragma unroll
-                for (int c = 0; c < NC; c++) {
-                    u32 E = 0;
-#pragma unroll
-                    for (int i = 0; i < M; i++) if ((fbs_unroll_mask(M, c) >> i) & 1) E += ai[i];
-                    const u32 x0 = (E * odd0) & (2 * N - 1);
-                    if constexpr (fast_psi) {
-                        const u32 lo = x0 & ((1u << (LOGN - 2)) - 1);
-                        PK[q][c] = (8u * (lo ^ (((lo >> 4) ^ (lo >> 8)) & 15u))) | ((x0 >> (LOGN - 2)) << 16) | ((E & 7u) << 20);
-                    } else PK[q][c] = x0 | ((E & 7u) << 20);
+                for (int og = 0; og < G; og++) {
+                    const u32 ba = r32_redc(pa[q][og], FQ_P1, FQ_P1_INVNEG), bb = r32_redc(pb2[q][og], FQ_P2, FQ_P2_INVNEG);   // < (NC/4 + 1) p + 1
+                    int gg = g + og; if (gg >= G) gg -= G;
+                    const u32 xg = (og == 0) ? 0u : (G == 2) ? (1u << SH) : ((u32)(g ^ gg) << SH);
+                    const rns2 d = rns_split(*(const u64 *)(Sb + q * PWB + (o ^ xg)));            // digit spectrum, < 2p
+                    if (og == 0) { oa = r32_mulwide(d.a, ba); ob = r32_mulwide(d.b, bb); }
+                    else { oa = r32_madwide(d.a, ba, oa); ob = r32_madwide(d.b, bb, ob); }        // < G * 2 (NC/4 + 1) p^2 < 2^64 (M = 2: G <= 3, M = 3: G = 2)
                 }
+                x[q][e].a = r32_fold(r32_redc(oa, FQ_P1, FQ_P1_INVNEG), 2 * FQ_P1);               // < 4 p before the fold
+                x[q][e].b = r32_fold(r32_redc(ob, FQ_P2, FQ_P2_INVNEG), 2 * FQ_P2);
             }
-            xsync();                                             // the partner warps' spectra are in shared memory
-#pragma unroll
-            for (int e = 0; e < 8; e++) {
-                const u32 o = bo[0] ^ P::elem_boff(e, 0);
-                constexpr int BR3[8] = {0, 4, 2, 6, 1, 5, 3, 7};
-                mbar_wait(full + slot, par);
-                const unsigned char *ks = (const unsigned char *)(RING + (size_t)slot * C::slice_w);
-                auto factor = [&](int q, int c) -> rns2 {        // X^{E_c} - 1 at this thread's element e
-                    const u32 pk = PK[q][c];
-                    if constexpr (fast_psi) {
-                        const u32 h = ((pk >> 16) + (u32)BR3[e] * (pk >> 20)) & 7u;
-                        return rns_split(*(const u64 *)((const unsigned char *)PSI + ((pk & 0xFFFFu) ^ (h * HMUL))));
-                    } else {
-                        const u32 xi = ((pk & 0xFFFFu) + (((u32)BR3[e] * (pk >> 20)) << (LOGN - 2))) & (2 * N - 1);
-                        return rns_split(PSI[psw(xi)]);
-                    }
-                };
-                // bundle_u = REDC(sum_c f_c * key_c[u][g]); factors outermost so that one key word (shared by the bootstraps
-                // the thread carries) and one factor are live at a time next to the 64-bit accumulators
-                u64 pa[TP][G], pb2[TP][G];
-#pragma unroll
-                for (int c = 0; c < NC; c++) {
-                    rns2 kk[G];
-#pragma unroll
-                    for (int og = 0; og < G; og++) kk[og] = rns_split(*(const u64 *)(ks + koff[og] + (size_t)c * G * G * T * 8));
-#pragma unroll
-                    for (int q = 0; q < TP; q++) {
-                        const rns2 f = factor(q, c);
-#pragma unroll
-                        for (int og = 0; og < G; og++) {
-                            if (c == 0) { pa[q][og] = r32_mulwide(f.a, kk[og].a); pb2[q][og] = r32_mulwide(f.b, kk[og].b); }
-                            else { pa[q][og] = r32_madwide(f.a, kk[og].a, pa[q][og]); pb2[q][og] = r32_madwide(f.b, kk[og].b, pb2[q][og]); }
-                        }                                                                    // < NC p^2 <= 7 p^2 < 2^63
-                    }
-                }
-#pragma unroll
-                for (int q = 0; q < TP; q++) {
-                    u64 oa = 0, ob = 0;
-#pragma unroll
-                    for (int og = 0; og < G; og++) {
-                        const u32 ba = r32_redc(pa[q][og], FQ_P1, FQ_P1_INVNEG), bb = r32_redc(pb2[q][og], FQ_P2, FQ_P2_INVNEG);   // < 2.75 p + 1
-                        int gg = g + og; if (gg >= G) gg -= G;
-                        const u32 xg = (og == 0) ? 0u : (G == 2) ? (1u << SH) : ((u32)(g ^ gg) << SH);
-                        const rns2 d = rns_split(*(const u64 *)(Sb + q * PWB + (o ^ xg)));            // digit spectrum, < 2p
-                        if (og == 0) { oa = r32_mulwide(d.a, ba); ob = r32_mulwide(d.b, bb); }
-                        else { oa = r32_madwide(d.a, ba, oa); ob = r32_madwide(d.b, bb, ob); }        // < G * 5.5 p^2 < 2^64 (G <= 2)
-                    }
-                    x[q][e].a = r32_fold(r32_redc(oa, FQ_P1, FQ_P1_INVNEG), 2 * FQ_P1);               // < 3.75 p before the fold
-                    x[q][e].b = r32_fold(r32_redc(ob, FQ_P2, FQ_P2_INVNEG), 2 * FQ_P2);
-                }
-                release_slot(e);
-            }
+            release_slot(e);
         }
         auto after_pass0 = [&] { xsync(); };                     // the partner warps have read this step's digit spectra
         ntt_inv1_from<LOGN, 0, TP, decltype(after_pass0), decltype(gsync), C::TWS>(x, tau, Sb, PWB, bo, twp, after_pass0, gsync, a.zero);
