@@ -746,16 +746,19 @@ __global__ void __launch_bounds__((PB / TP) * (K + 1) * (1 << LOGN) / 8, 1) k_bl
 }
 
 // ------------------------------------------------------------------------------------------------------
-// K2u: blind rotation with TWO key bits per step (key unrolling, params bsk_unroll = 2; L = 1).
-//   X^(a1 s1 + a2 s2) - 1 = (X^(a1+a2) - 1) s1 s2 + (X^a1 - 1) s1 (1 - s2) + (X^a2 - 1) (1 - s1) s2, so with GGSW ciphertexts
-//   G_0, G_1, G_2 of the three bit products:   ACC <- ACC + Dec(ACC) [x] ( sum_c (X^{e_c} - 1) G_c ),   e = (a1+a2, a1, a2).
-// One decomposition and one forward / inverse transform pair serve two key bits; the monomial factors are applied to the
+// K2u: blind rotation with M = 2 or 3 key bits per step (key unrolling, params bsk_unroll = M; L = 1).
+//   For key group t and every non-empty subset T of its M bits: e_T = sum_{i in T} a_i and the indicator bit
+//   m_T = prod_{i in T} s_i * prod_{i not in T} (1 - s_i).  Then X^(sum_i a_i s_i) - 1 = sum_T (X^{e_T} - 1) m_T, so with GGSW
+//   ciphertexts G_T of the 2^M - 1 indicator bits:   ACC <- ACC + Dec(ACC) [x] ( sum_T (X^{e_T} - 1) G_T ).
+//   (M = 2:  X^(a1 s1 + a2 s2) - 1 = (X^(a1+a2) - 1) s1 s2 + (X^a1 - 1) s1 (1 - s2) + (X^a2 - 1) (1 - s1) s2.)
+// One decomposition and one forward / inverse transform pair serve M key bits; the monomial factors are applied to the
 // KEY in the NTT domain, where X^e is the point-wise multiplication by psi^(e * (2 brev(i) + 1)) (table psi_pow), so the
 // accumulator is decomposed as it is: no rotated reads, ACC lives in registers for the whole blind rotation and shared
-// memory only holds the transpose scratch (32 KB per bootstrap at set A2).  Per coefficient and prime the point-wise part is
-//   bundle_u = REDC( sum_c f_c * key_c[u][g] ),  out_g = REDC( sum_u D_u * bundle_u )       (key in Montgomery form twice)
-// i.e. 8 products + 3 reductions against 2 x (2 + 1) for two classic steps, against a whole saved step of transforms.
-// The key (1.5 x the classic one, half as many steps) is streamed by TMA in per-element slices through a shared-memory ring
+// memory only holds the transpose scratch (32 KB per bootstrap at N = 2048, k = 1).  Per coefficient and prime the
+// point-wise part is
+//   bundle_u = REDC( sum_T f_T * key_T[u][g] ),  out_g = REDC( sum_u D_u * bundle_u )       (key in Montgomery form twice)
+// i.e. 2 (2^M - 1) + 2 products and 3 reductions for M key bits, against a whole saved step of transforms per extra bit.
+// The key ((2^M - 1) / M x the classic one) is streamed by TMA in per-element slices through a shared-memory ring
 // (BR2Cfg, full/empty mbarriers); a key word is read from shared memory once per thread and used for every bootstrap the
 // thread carries.  The table psi_pow (psi^x - 1) sits in shared memory too, index nibble XOR-folded against bank conflicts.
 // ------------------------------------------------------------------------------------------------------
