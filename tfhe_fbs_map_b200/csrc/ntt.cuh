@@ -23,9 +23,11 @@ struct NttPlan {
     // forward pass p covers index bits hi = LOGN-1-3p down to max(hi-2, 0)
     FQ_HDM static constexpr int fwd_hi(int p) { return LOGN - 1 - 3 * p; }
     FQ_HDM static constexpr int fwd_lb(int p) { return fwd_hi(p) - 2 > 0 ? fwd_hi(p) - 2 : 0; }
-    // inverse pass p covers index bits lo = 3p up to min(lo+2, LOGN-1)
-    FQ_HDM static constexpr int inv_lo(int p) { return 3 * p; }
-    FQ_HDM static constexpr int inv_lb(int p) { return 3 * p < LOGN - 3 ? 3 * p : LOGN - 3; }
+    // inverse pass p holds index bits lb..lb+2 in registers and processes those not done yet (bits >= inv_lo(p)).  The layouts
+    // mirror the forward ones (0, 3, .., LOGN-6, LOGN-3): the short pass comes second to last, so that the three highest
+    // index bits stay the WARP bits until the last transpose and only that one crosses warps.
+    FQ_HDM static constexpr int inv_lb(int p) { return p == NPASS - 1 ? LOGN - 3 : (3 * p < LOGN - 6 ? 3 * p : (LOGN - 6 > 0 ? LOGN - 6 : 0)); }
+    FQ_HDM static constexpr int inv_lo(int p) { return p == 0 ? 0 : inv_lb(p - 1) + 3; }
     // bank-conflict-free XOR swizzle of the low 4 index bits (tools/swizzle_search.py):
     // 4-bit columns added for index bits 4, 5, 6
     FQ_HDM static constexpr int sw_c0() { return (LOGN % 3 == 2) ? 1 : (LOGN % 3 == 0) ? 1 : 2; }
