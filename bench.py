@@ -360,8 +360,8 @@ def main():
             evals_per_s=world * B * args.steps / (ms_res * 1e-3), mismatches=mism_res,
             phase_ms_per_step=dict(lincomb=st.ms_lincomb / args.steps, keyswitch=st.ms_keyswitch / args.steps, blind_rotate=st.ms_blind_rotate / args.steps),
             roofline=dict(bound="hbm", achieved=achieved, peak=peaks.get("hbm_gbs"), unit="GB/s", frac=achieved / peaks.get("hbm_gbs"),
-                          traffic={3: 238.00e6, 2: 154.63e6}.get(ps.bsk_unroll, 61.95e6) / 1e9,
-                          traffic_note="GB per launch: dram__bytes_read+write of a 592-PBS launch (two waves), profiles/" + ("r1_v12_hot_kernels_summary.txt; the key-unrolled BSK (114 MB at 3 bits per step) does not stay L2-resident between waves and is re-read from HBM once per wave" if ps.bsk_unroll > 1 else "r1_v5_hot_kernels_summary.txt"),
+                          traffic={3: 238.35e6, 2: 154.63e6}.get(ps.bsk_unroll, 61.95e6) / 1e9,
+                          traffic_note="GB per launch: dram__bytes_read+write of a 592-PBS launch (two waves), profiles/" + ("r1_v13_hot_kernels_summary.txt; the key-unrolled BSK (114 MB at 3 bits per step) does not stay L2-resident between waves and is re-read from HBM once per wave" if ps.bsk_unroll > 1 else "r1_v5_hot_kernels_summary.txt"),
                           kernel="k_blind_rotate2" if ps.bsk_unroll > 1 else "k_blind_rotate", launch_ms=br_ms_avg, peak_source=peak_kind,
                           note="kernel is integer-issue bound by design (accumulator on chip, keys L2-resident); see roofline_int"),
             roofline_int=dict(bound="int32-multiply", achieved=mul32 / 1e12, peak=int_peak / 1e12, unit="T mul32/s", frac=mul32 / int_peak,
