@@ -36,7 +36,7 @@ typedef struct fbs_params {
     int32_t bsk_beta;   /* log2 blind-rotate base                      */
     int32_t ks_l;       /* key-switch levels                           */
     int32_t ks_beta;    /* log2 key-switch base (<= 8)                 */
-    int32_t bsk_unroll; /* 0/1: one key bit per blind-rotation step; 2: two (three GGSW per key pair, bsk_l = 1) */
+    int32_t bsk_unroll; /* key bits per blind-rotation step: 0/1 classic; 2 or 3: 2^m - 1 GGSW per key group, bsk_l = 1 */
     uint64_t lwe_noise; /* round(sigma_lwe  * Q)                       */
     uint64_t glwe_noise;/* round(sigma_glwe * Q)                       */
 } fbs_params;
@@ -51,7 +51,9 @@ typedef struct fbs_params {
  */
 typedef struct fbs_prog_desc {
     int32_t p;            /* plaintext modulus = --fbs_size (reference map_circuit.py:98)           */
-    int32_t n_inputs, n_lincombs, n_boots, n_levels, n_slots, n_outputs, reserved;
+    int32_t n_inputs, n_lincombs, n_boots, n_levels, n_slots, n_outputs;
+    int32_t contiguous_levels;    /* != 0: slots are never recycled (levelize reuse_slots=False / shard_pad): fbs_run_level accepts node
+                                     sub-ranges; without it a sub-range would corrupt recycled slots and is refused */
     const int32_t *lc_level_ptr;  /* [n_levels+1]                                                 */
     const int32_t *bs_level_ptr;  /* [n_levels+1]                                                 */
     const int32_t *lc_ptr;        /* [n_lincombs+1] CSR row pointers                              */
@@ -86,6 +88,10 @@ int fbs_abi_version(void);
 int fbs_ctx_create(const fbs_params *params, int device, uint64_t seed, fbs_ctx **out);
 int fbs_keygen(fbs_ctx *ctx);                 /* seeded, deterministic: identical on every rank/device */
 int fbs_ctx_destroy(fbs_ctx *ctx);
+/* Blind-rotation kernel choice for launches with fewer jobs than SMs: 0 = auto (split each bootstrap over a thread-block
+ * cluster of up to 8 CTAs when that still fits one wave), 1 = never, 2 / 4 / 8 = always that cluster size (tests, sweeps).
+ * All choices produce bit-identical ciphertexts. */
+int fbs_ctx_set_cluster(fbs_ctx *ctx, int32_t mode);
 int fbs_ctx_info(const fbs_ctx *ctx, int32_t *sm_count, int64_t *bsk_bytes, int64_t *ksk_bytes, int32_t *br_smem_bytes);
 
 /* ---- program ------------------------------------------------------------------------------------- */
@@ -105,28 +111,40 @@ int fbs_eval_bits(fbs_ctx *ctx, fbs_prog *prog, const uint8_t *in, int64_t B, in
 int fbs_wires_bytes(const fbs_ctx *ctx, const fbs_prog *prog, int64_t B, size_t *bytes);
 int fbs_encrypt_inputs(fbs_ctx *ctx, fbs_prog *prog, const uint8_t *in_dev, int64_t B, int64_t inst_offset,
                        int64_t B_total, uint64_t enc_seed, uint64_t *wires_dev, void *stream);
-/* runs bootstraps [node_begin, node_end) of level `level` (indices relative to the level; -1,-1 = all) */
+/* runs bootstraps [node_begin, node_end) of level `level` (indices relative to the level; -1,-1 = all).  A proper
+ * sub-range needs a program with contiguous_levels != 0 (recycled slots would be corrupted otherwise: refused). */
 int fbs_run_level(fbs_ctx *ctx, fbs_prog *prog, int32_t level, int32_t node_begin, int32_t node_end, int64_t B,
                   uint64_t *wires_dev, void *stream, fbs_run_stats *stats);
 int fbs_run(fbs_ctx *ctx, fbs_prog *prog, int64_t B, uint64_t *wires_dev, void *stream, fbs_run_stats *stats);
 int fbs_decrypt_outputs(fbs_ctx *ctx, fbs_prog *prog, int64_t B, const uint64_t *wires_dev, uint8_t *out_dev, void *stream);
 
 /* ---- fused exchange for node-sharded levels (BASELINE.json configs[3]) ---------------------------------
- * Every rank keeps a replica of the wire buffer.  After fbs_set_peers, the sample-extract epilogue of the blind-rotation
- * kernel stores each output ciphertext into the local buffer AND into every peer replica (NVLink peer stores), which
- * replaces the per-level all-gather; the caller only barriers between levels.  Buffers come from fbs_wires_alloc and
- * travel between processes as CUDA IPC handles (64 opaque bytes). */
+ * Every rank keeps a replica of the wire buffer (reference semantics: the level loop of fbs_exec_env.py:208-229 with the
+ * bootstraps of a level split across GPUs).  Buffers come from fbs_wires_alloc (payload + one flag page) and travel between
+ * processes as CUDA IPC handles (64 opaque bytes).  fbs_set_peers BINDS the peer replicas to one local buffer: when
+ * fbs_run_level runs on exactly that buffer, (1) the sample-extract epilogue of the blind-rotation kernel stores each
+ * output ciphertext into the local buffer AND into every peer replica (NVLink peer stores; replaces the per-level
+ * all-gather), and (2) levels are ordered ON THE DEVICE: after a level every rank publishes an epoch into the peers' flag
+ * pages (system-scope release) and the next level's first kernel waits for all of them (bounded spin) -- no host
+ * synchronisation between levels.  Every rank must call fbs_run_level for every level, in the same order (empty node
+ * ranges included), and barrier once on the host after fbs_set_peers / after (re-)encrypting inputs.  Any other wires
+ * pointer (fbs_eval_bits, fbs_pbs_batch, parity taps) never touches the peers.  rank = this process's index among the
+ * n_peers + 1 participants (rank < 0: peer stores only, the caller orders the levels itself, e.g. with a host barrier);
+ * n_peers = 0 unbinds.  fbs_sync_status reports a peer that never arrived (0 = none, else 1 + rank). */
 int fbs_wires_alloc(fbs_ctx *ctx, size_t bytes, uint64_t **out);
 int fbs_wires_free(fbs_ctx *ctx, uint64_t *wires_dev);
 int fbs_ipc_export(fbs_ctx *ctx, const uint64_t *wires_dev, unsigned char handle[64]);
 int fbs_ipc_import(fbs_ctx *ctx, const unsigned char handle[64], uint64_t **peer_wires);
 int fbs_ipc_close(fbs_ctx *ctx, uint64_t *peer_wires);
-int fbs_set_peers(fbs_ctx *ctx, uint64_t *const *peer_wires, int32_t n_peers);   /* n_peers = 0 switches it off */
+int fbs_set_peers(fbs_ctx *ctx, uint64_t *wires_local, size_t wires_bytes, uint64_t *const *peer_wires, int32_t n_peers, int32_t rank);
+/* enqueue a wait until every rank has completed all levels issued so far (end of a run, before decrypting) */
+int fbs_level_sync(fbs_ctx *ctx, uint64_t *wires_local, void *stream);
+int fbs_sync_status(fbs_ctx *ctx, int32_t *timed_out);
 
 /* ---- PBS micro-benchmark (BASELINE.json configs[4]) -------------------------------------------------
- * count independent bootstraps: encrypt msgs[i] in Z_2p, bootstrap with tables[i*2p .. i*2p+tlen[i]),
- * decrypt into out[i].  Host buffers.  `resident` != 0 keeps ciphertexts on the device across the timed
- * part so stats->ms_* cover key-switch + blind rotation only. */
+ * count independent bootstraps: encrypt msgs[i] in Z_2p, bootstrap with tables[i*2p .. i*2p+tlen[i]) (modes[i] = table
+ * mode s, NULL = 1), decrypt into out[i].  Host buffers; stats->ms_lincomb / ms_keyswitch / ms_blind_rotate cover the
+ * bootstrap proper (device time, CUDA events), encryption / decryption / copies are outside them. */
 int fbs_pbs_batch(fbs_ctx *ctx, int32_t p, const uint8_t *msgs, const uint8_t *tables, const uint8_t *tlen,
                   const int32_t *modes, int64_t count, uint64_t enc_seed, uint8_t *out, fbs_run_stats *stats);
 

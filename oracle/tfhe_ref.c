@@ -461,6 +461,21 @@ void ref_pbs(const ref_ctx *c, int p, const u64 *in, const u8 *table, int L, int
     free(ks); free(ms); free(tv); free(acc);
 }
 
+/* `count` independent bootstraps (one ref_pbs each, OpenMP over the batch): the checker of the full-size batched parity
+ * tests.  tables [count][tab_stride], out [count][kN+1], tap_acc [count][(k+1)N] or NULL. */
+void ref_pbs_batch(const ref_ctx *c, int p, const u64 *in, const u8 *tables, int tab_stride, const u8 *tlen, const int32_t *modes,
+                   int64_t count, u64 *out, u64 *tap_acc, int threads)
+{
+    size_t CT = (size_t)c->P.k * c->P.N + 1, AW = (size_t)(c->P.k + 1) * c->P.N;
+#ifdef _OPENMP
+    if (threads > 0) omp_set_num_threads(threads);
+#endif
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int64_t i = 0; i < count; i++)
+        ref_pbs(c, p, in + (size_t)i * CT, tables + (size_t)i * tab_stride, tlen[i], modes ? modes[i] : 1, out + (size_t)i * CT,
+                NULL, NULL, tap_acc ? tap_acc + (size_t)i * AW : NULL);
+}
+
 /* ---------------- levelised program (same flat descriptor as include/fbs_b200.h) ---------------- */
 typedef struct {
     int32_t p, n_inputs, n_lincombs, n_boots, n_levels, n_slots, n_outputs, reserved;

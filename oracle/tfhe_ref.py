@@ -68,6 +68,7 @@ def lib():
         L.ref_blind_rotate.argtypes = [vp, vp, vp, vp]
         L.ref_sample_extract.argtypes = [vp, vp, u64, vp]
         L.ref_pbs.argtypes = [vp, i32, vp, vp, i32, i32, vp, vp, vp, vp]
+        L.ref_pbs_batch.argtypes = [vp, i32, vp, vp, i32, vp, vp, i64, vp, vp, i32]
         L.ref_ntt_fwd.argtypes = [vp, vp]
         L.ref_ntt_inv.argtypes = [vp, vp]
         L.ref_polymul_schoolbook.argtypes = [i32, vp, vp, vp]
@@ -172,6 +173,20 @@ class RefTFHE:
         acc = np.zeros((ps.k + 1, ps.N), np.uint64)
         self.L.ref_pbs(self.ctx, p, _p(ct), _p(tab), len(tab), mode, _p(out), _p(ks), _p(ms), _p(acc))
         return out, ks, ms, acc
+
+    def pbs_batch(self, p, cts, tables, tlens, modes=None, want_acc=True, threads=0):
+        """count independent bootstraps on all host threads: (out [count][kN+1], acc [count][k+1][N] or None)."""
+        ps = self.ps
+        cts = np.ascontiguousarray(cts, np.uint64)
+        tables = np.ascontiguousarray(tables, np.uint8)
+        tlens = np.ascontiguousarray(tlens, np.uint8)
+        modes_a = None if modes is None else np.ascontiguousarray(modes, np.int32)
+        count = cts.shape[0]
+        out = np.zeros((count, self.ct_words), np.uint64)
+        acc = np.zeros((count, ps.k + 1, ps.N), np.uint64) if want_acc else None
+        self.L.ref_pbs_batch(self.ctx, p, _p(cts), _p(tables), tables.shape[1], _p(tlens), None if modes_a is None else _p(modes_a),
+                             count, _p(out), None if acc is None else _p(acc), threads)
+        return out, acc
 
     def eval_prog(self, program, in_bits, inst_offset=0, total=None, enc_seed=0, threads=0):
         """program: tfhe_fbs_map_b200.levelize.Program (only its flat arrays are used)."""

@@ -56,7 +56,11 @@ def lbf_index():
 
 
 def read_golden_lbf(fn):
-    from tfhe_fbs_map_b200.formats import read_lbf_file
+    from tfhe_fbs_map_b200.formats import read_lbf, read_lbf_file
+    if fn.endswith(".gz"):
+        import gzip
+        with gzip.open(os.path.join(GOLD, "lbf", fn), "rt") as f:
+            return read_lbf(f.read())
     return read_lbf_file(os.path.join(GOLD, "lbf", fn))
 
 

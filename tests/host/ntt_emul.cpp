@@ -128,6 +128,72 @@ template <int LOGN> int run() {
     printf("LOGN=%d bad=%d\n", LOGN, bad);
     return bad;
 }
+// ---- cluster-split transform (ntt.cuh: ntt_cross_fwd / ntt_cross_inv + local tables), as k_blind_rotate_cl runs it:
+// CTA loops play the cluster, the inbox arrays play the distributed-shared-memory exchange
+template <int LOGNS, int PASS, bool INV> void emu_local(const std::vector<fq_tw> &tw, std::vector<u64> &arr) {
+    using P = NttPlan<LOGNS>;
+    if constexpr (PASS < P::NPASS) {
+        std::vector<u64> sm(P::N);
+        const int lb = INV ? P::inv_lb(PASS) : P::fwd_lb(PASS);
+        for (int tau = 0; tau < P::T; tau++) {
+            rns2 x[1][8];
+            for (int e = 0; e < 8; e++) x[0][e] = rns_unpack(arr[P::idx(tau, e, lb)]);
+            if (INV) ntt_inv_pass_n<LOGNS, PASS, 1, true>(x, tau, tw.data()); else ntt_fwd_pass_n<LOGNS, PASS, 1>(x, tau, tw.data());
+            for (int e = 0; e < 8; e++) sm[P::swz(P::idx(tau, e, lb))] = rns_pack(x[0][e]);
+        }
+        for (int i = 0; i < P::N; i++) arr[i] = sm[P::swz(i)];
+        emu_local<LOGNS, PASS + 1, INV>(tw, arr);
+    }
+}
+template <int LOGN, int LOGC> int run_cluster() {
+    constexpr int N = 1 << LOGN, C = 1 << LOGC, LOGNS = LOGN - LOGC, Ns = N / C, Ts = Ns / 8, R = 8 / C;
+    Tables<LOGN> t; int bad = 0;
+    std::vector<u64> a(N), lazy(N);
+    for (int i = 0; i < N; i++) { a[i] = fbs_rnd_uniform(52 + LOGN, 9 + LOGC, i); rns2 v = rns_from_int(a[i]); v.a += (i % 2) * FQ_P1; v.b += ((i + 1) % 2) * FQ_P2; lazy[i] = rns_pack(v); }  // digits: < 2p
+    std::vector<u64> full = lazy;
+    emu_fwd<LOGN, 0>(t, full);                                           // the one-CTA transform is the reference here
+    // forward: cross stages on registers, exchange, local passes with the local table
+    std::vector<std::vector<u64>> inbox(C, std::vector<u64>(8 * Ts));
+    for (int c = 0; c < C; c++) for (int tau = 0; tau < Ts; tau++) {
+        rns2 x[8];
+        for (int h = 0; h < C; h++) for (int ri = 0; ri < R; ri++) x[h * R + ri] = rns_unpack(lazy[h * Ns + c * (Ns / C) + ri * Ts + tau]);
+        ntt_cross_fwd<LOGC>(x, t.psi_rev.data());
+        for (int h = 0; h < C; h++) for (int ri = 0; ri < R; ri++) inbox[h][(c * R + ri) * Ts + tau] = rns_pack(x[h * R + ri]);
+    }
+    std::vector<std::vector<u64>> spec(C);
+    for (int h = 0; h < C; h++) {
+        std::vector<fq_tw> twf(Ns);
+        for (int i = 1; i < Ns; i++) twf[i] = t.psi_rev[ntt_local_src(i, C + h)];
+        std::vector<u64> arr(Ns);
+        for (int tau = 0; tau < Ts; tau++) for (int e = 0; e < 8; e++) arr[tau + e * Ts] = inbox[h][e * Ts + tau];
+        emu_local<LOGNS, 0, false>(twf, arr);
+        for (int i = 0; i < Ns; i++) { rns2 v = rns_unpack(arr[i]), w = rns_unpack(full[h * Ns + i]);
+            if (v.a >= 4ULL * FQ_P1 || v.b >= 4ULL * FQ_P2 || v.a % FQ_P1 != w.a % FQ_P1 || v.b % FQ_P2 != w.b % FQ_P2) bad++; }
+        spec[h] = arr;
+    }
+    // inverse: local mirrored passes, exchange, cross stages; against the textbook inverse (unscaled) of the canonical spectrum
+    std::vector<u64> sp2(N);
+    for (int i = 0; i < N; i++) { rns2 v = canon4(rns_unpack(full[i])); v.a += (i & 1) * FQ_P1; v.b += ((i >> 1) & 1) * FQ_P2; sp2[i] = rns_pack(v); }
+    std::vector<std::vector<u64>> inbox2(C, std::vector<u64>(8 * Ts));
+    for (int h = 0; h < C; h++) {
+        std::vector<fq_tw> twi(Ns);
+        for (int i = 1; i < Ns; i++) twi[i] = t.psi_rev[ntt_local_src(i, 2 * C - 1 - h)];
+        std::vector<u64> arr(sp2.begin() + h * Ns, sp2.begin() + (h + 1) * Ns);
+        emu_local<LOGNS, 0, true>(twi, arr);
+        for (int tau = 0; tau < Ts; tau++) for (int e = 0; e < 8; e++) inbox2[e / R][(h * R + e % R) * Ts + tau] = arr[tau + e * Ts];
+    }
+    std::vector<u64> back(N);
+    for (int c = 0; c < C; c++) for (int tau = 0; tau < Ts; tau++) {
+        rns2 x[8];
+        for (int e = 0; e < 8; e++) x[e] = rns_unpack(inbox2[c][e * Ts + tau]);
+        ntt_cross_inv<LOGC>(x, t.psi_rev.data());
+        for (int h = 0; h < C; h++) for (int ri = 0; ri < R; ri++) back[h * Ns + c * (Ns / C) + ri * Ts + tau] = rns_pack(x[h * R + ri]);
+    }
+    for (int i = 0; i < N; i++) { rns2 v = rns_unpack(back[i]); if (v.a >= 2 * FQ_P1 || v.b >= 2 * FQ_P2) bad++;
+        if (mulp(v.a % FQ_P1, t.ninv[0], FQ_P1) != a[i] % FQ_P1 || mulp(v.b % FQ_P2, t.ninv[1], FQ_P2) != a[i] % FQ_P2) bad++; }
+    printf("cluster LOGN=%d C=%d bad=%d\n", LOGN, C, bad);
+    return bad;
+}
 int main() {
     int bad = 0;
     if ((u128)FQ_P1 * FQ_P2 != FQ_Q) bad++;
@@ -190,5 +256,6 @@ int main() {
     }
     printf("field bad=%d\n", bad);
     bad += run<8>(); bad += run<9>(); bad += run<10>(); bad += run<11>(); bad += run<12>();
+    bad += run_cluster<11, 1>(); bad += run_cluster<11, 2>(); bad += run_cluster<11, 3>(); bad += run_cluster<10, 1>(); bad += run_cluster<10, 2>(); bad += run_cluster<9, 1>();
     return bad ? 1 : 0;
 }

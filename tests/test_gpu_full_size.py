@@ -90,3 +90,29 @@ def test_blind_rotation_is_deterministic_under_load(be):
         for a, b in zip(runs[0], r):
             assert np.array_equal(a, b)
     assert np.array_equal(be.debug_decrypt(p, runs[0][0]), tables[np.arange(count), msgs])
+
+
+def test_640_pbs_bit_exact_against_cpu_oracle(be):
+    """Default set A3 at full size, batched: 640 bootstraps = two full waves of the two-bootstraps-per-CTA kernel
+    (k_blind_rotate2<11,1,2,2,3>) plus a 48-job tail on the one-bootstrap-per-CTA instantiation (<11,1,1,1,3>); every
+    accumulator and every extracted ciphertext must equal the C oracle's bit for bit."""
+    if be.params.name != "A3":
+        pytest.skip("batched full-size ciphertext parity runs on the default set only (CPU oracle time)")
+    ref = RefTFHE(be.params, seed=20241018)
+    p, count = 15, 640
+    rng = np.random.default_rng(21)
+    msgs = rng.integers(0, 2 * p, count).astype(np.int32)
+    low = rng.integers(0, 2, (count, p)).astype(np.uint8)
+    tables = np.concatenate([low, 1 - low], axis=1)
+    cts = be.debug_encrypt(p, msgs, np.arange(count, dtype=np.uint64) + 5, enc_seed=8)
+    assert np.array_equal(cts, ref.encrypt(p, msgs, np.arange(count, dtype=np.uint64) + 5, 8))
+    lens, modes = np.full(count, 2 * p, np.uint8), np.ones(count, np.int32)
+    be.set_cluster(1)                                  # this test is about the two one-CTA instantiations
+    try:
+        out, ks, ms, acc = be.debug_pbs(p, cts, tables, lens, modes)
+    finally:
+        be.set_cluster(0)
+    rout, racc = ref.pbs_batch(p, cts, tables, lens, modes)
+    bad = [i for i in range(count) if not (np.array_equal(acc[i], racc[i]) and np.array_equal(out[i], rout[i]))]
+    assert not bad, f"{len(bad)} of {count} bootstraps differ from the CPU oracle, first {bad[:5]}"
+    assert np.array_equal(be.debug_decrypt(p, out), tables[np.arange(count), msgs])

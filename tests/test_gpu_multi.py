@@ -1,0 +1,33 @@
+"""Real multi-rank GPU parity of the node-sharded path (BASELINE.json configs[3]): one process per
+GPU under torchrun, fused peer-store exchange (device-side and host hand-off) and NCCL all-gather, each rank's replica of
+the wire buffer bit-identical to the one-GPU wire buffer.  Skipped unless the box has at least two GPUs."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _ngpu():
+    try:
+        import torch
+        return torch.cuda.device_count()
+    except Exception:
+        return 0
+
+
+@pytest.mark.parametrize("param_set,lbf,p,batch", [("toy3", "aes_sbox_p11.lbf", 11, 4), ("A3", "mult8_p17.lbf", 17, 2)])
+def test_node_sharded_exchanges_bit_identical_to_one_gpu(param_set, lbf, p, batch):
+    n = _ngpu()
+    if n < 2:
+        pytest.skip("needs at least two GPUs")
+    world = 2 if n < 4 else 4
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
+           "--master-port", "29671", os.path.join(ROOT, "tests", "multi_gpu_worker.py"), "--param-set", param_set, "--lbf", lbf,
+           "--p", str(p), "--batch", str(batch)]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert r.stdout.count("MULTI_OK") == world, r.stdout[-3000:]

@@ -105,6 +105,7 @@ def test_program_equals_oracle_and_cleartext(ctxs, circuit, p, toy):
     inputs = selfcheck_inputs(e["input_names"])
     bits = np.array([inputs[nm][:B] for nm in prog.input_names], dtype=np.uint8)
     got = be.eval_bits(cp, bits)
+    seed0 = be.last_enc_seed                     # every encrypting call draws a fresh seed
     want = unpack_outputs(e, batch=B)
     for nm in prog.output_names:
         assert np.array_equal(got[prog.out_index[nm]], want[str(nm)]), nm
@@ -113,7 +114,7 @@ def test_program_equals_oracle_and_cleartext(ctxs, circuit, p, toy):
     got2 = be.eval_bits(cp, bits, max_wire_bytes=16 * (prog.n_slots * CT + 64 * 1024))
     assert np.array_equal(got, got2)
     if B * prog.n_boots <= 400:
-        r = ref.eval_prog(prog, bits[:, :6].copy(), enc_seed=be.enc_seed, total=B)
+        r = ref.eval_prog(prog, bits[:, :6].copy(), enc_seed=seed0, total=B)
         assert np.array_equal(r, got[:, :6])
 
 
@@ -180,16 +181,28 @@ def test_fused_peer_store_epilogue_single_gpu(ctxs):
     cp = be.load(prog)
     B = 8
     nbytes = be.wires_bytes(cp, B)
-    main_buf, p1, p2 = be.wires_alloc(nbytes), be.wires_alloc(nbytes), be.wires_alloc(nbytes)
+    main_buf, p1, p2, other = (be.wires_alloc(nbytes) for _ in range(4))
     try:
         inputs = selfcheck_inputs(e["input_names"])
         bits = np.array([inputs[nm][:B] for nm in prog.input_names], dtype=np.uint8)
         d_in = torch.from_numpy(bits).cuda()
-        for buf in (main_buf, p1, p2):                      # replicas start from the same encrypted inputs
-            be.encrypt_inputs(cp, d_in.data_ptr(), B, buf)
-        be.set_peers([p1, p2])
+        for buf in (main_buf, p1, p2, other):               # replicas start from the same encrypted inputs
+            be.encrypt_inputs(cp, d_in.data_ptr(), B, buf, enc_seed=5)
+        # rank < 0: peer stores only (no device-side flags: the "peers" here are not running anything)
+        be.set_peers(main_buf, nbytes, [p1, p2], -1)
+        # the binding belongs to main_buf ONLY: a run on any other buffer (fbs_eval_bits / fbs_pbs_batch use internal ones)
+        # must not write into the peers
+        snap = torch.empty(nbytes // 8, dtype=torch.int64, device="cuda")
+        cudart = ctypes.CDLL("libcudart.so")
+        cudart.cudaMemcpy(ctypes.c_void_p(snap.data_ptr()), ctypes.c_void_p(p1), ctypes.c_size_t(nbytes), 3)
+        be.run(cp, B, other)
+        be.pbs_batch(5, np.arange(4, dtype=np.uint8), np.tile(np.array([0, 1, 1, 0, 1, 0, 0, 0, 0, 0], np.uint8), (4, 1)), np.full(4, 5, np.uint8))
+        torch.cuda.synchronize()
+        after = torch.empty_like(snap)
+        cudart.cudaMemcpy(ctypes.c_void_p(after.data_ptr()), ctypes.c_void_p(p1), ctypes.c_size_t(nbytes), 3)
+        assert torch.equal(snap, after), "a level on an unregistered buffer stored into the peers"
         be.run(cp, B, main_buf)
-        be.set_peers([])
+        be.set_peers(None, 0, [], 0)
         torch.cuda.synchronize()
         words = nbytes // 8
         host = []
@@ -208,8 +221,71 @@ def test_fused_peer_store_epilogue_single_gpu(ctxs):
         for nm in prog.output_names:
             assert np.array_equal(d_out.cpu().numpy()[prog.out_index[nm]], want[str(nm)]), nm
     finally:
-        for buf in (main_buf, p1, p2):
+        be.set_peers(None, 0, [], 0)
+        for buf in (main_buf, p1, p2, other):
             be.wires_free(buf)
+
+
+def test_device_side_level_handoff_two_ranks_one_gpu():
+    """Node-sharded levels with the fused peer-store exchange AND the device-side level hand-off (per-level epoch flags,
+    no host synchronisation between levels), with both "ranks" living on this one GPU: two backends (same seeded keys), two
+    streams, each rank's peer is the other rank's wire buffer.  All levels of both ranks are enqueued without any host
+    sync; the result must be bit-identical to a plain one-rank run on the same encrypted inputs."""
+    import ctypes
+    import torch
+    from tfhe_fbs_map_b200.backend import B200Backend
+    from tfhe_fbs_map_b200.dist import level_node_range
+    e = next(x for x in load_ref_mapped() if x["circuit"] == "aes_sbox" and x["p"] == 11 and x["mapper"] == "search" and not x.get("strict"))
+    prog = levelize(read_lbf(e["lbf"]), 11, shard_pad=2)
+    B, world = 4, 2
+    bes = [B200Backend("toy3", device=0, seed=21) for _ in range(world)]
+    cps = [be.load(prog) for be in bes]
+    nbytes = bes[0].wires_bytes(cps[0], B)
+    bufs = [be.wires_alloc(nbytes) for be in bes]
+    solo = bes[0].wires_alloc(nbytes)
+    streams = [torch.cuda.Stream() for _ in range(world)]
+    cudart = ctypes.CDLL("libcudart.so")
+
+    def fetch(ptr):
+        t = torch.empty(nbytes // 8, dtype=torch.int64, device="cuda")
+        cudart.cudaMemcpy(ctypes.c_void_p(t.data_ptr()), ctypes.c_void_p(ptr), ctypes.c_size_t(nbytes), 3)
+        return t.cpu().numpy().reshape(prog.n_slots, B, bes[0].params.ct_words)
+    try:
+        inputs = selfcheck_inputs(e["input_names"])
+        bits = np.array([inputs[nm][:B] for nm in prog.input_names], dtype=np.uint8)
+        d_in = torch.from_numpy(bits).cuda()
+        for be, cp, buf in zip(bes, cps, bufs):
+            be.encrypt_inputs(cp, d_in.data_ptr(), B, buf, enc_seed=9)
+        bes[0].encrypt_inputs(cps[0], d_in.data_ptr(), B, solo, enc_seed=9)
+        torch.cuda.synchronize()
+        for r in range(world):
+            bes[r].set_peers(bufs[r], nbytes, [bufs[1 - r]], r)
+        a = prog.arrays
+        for rep in range(2):                                 # the epochs keep counting across runs
+            for lv in range(prog.n_levels):
+                width = int(a["bs_level_ptr"][lv + 1] - a["bs_level_ptr"][lv])
+                for r in range(world):
+                    nb, ne, _ = level_node_range(width, world, r)
+                    bes[r].run_level(cps[r], lv, B, bufs[r], nb, ne, stream=streams[r].cuda_stream)
+            for r in range(world):
+                bes[r].run_level_sync(bufs[r], stream=streams[r].cuda_stream)
+        torch.cuda.synchronize()
+        assert [be.sync_status() for be in bes] == [0, 0]
+        for r in range(world):
+            bes[r].set_peers(None, 0, [], 0)
+        bes[0].run(cps[0], B, solo)
+        torch.cuda.synchronize()
+        want, got0, got1 = fetch(solo), fetch(bufs[0]), fetch(bufs[1])
+        for q in range(prog.n_boots):
+            s = int(a["bs_slot"][q])
+            assert np.array_equal(want[s], got0[s]) and np.array_equal(want[s], got1[s]), f"bootstrap {q}"
+    finally:
+        for r in range(world):
+            bes[r].set_peers(None, 0, [], 0)
+            bes[r].wires_free(bufs[r])
+        bes[0].wires_free(solo)
+        for be in bes:
+            be.close()
 
 
 def test_edge_cases(ctxs):

@@ -18,11 +18,11 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("FBS_B200_LIB") or os.path.join(_HERE, "libfbs_b200.so")   # env override: kernel-variant experiments
 
 EXPORTS = [
-    "fbs_last_error", "fbs_abi_version", "fbs_ctx_create", "fbs_keygen", "fbs_ctx_destroy", "fbs_ctx_info",
+    "fbs_last_error", "fbs_abi_version", "fbs_ctx_create", "fbs_keygen", "fbs_ctx_destroy", "fbs_ctx_set_cluster", "fbs_ctx_info",
     "fbs_prog_load", "fbs_prog_free", "fbs_eval_bits", "fbs_wires_bytes", "fbs_encrypt_inputs", "fbs_run_level",
     "fbs_run", "fbs_decrypt_outputs", "fbs_pbs_batch", "fbs_clear_eval", "fbs_debug_get_keys", "fbs_debug_ntt",
     "fbs_debug_pbs", "fbs_debug_encrypt", "fbs_debug_decrypt", "fbs_measure_int_peak",
-    "fbs_wires_alloc", "fbs_wires_free", "fbs_ipc_export", "fbs_ipc_import", "fbs_ipc_close", "fbs_set_peers",
+    "fbs_wires_alloc", "fbs_wires_free", "fbs_ipc_export", "fbs_ipc_import", "fbs_ipc_close", "fbs_set_peers", "fbs_level_sync", "fbs_sync_status",
 ]
 
 
@@ -56,6 +56,7 @@ def load_library(path: str | None = None):
         lib.fbs_ctx_create.argtypes = [ctypes.POINTER(_params.CParams), ctypes.c_int, u64, ctypes.POINTER(vp)]
         lib.fbs_keygen.argtypes = [vp]
         lib.fbs_ctx_destroy.argtypes = [vp]
+        lib.fbs_ctx_set_cluster.argtypes = [vp, i32]
         lib.fbs_ctx_info.argtypes = [vp, ctypes.POINTER(i32), ctypes.POINTER(i64), ctypes.POINTER(i64), ctypes.POINTER(i32)]
         lib.fbs_prog_load.argtypes = [vp, ctypes.POINTER(CProgDesc), ctypes.POINTER(vp)]
         lib.fbs_prog_free.argtypes = [vp]
@@ -78,7 +79,9 @@ def load_library(path: str | None = None):
         lib.fbs_ipc_export.argtypes = [vp, vp, ctypes.c_char_p]
         lib.fbs_ipc_import.argtypes = [vp, ctypes.c_char_p, ctypes.POINTER(vp)]
         lib.fbs_ipc_close.argtypes = [vp, vp]
-        lib.fbs_set_peers.argtypes = [vp, ctypes.POINTER(vp), i32]
+        lib.fbs_set_peers.argtypes = [vp, vp, ctypes.c_size_t, ctypes.POINTER(vp), i32, i32]
+        lib.fbs_level_sync.argtypes = [vp, vp, vp]
+        lib.fbs_sync_status.argtypes = [vp, ctypes.POINTER(i32)]
         for name in EXPORTS:
             if name != "fbs_last_error":
                 getattr(lib, name).restype = ctypes.c_int
@@ -122,14 +125,23 @@ class CompiledProgram:
 
 
 class B200Backend:
-    """Device context + TFHE keys.  ``B200Backend("A", device=0, seed=1)`` generates keys on the GPU."""
+    """Device context + TFHE keys.  ``B200Backend("A", device=0, seed=1)`` generates keys on the GPU.
 
-    def __init__(self, param_set="A", device: int | None = None, seed: int = 0x5EED, keygen: bool = True, lib_path: str | None = None):
+    ``seed=None`` (default) draws the key seed from ``os.urandom``; pass an explicit seed for reproducible keys (tests,
+    benchmarks, and multi-GPU runs where every rank must derive the SAME keys).  Randomness is a counter-based
+    splitmix64 construction shared with the oracle -- a benchmark harness, not a CSPRNG.
+    Every encrypting call uses a fresh encryption seed (base seed mixed with a per-backend call counter), so no
+    (seed, ciphertext id) pair -- i.e. no mask/noise pair -- is ever reused across calls; ``enc_seed=`` overrides it
+    for bit-exact comparisons against the oracle."""
+
+    def __init__(self, param_set="A", device: int | None = None, seed: int | None = None, keygen: bool = True, lib_path: str | None = None):
         self.lib = load_library(lib_path)
         self.params = _params.get(param_set)
         if device is None:
             device = int(os.environ.get("LOCAL_RANK", "0"))
         self.device = device
+        if seed is None:
+            seed = int.from_bytes(os.urandom(8), "little")
         self.seed = seed
         self.ctx = ctypes.c_void_p()
         cp = _params.to_c(self.params)
@@ -137,8 +149,19 @@ class B200Backend:
         self.have_keys = False
         if keygen:
             self.keygen()
-        self.enc_seed = seed ^ 0xE2C0DE
+        self.enc_seed = (seed ^ 0xE2C0DE) & (2 ** 64 - 1)     # base; each encrypting call derives its own (see _fresh_enc_seed)
+        self._enc_calls = 0
+        self.last_enc_seed = None
         self.last_stats = None
+
+    def _fresh_enc_seed(self, explicit=None) -> int:
+        """Encryption seed of the next encrypting call: explicit, or base seed advanced by the call counter (splitmix64
+        increment), so ciphertext ids restarting at 0 never meet the same seed twice on one backend."""
+        if explicit is None:
+            self._enc_calls += 1
+            explicit = (self.enc_seed + self._enc_calls * 0x9E3779B97F4A7C15) & (2 ** 64 - 1)
+        self.last_enc_seed = int(explicit) & (2 ** 64 - 1)
+        return self.last_enc_seed
 
     def _check(self, rc):
         if rc != 0:
@@ -147,6 +170,10 @@ class B200Backend:
     def keygen(self):
         self._check(self.lib.fbs_keygen(self.ctx))
         self.have_keys = True
+
+    def set_cluster(self, mode: int):
+        """0 auto, 1 off, 2 / 4 / 8: force the cluster-split blind rotation of that size (bit-identical results)."""
+        self._check(self.lib.fbs_ctx_set_cluster(self.ctx, mode))
 
     def info(self):
         sm, bsk, ksk, sme = ctypes.c_int32(), ctypes.c_int64(), ctypes.c_int64(), ctypes.c_int32()
@@ -175,9 +202,19 @@ class B200Backend:
     def ipc_close(self, ptr: int):
         self._check(self.lib.fbs_ipc_close(self.ctx, ctypes.c_void_p(ptr)))
 
-    def set_peers(self, ptrs):
+    def set_peers(self, local_ptr, nbytes, ptrs, rank):
+        """Bind the peer replicas (other ranks' IPC-mapped buffers) to the local wire buffer ``local_ptr``; [] unbinds."""
         arr = (ctypes.c_void_p * max(1, len(ptrs)))(*ptrs)
-        self._check(self.lib.fbs_set_peers(self.ctx, arr, len(ptrs)))
+        self._check(self.lib.fbs_set_peers(self.ctx, ctypes.c_void_p(local_ptr or 0), nbytes, arr, len(ptrs), rank))
+
+    def run_level_sync(self, local_ptr, stream=0):
+        self._check(self.lib.fbs_level_sync(self.ctx, ctypes.c_void_p(local_ptr), ctypes.c_void_p(stream)))
+
+    def sync_status(self) -> int:
+        """0, or 1 + rank of a peer whose level flag never arrived (device-side level hand-off timed out)."""
+        v = ctypes.c_int32()
+        self._check(self.lib.fbs_sync_status(self.ctx, ctypes.byref(v)))
+        return v.value
 
     def measure_int_peak(self) -> float:
         """Sustained IMAD.WIDE rate of this device in 32x32->64 multiplies per second."""
@@ -215,7 +252,7 @@ class B200Backend:
 
     # ------------------------------------------------------------------ evaluation with host buffers
     def eval_bits(self, cprog: CompiledProgram, in_bits: np.ndarray, inst_offset=0, total=None, max_wire_bytes=0,
-                  out: np.ndarray | None = None, in_ptr=None, out_ptr=None, B=None) -> np.ndarray:
+                  out: np.ndarray | None = None, in_ptr=None, out_ptr=None, B=None, enc_seed=None) -> np.ndarray:
         """in_bits: uint8 [n_inputs][B] -> uint8 [n_outputs][B] (values mod 2p).  Encrypt, run every level as
         one batched bootstrap, decrypt.  ``in_ptr``/``out_ptr`` allow pinned host buffers (bench.py)."""
         if not self.have_keys:
@@ -231,7 +268,7 @@ class B200Backend:
             out_ptr = out.ctypes.data
         st = RunStats()
         self._check(self.lib.fbs_eval_bits(self.ctx, cprog.handle, ctypes.c_void_p(in_ptr), B, inst_offset, total or B,
-                                           ctypes.c_uint64(self.enc_seed), max_wire_bytes, ctypes.c_void_p(out_ptr), ctypes.byref(st)))
+                                           ctypes.c_uint64(self._fresh_enc_seed(enc_seed)), max_wire_bytes, ctypes.c_void_p(out_ptr), ctypes.byref(st)))
         self.last_stats = st.as_dict()
         return out
 
@@ -244,7 +281,7 @@ class B200Backend:
         self.last_stats = st.as_dict()
         return out
 
-    def pbs_batch(self, p, msgs, tables, tlens, modes=None):
+    def pbs_batch(self, p, msgs, tables, tlens, modes=None, enc_seed=None):
         """BASELINE config 5: independent bootstraps.  tables: uint8 [count][2p]."""
         msgs = np.ascontiguousarray(msgs, dtype=np.uint8)
         tables = np.ascontiguousarray(tables, dtype=np.uint8)
@@ -255,7 +292,7 @@ class B200Backend:
         out = np.zeros(count, dtype=np.uint8)
         st = RunStats()
         self._check(self.lib.fbs_pbs_batch(self.ctx, p, _ptr(msgs), _ptr(tables), _ptr(tlens), _ptr(modes_a), count,
-                                           ctypes.c_uint64(self.enc_seed), _ptr(out), ctypes.byref(st)))
+                                           ctypes.c_uint64(self._fresh_enc_seed(enc_seed)), _ptr(out), ctypes.byref(st)))
         self.last_stats = st.as_dict()
         return out
 
@@ -265,9 +302,9 @@ class B200Backend:
         self._check(self.lib.fbs_wires_bytes(self.ctx, cprog.handle, B, ctypes.byref(n)))
         return n.value
 
-    def encrypt_inputs(self, cprog, in_dev_ptr, B, wires_ptr, stream=0, inst_offset=0, total=None):
+    def encrypt_inputs(self, cprog, in_dev_ptr, B, wires_ptr, stream=0, inst_offset=0, total=None, enc_seed=None):
         self._check(self.lib.fbs_encrypt_inputs(self.ctx, cprog.handle, ctypes.c_void_p(in_dev_ptr), B, inst_offset, total or B,
-                                                ctypes.c_uint64(self.enc_seed), ctypes.c_void_p(wires_ptr), ctypes.c_void_p(stream)))
+                                                ctypes.c_uint64(self._fresh_enc_seed(enc_seed)), ctypes.c_void_p(wires_ptr), ctypes.c_void_p(stream)))
 
     def run_level(self, cprog, level, B, wires_ptr, node_begin=-1, node_end=-1, stream=0, stats=None):
         self._check(self.lib.fbs_run_level(self.ctx, cprog.handle, level, node_begin, node_end, B, ctypes.c_void_p(wires_ptr),

@@ -74,6 +74,31 @@ static const BRVariant g_br_variants[] = {
     BRV2(9, 1, 2, 2, 3),                           // toy3v
 };
 
+// cluster-split low-latency kernels (one bootstrap over C = 2^LOGC CTAs), for launches that would leave SMs idle
+template <int LOGN, int K, int M, int LOGC>
+static cudaError_t brc_launch(const BRArgs &a, long long jobs, size_t smem, cudaStream_t st)
+{
+    using Cf = BRCCfg<LOGN, K, M, LOGC>;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)((jobs - a.job_begin) << LOGC)); cfg.blockDim = dim3(Cf::THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 1 << LOGC; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, k_blind_rotate_cl<LOGN, K, M, LOGC>, a);
+}
+template <int LOGN, int K, int M, int LOGC>
+static cudaError_t brc_prepare(size_t smem)
+{
+    return cudaFuncSetAttribute(k_blind_rotate_cl<LOGN, K, M, LOGC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+}
+template <int LOGN, int K, int M, int LOGC> static size_t brc_smem(int n) { return BRCCfg<LOGN, K, M, LOGC>::smem_bytes(n); }
+struct BRCVariant { int logN, k, unr, logC; size_t (*smem)(int n); br_launch_fn launch; cudaError_t (*prepare)(size_t smem); };
+#define BRCV(LOGN, K, M, LOGC) { LOGN, K, M, LOGC, brc_smem<LOGN, K, M, LOGC>, brc_launch<LOGN, K, M, LOGC>, brc_prepare<LOGN, K, M, LOGC> }
+static const BRCVariant g_brc_variants[] = {
+    BRCV(11, 1, 3, 1), BRCV(11, 1, 3, 2), BRCV(11, 1, 3, 3),      // sets A3 / toy5v: clusters of 2, 4, 8
+    BRCV(11, 1, 2, 1), BRCV(11, 1, 2, 2), BRCV(11, 1, 2, 3),      // sets A2 / toy5u
+};
+
 typedef void (*ntt_launch_fn)(const u64 *, u64 *, int, const fq_tw *, const fq_tw *, u32, u32, long long, cudaStream_t, int);
 template <int LOGN>
 static void ntt_launch(const u64 *in, u64 *out, int mode, const fq_tw *pr, const fq_tw *pir, u32 s1, u32 s2, long long count, cudaStream_t st, int g1)
@@ -92,10 +117,18 @@ struct fbs_ctx {
     bool have_keys = false;
     const BRVariant *br = nullptr; size_t br_smem = 0;        // widest variant (most bootstraps per CTA)
     const BRVariant *br1 = nullptr; size_t br1_smem = 0;      // one bootstrap per CTA, for launches with <= sm_count jobs
+    const BRCVariant *brc[4] = {}; size_t brc_smem[4] = {};   // [log2 C]: one bootstrap per cluster of C CTAs (launches with <= sm_count / C jobs)
+    int cluster_mode = 0;                                     // 0 auto, 1 never, 2 / 4 / 8 force that cluster size (fbs_ctx_set_cluster)
     u8 *d_s_lwe = nullptr, *d_s_big = nullptr;
     u64 *d_ksk = nullptr, *d_colsum = nullptr, *d_bsk = nullptr, *d_bsk_coef = nullptr;
     u8 *d_kbt = nullptr;                                       // byte-transposed KSK for the tensor-core key switch
-    int n_peers = 0; u64 *peers[8] = {};                       // peer replicas of the wire buffer (fbs_set_peers)
+    // node-sharded multi-GPU (fbs_set_peers): peer replicas of ONE registered local wire buffer; the epilogue only stores to
+    // them when a level runs on exactly that buffer.  Each replica ends in a flag page (fbs_wires_alloc): flags[r] = last level
+    // epoch rank r has completed (written by rank r with a system-scope release after its peer stores).
+    int n_peers = 0, peer_rank = 0; u64 *peers[8] = {};
+    u64 *peer_local = nullptr; size_t peer_bytes = 0;
+    u64 *flags_local = nullptr, *peer_flags[8] = {};
+    u64 epoch = 0; int *d_sync_err = nullptr;
     fq_tw *d_psi_rev = nullptr, *d_psi_inv_rev = nullptr;
     u64 *d_psi_pow = nullptr;                                  // psi^x - 1, x < 2N, packed residues (key-unrolled kernel)
     int unroll = 1, n_ggsw = 0; u32 mont2_ninv[2] = {0, 0};    // 2^64/N per prime
@@ -111,10 +144,13 @@ struct fbs_ctx {
     // staging for host-buffer calls
     u8 *d_io = nullptr; size_t cap_io = 0;
     u64 *d_wires = nullptr; size_t cap_wires = 0;
+    u8 *d_clear_io = nullptr; size_t cap_clear_io = 0;         // fbs_clear_eval scratch
+    int32_t *d_clear_lcv = nullptr; size_t cap_clear_lcv = 0;
 };
 struct fbs_prog {
     fbs_ctx *ctx = nullptr;
     int32_t p = 0, n_inputs = 0, n_lincombs = 0, n_boots = 0, n_levels = 0, n_slots = 0, n_outputs = 0;
+    bool contiguous_levels = false;                       // slots are never recycled: node sub-ranges of a level may run alone
     std::vector<int32_t> lc_level_ptr, bs_level_ptr, bs_lc;
     int max_lc_per_level = 0;
     int32_t *d_i32 = nullptr; u8 *d_tab = nullptr;        // one arena for all int32 arrays
@@ -190,6 +226,12 @@ static int ctx_create_impl(const fbs_params *params, int device, uint64_t seed, 
     CK(br->prepare((size_t)prop.sharedMemPerBlockOptin));
     c->br1_smem = c->br1->smem(P.n);
     if (c->br1 != c->br) CK(c->br1->prepare((size_t)prop.sharedMemPerBlockOptin));
+    for (const BRCVariant &v : g_brc_variants) if (v.logN == logN && v.k == P.k && v.unr == unroll && P.bsk_l == 1) {
+        const size_t sm = v.smem(P.n);
+        if (sm > (size_t)prop.sharedMemPerBlockOptin) continue;
+        CK(v.prepare((size_t)prop.sharedMemPerBlockOptin));
+        c->brc[v.logC] = &v; c->brc_smem[v.logC] = sm;
+    }
     CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     for (auto &e : c->ev) CK(cudaEventCreate(&e));
     // twiddles psi^bitrev(i): 7 generates Z_P^*
@@ -270,12 +312,22 @@ extern "C" int fbs_ctx_destroy(fbs_ctx *c)
     if (!c) return FBS_OK;
     cudaSetDevice(c->device);
     void *ptrs[] = {c->d_kbt, c->d_s_lwe, c->d_s_big, c->d_ksk, c->d_colsum, c->d_bsk, c->d_bsk_coef, c->d_psi_rev, c->d_psi_inv_rev, c->d_psi_pow,
-                    c->d_gad_bsk, c->d_gad_ks, c->d_digits, c->d_body, c->d_ms, c->d_io, c->d_wires};
+                    c->d_gad_bsk, c->d_gad_ks, c->d_digits, c->d_body, c->d_ms, c->d_io, c->d_wires, c->d_clear_io, c->d_clear_lcv, c->d_sync_err};
     for (void *p : ptrs) if (p) cudaFree(p);
     for (auto &e : c->ev) if (e) cudaEventDestroy(e);
     for (auto &e : c->ev_pool) if (e) cudaEventDestroy(e);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
+    return FBS_OK;
+}
+extern "C" int fbs_ctx_set_cluster(fbs_ctx *c, int32_t mode)
+{
+    if (!c || !(mode == 0 || mode == 1 || mode == 2 || mode == 4 || mode == 8)) return fail(FBS_ERR_ARG, "fbs_ctx_set_cluster: mode must be 0 (auto), 1 (off), 2, 4 or 8");
+    if (mode > 1) {
+        int lc = mode == 2 ? 1 : mode == 4 ? 2 : 3;
+        if (!c->brc[lc]) return fail(FBS_ERR_ARG, "fbs_ctx_set_cluster: no cluster kernel of that size for this parameter set");
+    }
+    c->cluster_mode = mode;
     return FBS_OK;
 }
 extern "C" int fbs_ctx_info(const fbs_ctx *c, int32_t *sm_count, int64_t *bsk_bytes, int64_t *ksk_bytes, int32_t *br_smem_bytes)
@@ -292,15 +344,40 @@ extern "C" int fbs_ctx_info(const fbs_ctx *c, int32_t *sm_count, int64_t *bsk_by
 // ------------------------------------------------------------------------------------------------------
 // program
 // ------------------------------------------------------------------------------------------------------
+// CSR pointer array: starts at 0, monotone, `count + 1` entries; returns the final value or -1
+static int csr_total(const int32_t *ptr, int count)
+{
+    if (count == 0) return 0;
+    if (!ptr || ptr[0] != 0) return -1;
+    for (int i = 0; i < count; i++) if (ptr[i + 1] < ptr[i]) return -1;
+    return ptr[count];
+}
+static int prog_load_impl(fbs_ctx *c, const fbs_prog_desc *d, fbs_prog *g);
 extern "C" int fbs_prog_load(fbs_ctx *c, const fbs_prog_desc *d, fbs_prog **out)
 {
     if (!c || !d || !out) return fail(FBS_ERR_ARG, "fbs_prog_load: null argument");
+    *out = nullptr;
+    fbs_prog *g = new fbs_prog();
+    const int rc = prog_load_impl(c, d, g);
+    if (rc != FBS_OK) { const std::string keep = g_err; fbs_prog_free(g); g_err = keep; return rc; }   // no leak on any error path
+    *out = g;
+    return FBS_OK;
+}
+static int prog_load_impl(fbs_ctx *c, const fbs_prog_desc *d, fbs_prog *g)
+{
+    g->ctx = c;
     if (d->p < 2 || d->p > 128) return fail(FBS_ERR_ARG, "p out of range");
-    CK(cudaSetDevice(c->device));
-    const int nnz = d->n_lincombs ? d->lc_ptr[d->n_lincombs] : 0;
-    const int onz = d->n_outputs ? d->out_ptr[d->n_outputs] : 0;
-    const int tabn = d->n_boots ? d->bs_tab_ptr[d->n_boots] : 0;
-    // validation: slots in range, tables <= 2p and <= 64 entries, levels monotone
+    if (d->n_inputs < 0 || d->n_lincombs < 0 || d->n_boots < 0 || d->n_levels < 0 || d->n_slots < 0 || d->n_outputs < 0)
+        return fail(FBS_ERR_ARG, "fbs_prog_load: negative count");
+    if (!d->lc_level_ptr || !d->bs_level_ptr) return fail(FBS_ERR_ARG, "fbs_prog_load: null level pointers");
+    // every CSR / level pointer array: monotone from 0, final value = the count it partitions
+    const int nnz = csr_total(d->lc_ptr, d->n_lincombs), onz = csr_total(d->out_ptr, d->n_outputs), tabn = csr_total(d->bs_tab_ptr, d->n_boots);
+    if (nnz < 0 || onz < 0 || tabn < 0) return fail(FBS_ERR_ARG, "fbs_prog_load: lc_ptr / out_ptr / bs_tab_ptr must start at 0 and be monotone");
+    if (csr_total(d->lc_level_ptr, d->n_levels) != d->n_lincombs || csr_total(d->bs_level_ptr, d->n_levels) != d->n_boots)
+        return fail(FBS_ERR_ARG, "fbs_prog_load: level pointers must be monotone from 0 and end at n_lincombs / n_boots");
+    if ((nnz && (!d->lc_slot || !d->lc_coef)) || (d->n_lincombs && !d->lc_const) || (onz && (!d->out_slot || !d->out_coef)) || (d->n_outputs && !d->out_const) ||
+        (d->n_boots && (!d->bs_lc || !d->bs_slot || !d->bs_mode || !d->bs_tab)) || (d->n_inputs && !d->in_slot))
+        return fail(FBS_ERR_ARG, "fbs_prog_load: null array");
     for (int i = 0; i < nnz; i++) if (d->lc_slot[i] < 0 || d->lc_slot[i] >= d->n_slots) return fail(FBS_ERR_ARG, "lincomb operand slot out of range");
     for (int i = 0; i < onz; i++) if (d->out_slot[i] < 0 || d->out_slot[i] >= d->n_slots) return fail(FBS_ERR_ARG, "output operand slot out of range");
     for (int i = 0; i < d->n_inputs; i++) if (d->in_slot[i] < 0 || d->in_slot[i] >= d->n_slots) return fail(FBS_ERR_ARG, "input slot out of range");
@@ -309,18 +386,20 @@ extern "C" int fbs_prog_load(fbs_ctx *c, const fbs_prog_desc *d, fbs_prog **out)
         if (L < 1 || L > 2 * d->p || L > 64) return fail(FBS_ERR_ARG, "bootstrap table longer than 2p (or 64) entries");
         if (d->bs_slot[q] < 0 || d->bs_slot[q] >= d->n_slots) return fail(FBS_ERR_ARG, "bootstrap slot out of range");
         if (d->bs_lc[q] < 0 || d->bs_lc[q] >= d->n_lincombs) return fail(FBS_ERR_ARG, "bootstrap lincomb index out of range");
+        if (d->bs_mode[q] < 0 || d->bs_mode[q] >= 2 * d->p) return fail(FBS_ERR_ARG, "bootstrap table mode out of range");
+        for (int t = d->bs_tab_ptr[q]; t < d->bs_tab_ptr[q + 1]; t++) if (d->bs_tab[t] >= 2 * d->p) return fail(FBS_ERR_ARG, "bootstrap table entry >= 2p");
     }
-    fbs_prog *g = new fbs_prog();
-    g->ctx = c; g->p = d->p; g->n_inputs = d->n_inputs; g->n_lincombs = d->n_lincombs; g->n_boots = d->n_boots;
-    g->n_levels = d->n_levels; g->n_slots = d->n_slots; g->n_outputs = d->n_outputs;
+    CK(cudaSetDevice(c->device));
+    g->p = d->p; g->n_inputs = d->n_inputs; g->n_lincombs = d->n_lincombs; g->n_boots = d->n_boots;
+    g->n_levels = d->n_levels; g->n_slots = d->n_slots; g->n_outputs = d->n_outputs; g->contiguous_levels = d->contiguous_levels != 0;
     g->lc_level_ptr.assign(d->lc_level_ptr, d->lc_level_ptr + d->n_levels + 1);
     g->bs_level_ptr.assign(d->bs_level_ptr, d->bs_level_ptr + d->n_levels + 1);
     g->bs_lc.assign(d->bs_lc, d->bs_lc + d->n_boots);
     for (int lv = 0; lv < d->n_levels; lv++) {
         g->max_lc_per_level = std::max(g->max_lc_per_level, g->lc_level_ptr[lv + 1] - g->lc_level_ptr[lv]);
         for (int q = g->bs_level_ptr[lv]; q < g->bs_level_ptr[lv + 1]; q++) {
-            if (g->bs_lc[q] < g->lc_level_ptr[lv] || g->bs_lc[q] >= g->lc_level_ptr[lv + 1]) { delete g; return fail(FBS_ERR_ARG, "bootstrap uses a lincomb of another level"); }
-            if (q > g->bs_level_ptr[lv] && g->bs_lc[q] < g->bs_lc[q - 1]) { delete g; return fail(FBS_ERR_ARG, "bootstraps of a level must be sorted by lincomb index"); }
+            if (g->bs_lc[q] < g->lc_level_ptr[lv] || g->bs_lc[q] >= g->lc_level_ptr[lv + 1]) return fail(FBS_ERR_ARG, "bootstrap uses a lincomb of another level");
+            if (q > g->bs_level_ptr[lv] && g->bs_lc[q] < g->bs_lc[q - 1]) return fail(FBS_ERR_ARG, "bootstraps of a level must be sorted by lincomb index");
         }
     }
     struct Piece { const int32_t *src; size_t n; int32_t **dst; };
@@ -334,7 +413,7 @@ extern "C" int fbs_prog_load(fbs_ctx *c, const fbs_prog_desc *d, fbs_prog **out)
     size_t tot = 0;
     for (auto &pc : pieces) tot += pc.n + 4;
     std::vector<int32_t> host(tot, 0);
-    if (dev_alloc(&g->d_i32, tot) != FBS_OK) { delete g; return FBS_ERR_CUDA; }
+    CKR(dev_alloc(&g->d_i32, tot));
     size_t off = 0;
     for (auto &pc : pieces) {
         if (pc.n && pc.src) memcpy(host.data() + off, pc.src, pc.n * 4);
@@ -342,9 +421,8 @@ extern "C" int fbs_prog_load(fbs_ctx *c, const fbs_prog_desc *d, fbs_prog **out)
         off += (pc.n + 3) & ~(size_t)3;
     }
     CK(cudaMemcpy(g->d_i32, host.data(), tot * 4, cudaMemcpyHostToDevice));
-    if (dev_alloc(&g->d_tab, (size_t)tabn + 16) != FBS_OK) { delete g; return FBS_ERR_CUDA; }
+    CKR(dev_alloc(&g->d_tab, (size_t)tabn + 16));
     if (tabn) CK(cudaMemcpy(g->d_tab, d->bs_tab, tabn, cudaMemcpyHostToDevice));
-    *out = g;
     return FBS_OK;
 }
 extern "C" int fbs_prog_free(fbs_prog *g)
@@ -385,10 +463,10 @@ extern "C" int fbs_encrypt_inputs(fbs_ctx *c, fbs_prog *g, const uint8_t *in_dev
     return FBS_OK;
 }
 
-template <int LK> static void launch_lc(const LCArgs &a, long long tiles, cudaStream_t st)
+template <int LK> static void launch_lc(const LCArgs &a, long long tiles, cudaStream_t st, int sm_count)
 {
-    // column chunks so that even a level with few ciphertexts puts about two CTAs on every SM (148 SMs on B200)
-    int ny = (int)std::min<long long>(std::max<long long>(1, (2 * 148 + tiles - 1) / tiles), (a.D + 1 + 255) / 256);
+    // column chunks so that even a level with few ciphertexts puts about two CTAs on every SM
+    int ny = (int)std::min<long long>(std::max<long long>(1, (2 * sm_count + tiles - 1) / tiles), (a.D + 1 + 255) / 256);
     k_lincomb_decomp<LK><<<dim3((unsigned)tiles, (unsigned)ny), 256, 0, st>>>(a);
 }
 
@@ -398,8 +476,23 @@ static int run_level_impl(fbs_ctx *c, fbs_prog *g, int level, int nb, int ne, in
     cudaEvent_t *E = evq ? evq : c->ev;
     const bool rec = timed || evq;
     const int b0 = g->bs_level_ptr[level], b1 = g->bs_level_ptr[level + 1];
+    const bool whole = (nb < 0 && ne < 0) || (nb == 0 && ne == b1 - b0);
     if (nb < 0 && ne < 0) { nb = 0; ne = b1 - b0; }
     if (nb < 0 || ne > b1 - b0 || nb > ne) return fail(FBS_ERR_ARG, "fbs_run_level: node range outside the level");
+    if (!whole && !g->contiguous_levels)
+        return fail(FBS_ERR_ARG, "fbs_run_level: a node sub-range needs a program levelised with contiguous_levels (slots are recycled otherwise)");
+    // Node-sharded level on the registered, peer-mapped wire buffer: wait (on the device) until every rank has finished the
+    // previous level, and publish this rank's completion after the blind rotation's peer stores -- no host sync between levels.
+    const bool fused = c->n_peers > 0 && wires == c->peer_local, handoff = fused && c->peer_rank >= 0;
+    if (fused && (size_t)g->n_slots * (size_t)B * ct_words(c) * 8 > c->peer_bytes) return fail(FBS_ERR_ARG, "fbs_run_level: program does not fit the registered peer wire buffer");
+    if (handoff) {
+        if (c->epoch > 0) { k_level_wait<<<1, 32, 0, st>>>(c->flags_local, c->n_peers + 1, c->peer_rank, c->epoch, c->d_sync_err); CK(cudaGetLastError()); }
+    }
+    struct Signal {            // runs on every exit path of a fused level, including an empty node range
+        fbs_ctx *c; cudaStream_t st; bool on;
+        ~Signal() { if (on) { LevelPeers lp{}; lp.n = c->n_peers; for (int i = 0; i < c->n_peers; i++) lp.flags[i] = c->peer_flags[i];
+                              c->epoch++; k_level_signal<<<1, 32, 0, st>>>(lp, c->peer_rank, c->epoch); } }
+    } signal{c, st, handoff};
     if (nb == ne) return FBS_OK;
     const fbs_params &P = c->P;
     const int D = P.k * P.N, n = P.n;
@@ -416,9 +509,10 @@ static int run_level_impl(fbs_ctx *c, fbs_prog *g, int level, int nb, int ne, in
     la.wires = wires; la.lc_ptr = g->d_lc_ptr; la.lc_slot = g->d_lc_slot; la.lc_coef = g->d_lc_coef; la.lc_const = g->d_lc_const;
     la.digits = c->d_digits; la.body = c->d_body; la.B = B; la.M = M; la.lc_begin = lc0; la.D = D; la.p = g->p; la.ks_beta = P.ks_beta;
     switch (P.ks_l) {
-    case 1: launch_lc<1>(la, tiles, st); break; case 2: launch_lc<2>(la, tiles, st); break; case 3: launch_lc<3>(la, tiles, st); break;
-    case 4: launch_lc<4>(la, tiles, st); break; case 5: launch_lc<5>(la, tiles, st); break; case 6: launch_lc<6>(la, tiles, st); break;
-    case 7: launch_lc<7>(la, tiles, st); break; default: launch_lc<8>(la, tiles, st); break;
+    case 1: launch_lc<1>(la, tiles, st, c->sm_count); break; case 2: launch_lc<2>(la, tiles, st, c->sm_count); break;
+    case 3: launch_lc<3>(la, tiles, st, c->sm_count); break; case 4: launch_lc<4>(la, tiles, st, c->sm_count); break;
+    case 5: launch_lc<5>(la, tiles, st, c->sm_count); break; case 6: launch_lc<6>(la, tiles, st, c->sm_count); break;
+    case 7: launch_lc<7>(la, tiles, st, c->sm_count); break; default: launch_lc<8>(la, tiles, st, c->sm_count); break;
     }
     CK(cudaGetLastError());
     if (rec) CK(cudaEventRecord(E[1], st));
@@ -433,15 +527,22 @@ static int run_level_impl(fbs_ctx *c, fbs_prog *g, int level, int nb, int ne, in
     ba.ms = c->d_ms; ba.bsk = c->d_bsk; ba.psi_rev = c->d_psi_rev; ba.psi_inv_rev = c->d_psi_inv_rev; ba.psi_pow = c->d_psi_pow;
     ba.bs_lc = g->d_bs_lc; ba.bs_slot = g->d_bs_slot; ba.bs_tab_ptr = g->d_bs_tab_ptr; ba.bs_mode = g->d_bs_mode; ba.bs_tab = g->d_tab;
     ba.wires = wires; ba.tap_acc = tap_acc; ba.B = B; ba.jobs = (long long)(node1 - node0) * B; ba.node_begin = node0;
-    ba.n_peers = c->n_peers;
-    for (int pr = 0; pr < c->n_peers; pr++) ba.peer_wires[pr] = c->peers[pr]; ba.lc_begin = lc0; ba.n = n; ba.p = g->p; ba.beta = P.bsk_beta;
+    ba.n_peers = fused ? c->n_peers : 0;      // peers are bound to the registered buffer only (never to c->d_wires or a tap buffer)
+    for (int pr = 0; pr < ba.n_peers; pr++) ba.peer_wires[pr] = c->peers[pr];
+    ba.lc_begin = lc0; ba.n = n; ba.p = g->p; ba.beta = P.bsk_beta;
     const long long jobs = (long long)(node1 - node0) * B;
     // Full waves run the widest variant (pb bootstraps per CTA, one CTA per SM).  A last partial wave of at most one job
     // per SM goes to the one-bootstrap-per-CTA variant instead: it spreads over all SMs and finishes sooner than half-idle
     // paired CTAs would (and starts as soon as SMs drain from the first launch).
     const long long wave = (long long)c->sm_count * c->br->pb, tail = jobs % wave;
     int n_br_launches = 1;
-    if (c->br1 != c->br && tail > 0 && tail <= c->sm_count) {
+    // Fewer jobs than SMs: split each bootstrap over a cluster of C CTAs (largest C in {8, 4, 2} whose jobs * C CTAs still fit
+    // one wave), cutting the latency of the level instead of idling SMs.  Results are bit-identical to the one-CTA kernels.
+    int logC = 0;
+    if (c->cluster_mode == 0) { for (int lc = 3; lc >= 1; lc--) if (c->brc[lc] && (jobs << lc) <= c->sm_count) { logC = lc; break; } }
+    else if (c->cluster_mode > 1) { for (int lc = 1; lc <= 3; lc++) if ((1 << lc) == c->cluster_mode && c->brc[lc]) logC = lc; }
+    if (logC) CK(c->brc[logC]->launch(ba, jobs, c->brc_smem[logC], st));
+    else if (c->br1 != c->br && tail > 0 && tail <= c->sm_count) {
         if (jobs > tail) { BRArgs bw = ba; CK(c->br->launch(bw, jobs - tail, c->br_smem, st)); n_br_launches = 2; }
         ba.job_begin = jobs - tail;
         CK(c->br1->launch(ba, jobs, c->br1_smem, st));
@@ -587,8 +688,9 @@ extern "C" int fbs_clear_eval(fbs_ctx *c, fbs_prog *g, const uint8_t *in, int64_
     CK(cudaSetDevice(c->device));
     cudaStream_t st = c->stream;
     const size_t nio = (size_t)(g->n_inputs + g->n_outputs + g->n_slots + 1) * B;
-    u8 *d_io = nullptr; int32_t *d_lcv = nullptr; int *d_err = nullptr;
-    CKR(dev_alloc(&d_io, nio)); CKR(dev_alloc(&d_lcv, (size_t)std::max(1, g->max_lc_per_level) * B)); CKR(dev_alloc(&d_err, 1));
+    // grow-only scratch of the context (no allocation per call): io bytes, lincomb values, error word
+    CKR(grow(&c->d_clear_io, &c->cap_clear_io, nio)); CKR(grow(&c->d_clear_lcv, &c->cap_clear_lcv, (size_t)std::max(1, g->max_lc_per_level) * B + 1));
+    u8 *d_io = c->d_clear_io; int32_t *d_lcv = c->d_clear_lcv + 1; int *d_err = c->d_clear_lcv;
     CK(cudaMemsetAsync(d_err, 0, 4, st));
     u8 *d_in = d_io, *d_out = d_in + (size_t)g->n_inputs * B, *d_vals = d_out + (size_t)g->n_outputs * B;
     if (g->n_inputs) CK(cudaMemcpyAsync(d_in, in, (size_t)g->n_inputs * B, cudaMemcpyHostToDevice, st));
@@ -606,7 +708,6 @@ extern "C" int fbs_clear_eval(fbs_ctx *c, fbs_prog *g, const uint8_t *in, int64_
     CK(cudaMemcpyAsync(&err, d_err, 4, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     if (stats) { float t; CK(cudaEventElapsedTime(&t, c->ev[6], c->ev[7])); stats->ms_total += t; stats->n_launches += 1; stats->n_pbs += (int64_t)g->n_boots * B; }
-    cudaFree(d_io); cudaFree(d_lcv); cudaFree(d_err);
     if (err) return fail(FBS_ERR_ARG, "cleartext evaluation: table index out of range at bootstrap #" + std::to_string(err - 1));
     return FBS_OK;
 }
@@ -629,7 +730,7 @@ static int make_pbs_prog(fbs_ctx *c, int p, const uint8_t *tables, int tab_strid
     }
     lc_ptr[n] = n; out_ptr[n] = n;
     fbs_prog_desc d{};
-    d.p = p; d.n_inputs = n; d.n_lincombs = n; d.n_boots = n; d.n_levels = 1; d.n_slots = 2 * n; d.n_outputs = n;
+    d.p = p; d.n_inputs = n; d.n_lincombs = n; d.n_boots = n; d.n_levels = 1; d.n_slots = 2 * n; d.n_outputs = n; d.contiguous_levels = 1;
     d.lc_level_ptr = lvl.data(); d.bs_level_ptr = lvl.data(); d.lc_ptr = lc_ptr.data(); d.lc_slot = lc_slot.data(); d.lc_coef = lc_coef.data();
     d.lc_const = lc_const.data(); d.bs_lc = bs_lc.data(); d.bs_slot = bs_slot.data(); d.bs_tab_ptr = tab_ptr.data(); d.bs_tab = tab.data();
     d.bs_mode = mode.data(); d.in_slot = in_slot.data(); d.out_ptr = out_ptr.data(); d.out_slot = out_slot.data(); d.out_coef = out_coef.data(); d.out_const = out_const.data();
@@ -744,14 +845,13 @@ extern "C" int fbs_debug_pbs(fbs_ctx *c, int32_t p, const uint64_t *in_cts, cons
         if ((rc = dev_alloc(&d_w, (size_t)2 * count * CT)) != FBS_OK) break;
         if ((rc = dev_alloc(&d_ks, (size_t)(count + 16) * (P.n + 1))) != FBS_OK) break;
         if ((rc = dev_alloc(&d_acc, (size_t)count * (P.k + 1) * P.N)) != FBS_OK) break;
-        cudaMemcpy(d_w, in_cts, (size_t)count * CT * 8, cudaMemcpyHostToDevice);
+        if (cudaMemcpy(d_w, in_cts, (size_t)count * CT * 8, cudaMemcpyHostToDevice) != cudaSuccess) { rc = fail(FBS_ERR_CUDA, std::string("debug_pbs H2D: ") + cudaGetErrorString(cudaGetLastError())); break; }
         if ((rc = run_level_impl(c, g, 0, -1, -1, 1, d_w, st, nullptr, d_ks, d_acc, false)) != FBS_OK) break;
         if (cudaStreamSynchronize(st) != cudaSuccess) { rc = fail(FBS_ERR_CUDA, std::string("debug_pbs: ") + cudaGetErrorString(cudaGetLastError())); break; }
-        cudaMemcpy(out_cts, d_w + (size_t)count * CT, (size_t)count * CT * 8, cudaMemcpyDeviceToHost);
-        if (tap_ks) cudaMemcpy(tap_ks, d_ks, (size_t)count * (P.n + 1) * 8, cudaMemcpyDeviceToHost);
-        if (tap_ms) cudaMemcpy(tap_ms, c->d_ms, (size_t)count * (P.n + 1) * 2, cudaMemcpyDeviceToHost);
-        if (tap_acc) cudaMemcpy(tap_acc, d_acc, (size_t)count * (P.k + 1) * P.N * 8, cudaMemcpyDeviceToHost);
-        cudaError_t e = cudaGetLastError();
+        cudaError_t e = cudaMemcpy(out_cts, d_w + (size_t)count * CT, (size_t)count * CT * 8, cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess && tap_ks) e = cudaMemcpy(tap_ks, d_ks, (size_t)count * (P.n + 1) * 8, cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess && tap_ms) e = cudaMemcpy(tap_ms, c->d_ms, (size_t)count * (P.n + 1) * 2, cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess && tap_acc) e = cudaMemcpy(tap_acc, d_acc, (size_t)count * (P.k + 1) * P.N * 8, cudaMemcpyDeviceToHost);
         if (e != cudaSuccess) rc = fail(FBS_ERR_CUDA, std::string("debug_pbs copies: ") + cudaGetErrorString(e));
     } while (0);
     if (d_w) cudaFree(d_w); if (d_ks) cudaFree(d_ks); if (d_acc) cudaFree(d_acc);
@@ -801,11 +901,14 @@ extern "C" int fbs_measure_int_peak(fbs_ctx *c, double *mul32_per_s)
 // ------------------------------------------------------------------------------------------------------
 // peer-mapped wire buffers for the fused sample-extract + exchange of node-sharded levels
 // ------------------------------------------------------------------------------------------------------
+static inline size_t flag_offset(size_t bytes) { return (bytes + 255) & ~(size_t)255; }
 extern "C" int fbs_wires_alloc(fbs_ctx *c, size_t bytes, uint64_t **out)
 {
     if (!c || !out || bytes == 0) return fail(FBS_ERR_ARG, "fbs_wires_alloc: bad argument");
     CK(cudaSetDevice(c->device));
-    CK(cudaMalloc((void **)out, bytes));             // a plain cudaMalloc allocation: exportable with CUDA IPC
+    // a plain cudaMalloc allocation (exportable with CUDA IPC), followed by one flag page for the device-side level hand-off
+    CK(cudaMalloc((void **)out, flag_offset(bytes) + FBS_FLAG_PAGE));
+    CK(cudaMemset((char *)*out + flag_offset(bytes), 0, FBS_FLAG_PAGE));
     return FBS_OK;
 }
 extern "C" int fbs_wires_free(fbs_ctx *c, uint64_t *p)
@@ -841,10 +944,43 @@ extern "C" int fbs_ipc_close(fbs_ctx *c, uint64_t *peer_ptr)
     if (peer_ptr) CK(cudaIpcCloseMemHandle(peer_ptr));
     return FBS_OK;
 }
-extern "C" int fbs_set_peers(fbs_ctx *c, uint64_t *const *peer_wires, int32_t n_peers)
+extern "C" int fbs_set_peers(fbs_ctx *c, uint64_t *wires_local, size_t wires_bytes, uint64_t *const *peer_wires, int32_t n_peers, int32_t rank)
 {
-    if (!c || n_peers < 0 || n_peers > 8 || (n_peers && !peer_wires)) return fail(FBS_ERR_ARG, "fbs_set_peers: at most 8 peers");
-    c->n_peers = n_peers;
-    for (int i = 0; i < n_peers; i++) c->peers[i] = peer_wires[i];
+    if (!c || n_peers < 0 || n_peers > 8 || (n_peers && (!peer_wires || !wires_local || wires_bytes == 0)) || rank > n_peers)
+        return fail(FBS_ERR_ARG, "fbs_set_peers: at most 8 peers, rank in [0, n_peers] (or < 0: peer stores only, caller orders the levels)");
+    CK(cudaSetDevice(c->device));
+    CK(cudaDeviceSynchronize());                    // nothing in flight still uses the old binding
+    c->n_peers = n_peers; c->peer_rank = rank; c->epoch = 0;
+    c->peer_local = n_peers ? wires_local : nullptr; c->peer_bytes = n_peers ? wires_bytes : 0;
+    c->flags_local = n_peers ? (u64 *)((char *)wires_local + flag_offset(wires_bytes)) : nullptr;
+    for (int i = 0; i < n_peers; i++) {
+        if (!peer_wires[i]) return fail(FBS_ERR_ARG, "fbs_set_peers: null peer pointer");
+        c->peers[i] = peer_wires[i];
+        c->peer_flags[i] = (u64 *)((char *)peer_wires[i] + flag_offset(wires_bytes));
+    }
+    if (n_peers) {
+        CK(cudaMemset(c->flags_local, 0, FBS_FLAG_PAGE));   // the caller barriers across ranks before the first level
+        if (!c->d_sync_err) CKR(dev_alloc(&c->d_sync_err, 1));
+        CK(cudaMemset(c->d_sync_err, 0, sizeof(int)));
+    }
+    return FBS_OK;
+}
+extern "C" int fbs_level_sync(fbs_ctx *c, uint64_t *wires_local, void *stream)
+{
+    if (!c || !wires_local) return fail(FBS_ERR_ARG, "fbs_level_sync: bad argument");
+    if (c->n_peers == 0 || wires_local != c->peer_local || c->peer_rank < 0) return fail(FBS_ERR_STATE, "fbs_level_sync: buffer is not registered with fbs_set_peers for the device-side hand-off");
+    CK(cudaSetDevice(c->device));
+    if (c->epoch > 0) { k_level_wait<<<1, 32, 0, (cudaStream_t)stream>>>(c->flags_local, c->n_peers + 1, c->peer_rank, c->epoch, c->d_sync_err); CK(cudaGetLastError()); }
+    return FBS_OK;
+}
+extern "C" int fbs_sync_status(fbs_ctx *c, int32_t *timed_out)
+{
+    if (!c || !timed_out) return fail(FBS_ERR_ARG, "fbs_sync_status: bad argument");
+    *timed_out = 0;
+    if (!c->d_sync_err) return FBS_OK;
+    CK(cudaSetDevice(c->device));
+    int v = 0;
+    CK(cudaMemcpy(&v, c->d_sync_err, sizeof(int), cudaMemcpyDeviceToHost));
+    *timed_out = v;
     return FBS_OK;
 }

@@ -1051,6 +1051,355 @@ __global__ void __launch_bounds__((PB / TP) * (K + 1) * (1 << LOGN) / 8, 1) k_bl
 }
 
 // ------------------------------------------------------------------------------------------------------
+// K2c: low-latency blind rotation -- ONE bootstrap split across a thread-block cluster of C = 2^LOGC CTAs.
+// For launches with fewer jobs than SMs (narrow circuit levels, node-sharded levels, small batches) the one-CTA kernels leave
+// most of the chip idle and a bootstrap takes n/M strictly sequential steps of one SM's latency-bound work.  Here the
+// ring elements are split over C SMs (ntt.cuh "cluster-split transform"): CTA h owns, in the coefficient domain, the residues
+// r in [h*Ns/C, (h+1)*Ns/C) of every sub-block (accumulate / decompose / cross butterflies are register work), and in the
+// spectral domain the positions [h*Ns, (h+1)*Ns) (local transforms of size Ns = N/C, point-wise products with 1/C of the key).
+// Per step two all-to-all exchanges through DISTRIBUTED SHARED MEMORY (st.async into the destination CTA's inbox,
+// completion counted in bytes on that CTA's mbarrier): no cluster-wide barrier inside the loop, the data dependence is the
+// flow control (a CTA cannot send exchange k+1 before it has received everybody's exchange k, and everybody sent that only
+// after consuming what it received before).  The key is streamed by TMA as in k_blind_rotate2 (same HBM layout: per slice
+// NC*G*G runs of Ts words, issued by the lanes of warp 0), ring depth up to 8 slices = one whole step ahead.
+// Arithmetic, rounding and term order are those of k_blind_rotate2<M>: results are bit-identical.
+// ------------------------------------------------------------------------------------------------------
+template <int LOGN, int K, int M, int LOGC>
+struct BRCCfg {
+    static_assert(M == 2 || M == 3, "two or three key bits per step");
+    static_assert(LOGC >= 1 && LOGC <= 3, "cluster of 2, 4 or 8 CTAs");
+    static constexpr int NC = (1 << M) - 1;
+    static constexpr int N = 1 << LOGN, G = K + 1, C = 1 << LOGC, LOGNS = LOGN - LOGC, Ns = N >> LOGC, Ts = Ns / 8, R = 8 / C, T = N / 8;
+    static_assert(Ts >= 32 && Ts % 32 == 0, "a polynomial's threads in a CTA are whole warps");
+    static constexpr int THREADS = G * Ts;
+    static constexpr int RUNS = NC * G * G;                       // contiguous key runs (Ts words each) per slice
+    static constexpr size_t s_w = (size_t)G * Ns;                 // transpose scratch / digit spectra
+    static constexpr size_t inbox_w = (size_t)G * 8 * Ts;         // one exchange direction
+    static constexpr size_t psi_w = 2 * (size_t)N;
+    static constexpr size_t tw_w = 2 * (size_t)Ns;                // one local twiddle table (16 B entries)
+    static constexpr size_t slice_w = (size_t)RUNS * Ts;
+    static constexpr size_t fixed_b = 8 * (s_w + 2 * inbox_w + psi_w + 2 * tw_w) + 2048 + 256;
+    static constexpr int R_fit = (int)((227 * 1024 - fixed_b) / (8 * slice_w));
+    static constexpr int RING = R_fit > 8 ? 8 : R_fit;
+    static_assert(RING >= 2, "key ring does not fit shared memory");
+    __host__ __device__ static constexpr size_t ms_stride(int n) { return (((size_t)(n + 1) * 2 + 15) / 16) * 16; }
+    __host__ __device__ static constexpr size_t smem_bytes(int n) { return 8 * (s_w + 2 * inbox_w + psi_w + 2 * tw_w + RING * slice_w + 2 * RING + 2) + ms_stride(n); }
+};
+__device__ __forceinline__ u32 cluster_ctarank() { u32 r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ u32 mapa_shared(u32 local_addr, u32 cta) { u32 r; asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(cta)); return r; }
+__device__ __forceinline__ void cluster_sync_all()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// 8-byte store into another CTA's shared memory, completion (8 bytes) counted on that CTA's mbarrier
+__device__ __forceinline__ void st_async_u64(u32 remote_addr, u64 v, u32 remote_bar)
+{
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];" ::"r"(remote_addr), "l"(v), "r"(remote_bar) : "memory");
+}
+// acquire at cluster scope: pairs with the complete_tx of remote st.async.  The spin is bounded: a cluster whose exchange never
+// completes (a lost store would be a bug, not a load condition) traps after FBS_XCHG_TIMEOUT_NS instead of hanging the GPU.
+#ifndef FBS_XCHG_TIMEOUT_NS
+#define FBS_XCHG_TIMEOUT_NS 4000000000ULL
+#endif
+__device__ __forceinline__ void mbar_wait_cluster(u64 *bar, u32 parity)
+{
+    u32 ok;
+    u64 t0 = 0;
+    for (;;) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+        if (ok) return;
+        u64 t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        if (t0 == 0) t0 = t1;
+        else if (t1 - t0 > FBS_XCHG_TIMEOUT_NS) __trap();
+    }
+}
+template <int LOGN, int K, int M, int LOGC>
+__global__ void __launch_bounds__((K + 1) * (1 << (LOGN - LOGC)) / 8, 1) k_blind_rotate_cl(BRArgs a)
+{
+    using Cf = BRCCfg<LOGN, K, M, LOGC>;
+    using P = NttPlan<Cf::LOGNS>;
+    constexpr int NC = Cf::NC, N = Cf::N, G = Cf::G, C = Cf::C, Ns = Cf::Ns, Ts = Cf::Ts, R = Cf::R, T = Cf::T, RING = Cf::RING, LOGNS = Cf::LOGNS;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int tid = threadIdx.x, g = tid / Ts, tau = tid % Ts, lane = tid & 31, warp = tid >> 5;
+    const int h = (int)cluster_ctarank();                         // this CTA's sub-block / residue range
+    const int tau_g = h * Ts + tau;                               // spectrum positions 8*tau_g + e of the full transform
+    u64 *S = (u64 *)smem_raw;
+    u64 *INF = S + Cf::s_w, *INI = INF + Cf::inbox_w;             // inboxes: forward / inverse exchange, [g][e][tau]
+    u64 *PSI = INI + Cf::inbox_w;
+    u64 *TWF = PSI + Cf::psi_w, *TWI = TWF + Cf::tw_w;            // local twiddle tables (fq_tw entries)
+    u64 *RNG = TWI + Cf::tw_w;
+    u64 *full = RNG + (size_t)RING * Cf::slice_w, *empty = full + RING, *xbar = empty + RING;   // xbar[0]: forward inbox full, xbar[1]: inverse
+    u16 *s_ms = (u16 *)(xbar + 2);
+    const int n = a.n, p = a.p;
+    const int n_pairs = (n + M - 1) / M, n_slices = 8 * n_pairs;
+
+    const long long job = a.job_begin + (long long)(blockIdx.x >> LOGC);      // grid = exactly C CTAs per job
+    const int node = a.node_begin + (int)(job / a.B);
+    const long long inst = job % a.B;
+    {
+        const u16 *ms = a.ms + ((size_t)(a.bs_lc[node] - a.lc_begin) * a.B + inst) * (size_t)(n + 1);
+        for (int i = tid; i <= n; i += Cf::THREADS) s_ms[i] = ms[i];
+    }
+    const int tab0 = a.bs_tab_ptr[node], tabL = a.bs_tab_ptr[node + 1] - tab0, mode = a.bs_mode[node];
+    auto psw = [](u32 x) { return x ^ (((x >> 4) ^ (x >> 8)) & 15u); };
+    for (int i = tid; i < 2 * N; i += Cf::THREADS) PSI[psw((u32)i)] = a.psi_pow[i];
+    for (int i = 1 + tid; i < Ns; i += Cf::THREADS) {
+        ((uint4 *)TWF)[i] = __ldg((const uint4 *)a.psi_rev + ntt_local_src(i, C + h));
+        ((uint4 *)TWI)[i] = __ldg((const uint4 *)a.psi_rev + ntt_local_src(i, 2 * C - 1 - h));
+    }
+    fq_tw cw[C];                                                  // cross-stage twiddles psi_rev[1 .. C)
+#pragma unroll
+    for (int i = 1; i < C; i++) cw[i] = fq_tw_load<false>(a.psi_rev + i);
+    cw[0] = cw[1];
+    if (tid == 0) {
+        for (int r = 0; r < RING; r++) { mbar_init(full + r, 1); mbar_init(empty + r, Cf::THREADS / 32); }
+        mbar_init(xbar, 1); mbar_init(xbar + 1, 1);
+    }
+    __syncthreads();
+    cluster_sync_all();                                           // every CTA's barriers exist before anybody stores remotely
+    // key slice `sl` of this CTA: RUNS runs of Ts words, run i at bsk + (sl*RUNS + i)*T + h*Ts
+    auto issue_slice = [&](int sl, int slot) {                    // called by all lanes of warp 0
+        if (lane == 0) mbar_expect_tx(full + slot, (u32)(Cf::slice_w * 8));
+        __syncwarp();
+        fence_proxy_async();
+        for (int i = lane; i < Cf::RUNS; i += 32)
+            tma_load_1d(RNG + (size_t)slot * Cf::slice_w + (size_t)i * Ts, a.bsk + ((size_t)sl * Cf::RUNS + i) * T + (size_t)h * Ts, (u32)(Ts * 8), full + slot);
+    };
+    if (warp == 0) for (int sl = 0; sl < RING && sl < n_slices; sl++) issue_slice(sl, sl);
+    // remote addresses of the inboxes / exchange barriers of every CTA of the cluster
+    u32 r_inf[C], r_ini[C], r_xf[C], r_xi[C];
+#pragma unroll
+    for (int c = 0; c < C; c++) {
+        r_inf[c] = mapa_shared(smem_u32(INF), (u32)c); r_ini[c] = mapa_shared(smem_u32(INI), (u32)c);
+        r_xf[c] = mapa_shared(smem_u32(xbar), (u32)c); r_xi[c] = mapa_shared(smem_u32(xbar + 1), (u32)c);
+    }
+    const u32 send_off = (u32)((((g * 8 + h * R) * Ts) + tau) * 8);    // my R values land in rows h*R + ri of the receiver's inbox
+    const u32 inbox_bytes = (u32)(Cf::inbox_w * 8);
+    // ---- accumulator init in registers: register e = hh*R + ri holds coefficient j = hh*Ns + h*(Ns/C) + ri*Ts + tau of polynomial g
+    rns2 av[8];
+    {
+        const u64 delta = fbs_delta(p), off = fq_mul((u64)mode, delta >> 1);
+        const int bt = s_ms[n];
+#pragma unroll
+        for (int e = 0; e < 8; e++) {
+            const int j = (e / R) * Ns + h * (Ns / C) + (e % R) * Ts + tau;
+            u64 val = 0;
+            if (g == K) {
+                int src = j + bt;
+                bool neg = false;
+                if (src >= 2 * N) src -= 2 * N;
+                if (src >= N) { src -= N; neg = true; }
+                int x = (int)((2LL * src * p + N) / (2LL * N));
+                if (x >= p) { x -= p; neg = !neg; }
+                const u64 tvx = (x < tabL) ? (u64)__ldg(a.bs_tab + tab0 + x) : 0;
+                const u64 F = fq_sub(fq_mul(tvx, delta), off);
+                val = neg ? fq_neg(F) : F;
+            }
+            av[e] = rns_from_int(val);
+        }
+    }
+    const int bar_g = 1 + g;
+    auto gsync = [bar_g] { bar_sync_named(bar_g, Ts); };
+    const int bar_x = 1 + G + (tau >> 5);
+    auto xsync = [bar_x] { bar_sync_named(bar_x, G * 32); };
+    const int beta = a.beta;
+    const u64 rc = 1ULL << (62 - beta);
+    constexpr int SH = LOGNS + 3;
+    constexpr size_t PWB = Cf::s_w * 8;
+    unsigned char *Sb = (unsigned char *)S;
+    u32 bo[LOGNS];
+#pragma unroll
+    for (int lb = 0; lb < LOGNS; lb++) bo[lb] = P::tau_boff(tau, lb) | ((u32)g << SH);
+    static_assert(P::idx(1, 1, P::inv_lb(P::NPASS - 1)) == 1 + Ts && P::idx(1, 1, P::fwd_lb(0)) == 1 + Ts, "local transforms start / end with register e at local index tau + e*Ts");
+    const u32 odd0 = 2u * (__brev((u32)tau_g) >> (32 - (LOGN - 3))) + 1u;
+    u32 koff[G];
+#pragma unroll
+    for (int og = 0; og < G; og++) { int gg = g + og; if (gg >= G) gg -= G; koff[og] = (u32)(((gg * G + g) * Ts + tau) * 8); }
+    int slot = 0; u32 par = 0;
+    const fq_tw *twf = (const fq_tw *)TWF, *twi = (const fq_tw *)TWI;
+
+    for (int t = 0; t < n_pairs; t++) {
+        const u32 xpar = (u32)(t & 1);
+        // ---- decompose, cross butterflies, forward exchange
+        rns2 dg[1][8];
+#pragma unroll
+        for (int e = 0; e < 8; e++) {
+            const u32 tt = rns_crt_hi(av[e]);
+            const u32 d = (u32)fbs_digit1_t(tt, av[e].a, beta, rc);
+            dg[0][e].a = d + FQ_P1;
+            dg[0][e].b = d + FQ_P2;
+        }
+        ntt_cross_fwd<LOGC>(dg[0], cw, a.zero);
+        if (tid == 0) mbar_expect_tx(xbar, inbox_bytes);
+#pragma unroll
+        for (int e = 0; e < 8; e++) st_async_u64(r_inf[e / R] + send_off + (u32)((e % R) * Ts * 8), rns_pack(dg[0][e]), r_xf[e / R]);
+        mbar_wait_cluster(xbar, xpar);
+#pragma unroll
+        for (int e = 0; e < 8; e++) dg[0][e] = rns_unpack(INF[(size_t)(g * 8 + e) * Ts + tau]);
+        // ---- local forward transform of size Ns; spectra (position 8*tau_g + e) to S for the partner groups
+        ntt_fwd1_from<LOGNS, 0, 1, decltype(gsync), true>(dg, tau, Sb, PWB, bo, twf, gsync, true, a.zero);
+#pragma unroll
+        for (int e = 0; e < 8; e++) {
+            const u32 o = bo[0] ^ P::elem_boff(e, 0);
+            dg[0][e].a = r32_fold(dg[0][e].a, 2 * FQ_P1);
+            dg[0][e].b = r32_fold(dg[0][e].b, 2 * FQ_P2);
+            *(u64 *)(Sb + o) = rns_pack(dg[0][e]);
+        }
+        rns2 x[1][8];
+        auto release_slot = [&](int e) {
+            __syncwarp();
+            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(empty + slot)) : "memory");
+            if (warp == 0) {
+                const int nxt = 8 * t + e + RING;
+                if (nxt < n_slices) {
+                    if (lane == 0) mbar_wait(empty + slot, par);
+                    __syncwarp();
+                    issue_slice(nxt, slot);
+                }
+            }
+            if (++slot == RING) { slot = 0; par ^= 1; }
+        };
+        constexpr bool fast_psi = (LOGN - 2 >= 9) && (LOGN + 1 <= 12);
+        constexpr u32 HMUL = 8u * ((1u << (LOGN - 2)) | (fast_psi ? (1u << (LOGN - 2 - 8)) : 0u));
+        u32 PK[NC];
+        {
+            u32 ai[M];
+#pragma unroll
+            for (int i = 0; i < M; i++) ai[i] = (M * t + i < n) ? s_ms[M * t + i] : 0u;
+#pragma unroll
+            for (int c = 0; c < NC; c++) {
+                u32 E = 0;
+#pragma unroll
+                for (int i = 0; i < M; i++) if ((fbs_unroll_mask(M, c) >> i) & 1) E += ai[i];
+                const u32 x0 = (E * odd0) & (2 * N - 1);
+                if constexpr (fast_psi) {
+                    const u32 lo = x0 & ((1u << (LOGN - 2)) - 1);
+                    PK[c] = (8u * (lo ^ (((lo >> 4) ^ (lo >> 8)) & 15u))) | ((x0 >> (LOGN - 2)) << 16) | ((E & 7u) << 20);
+                } else PK[c] = x0 | ((E & 7u) << 20);
+            }
+        }
+        xsync();
+#pragma unroll
+        for (int e = 0; e < 8; e++) {
+            const u32 o = bo[0] ^ P::elem_boff(e, 0);
+            constexpr int BR3[8] = {0, 4, 2, 6, 1, 5, 3, 7};
+            mbar_wait(full + slot, par);
+            const unsigned char *ks = (const unsigned char *)(RNG + (size_t)slot * Cf::slice_w);
+            auto factor = [&](int c) -> rns2 {
+                const u32 pk = PK[c];
+                if constexpr (fast_psi) {
+                    const u32 hh = ((pk >> 16) + (u32)BR3[e] * (pk >> 20)) & 7u;
+                    return rns_split(*(const u64 *)((const unsigned char *)PSI + ((pk & 0xFFFFu) ^ (hh * HMUL))));
+                } else {
+                    const u32 xi = ((pk & 0xFFFFu) + (((u32)BR3[e] * (pk >> 20)) << (LOGN - 2))) & (2 * N - 1);
+                    return rns_split(PSI[psw(xi)]);
+                }
+            };
+            u64 pa[G], pb2[G];
+#pragma unroll
+            for (int c = 0; c < NC; c++) {
+                const rns2 f = factor(c);
+#pragma unroll
+                for (int og = 0; og < G; og++) {
+                    const rns2 kk = rns_split(*(const u64 *)(ks + koff[og] + (size_t)c * G * G * Ts * 8));
+                    if (c == 0) { pa[og] = r32_mulwide(f.a, kk.a); pb2[og] = r32_mulwide(f.b, kk.b); }
+                    else { pa[og] = r32_madwide(f.a, kk.a, pa[og]); pb2[og] = r32_madwide(f.b, kk.b, pb2[og]); }
+                }
+            }
+            u64 oa = 0, ob = 0;
+#pragma unroll
+            for (int og = 0; og < G; og++) {
+                const u32 ba = r32_redc(pa[og], FQ_P1, FQ_P1_INVNEG), bb = r32_redc(pb2[og], FQ_P2, FQ_P2_INVNEG);
+                int gg = g + og; if (gg >= G) gg -= G;
+                const u32 xg = (og == 0) ? 0u : (G == 2) ? (1u << SH) : ((u32)(g ^ gg) << SH);
+                const rns2 d = rns_split(*(const u64 *)(Sb + (o ^ xg)));
+                if (og == 0) { oa = r32_mulwide(d.a, ba); ob = r32_mulwide(d.b, bb); }
+                else { oa = r32_madwide(d.a, ba, oa); ob = r32_madwide(d.b, bb, ob); }
+            }
+            x[0][e].a = r32_fold(r32_redc(oa, FQ_P1, FQ_P1_INVNEG), 2 * FQ_P1);
+            x[0][e].b = r32_fold(r32_redc(ob, FQ_P2, FQ_P2_INVNEG), 2 * FQ_P2);
+            release_slot(e);
+        }
+        // ---- local inverse transform, inverse exchange, cross butterflies, accumulate
+        auto after_pass0 = [&] { xsync(); };
+        ntt_inv1_from<LOGNS, 0, 1, decltype(after_pass0), decltype(gsync), true>(x, tau, Sb, PWB, bo, twi, after_pass0, gsync, a.zero);
+        if (tid == 0) mbar_expect_tx(xbar + 1, inbox_bytes);
+#pragma unroll
+        for (int e = 0; e < 8; e++) st_async_u64(r_ini[e / R] + send_off + (u32)((e % R) * Ts * 8), rns_pack(x[0][e]), r_xi[e / R]);
+        mbar_wait_cluster(xbar + 1, xpar);
+#pragma unroll
+        for (int e = 0; e < 8; e++) x[0][e] = rns_unpack(INI[(size_t)(g * 8 + e) * Ts + tau]);
+        ntt_cross_inv<LOGC>(x[0], cw, a.zero);
+#pragma unroll
+        for (int e = 0; e < 8; e++) {
+            av[e].a = r32_csub(r32_fold(av[e].a + x[0][e].a + a.zero, 2 * FQ_P1), FQ_P1);
+            av[e].b = r32_csub(r32_fold(av[e].b + x[0][e].b + a.zero, 2 * FQ_P2), FQ_P2);
+        }
+    }
+    // ---- K3: sample extraction straight from the registers (every CTA writes the coefficients it owns), fused peer stores
+    {
+        const size_t CT = (size_t)K * N + 1;
+        const size_t off = ((size_t)a.bs_slot[node] * a.B + inst) * CT;
+        u64 *out = a.wires + off;
+#pragma unroll
+        for (int e = 0; e < 8; e++) {
+            const int j = (e / R) * Ns + h * (Ns / C) + (e % R) * Ts + tau;
+            if (g < K) {                                             // mask: out[g*N + jj] = (jj == 0 ? a_0 : -a_{N-jj}), jj = (N - j) mod N
+                const int jj = (j == 0) ? 0 : N - j;
+                const u64 val = rns_to_int(j == 0 ? av[e] : rns_neg(av[e]));
+                out[(size_t)g * N + jj] = val;
+                for (int pr = 0; pr < a.n_peers; pr++) a.peer_wires[pr][off + (size_t)g * N + jj] = val;
+            } else if (j == 0) {
+                const u64 val = fq_add(rns_to_int(av[e]), fq_mul((u64)mode, fbs_delta(p) >> 1));
+                out[(size_t)K * N] = val;
+                for (int pr = 0; pr < a.n_peers; pr++) a.peer_wires[pr][off + (size_t)K * N] = val;
+            }
+            if (a.tap_acc) a.tap_acc[(size_t)job * G * N + (size_t)g * N + j] = rns_to_int(av[e]);
+        }
+    }
+    cluster_sync_all();                                           // nobody leaves while a neighbour may still address its shared memory
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Device-side level hand-off for node-sharded multi-GPU runs.  Every rank's wire replica ends in a
+// flag page: flags[r] = number of levels rank r has completed.  After a level's blind rotation (whose epilogue stored the
+// outputs into every peer replica) k_level_signal publishes the new epoch into every peer's page with a system-scope
+// release; before the next level's lincomb k_level_wait spins with system-scope acquires until every rank has published
+// it.  The spin is bounded (FBS_SYNC_TIMEOUT_NS): on timeout it raises *err and lets the stream continue, so a lost peer
+// shows up as an error code instead of a hung GPU.
+// ------------------------------------------------------------------------------------------------------
+#define FBS_FLAG_PAGE 4096
+#ifndef FBS_SYNC_TIMEOUT_NS
+#define FBS_SYNC_TIMEOUT_NS 20000000000ULL
+#endif
+struct LevelPeers { int n; u64 *flags[8]; };
+__global__ void k_level_signal(LevelPeers lp, int rank, u64 epoch)
+{
+    __threadfence_system();                       // the preceding kernels' peer stores are ordered before the flags
+    if ((int)threadIdx.x < lp.n)
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(lp.flags[threadIdx.x] + rank), "l"(epoch) : "memory");
+}
+__global__ void k_level_wait(const u64 *flags, int world, int rank, u64 epoch, int *err)
+{
+    const int r = threadIdx.x;
+    if (r < world && r != rank) {
+        u64 t0, t1, v;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        for (;;) {
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flags + r) : "memory");
+            if (v >= epoch) break;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            if (t1 - t0 > FBS_SYNC_TIMEOUT_NS) { atomicExch(err, 1 + r); break; }
+            __nanosleep(200);
+        }
+    }
+    __syncwarp();
+    __threadfence_system();
+}
+
+// ------------------------------------------------------------------------------------------------------
 // cleartext evaluator: the reference's hot loop (fbs_exec_env.py:215-220) as one thread per instance
 // wire values live in vals[slot][B] (uint8) so that neighbouring threads touch neighbouring bytes
 // ------------------------------------------------------------------------------------------------------

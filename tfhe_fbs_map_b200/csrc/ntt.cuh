@@ -147,6 +147,70 @@ FQ_HD void ntt_inv_pass(rns2 (&x)[8], int tau, const fq_tw *__restrict__ psi_inv
     ntt_inv_pass_n<LOGN, PASS, 1>(*reinterpret_cast<rns2(*)[1][8]>(&x), tau, psi_inv_rev, z);
 }
 
+// ---- cluster-split transform: one polynomial spread over C = 2^LOGC CTAs (k_blind_rotate_cl) ----------
+// Index j = h*Ns + r, Ns = N/C.  The first LOGC forward stages (index bits LOGN-1 .. LOGN-LOGC) couple the C sub-blocks h at
+// equal r; after them sub-block h is an independent transform of size Ns whose twiddles are the entries
+// psi_rev[(C + h)*m + blk] of the full table (m, blk: the sub-transform's own block size / block index).  So CTA h runs the
+// ordinary NttPlan<LOGN-LOGC> passes on a LOCAL table  TWF[m + x] = psi_rev[(C + h)*m + x]  (x < m; m = 1, 2, .., Ns/2),  and
+// the mirrored inverse passes on  TWI[m + x] = psi_rev[(2C - 1 - h)*m + x]  (reads TWI[2m - 1 - ti] = psi_rev[(2C - h)*m - 1 - ti]
+// = the mirror image of full-table index C*m + h*m + ti).  In the coefficient domain a thread owns the C sub-block values of
+// R = 8/C residues r (register e = h*R + ri), so the cross stages are register butterflies with compile-time twiddle
+// indices psi_rev[m + (h >> (s+1))], m = 2^(LOGC-1-s); between the cross stages and the local passes the C CTAs exchange
+// registers through distributed shared memory (thread tau of CTA c <-> thread tau of CTA h: a C x C block transpose).
+FQ_HD int ntt_local_src(int i, int hpre)              // full-table index of local-table entry i (1 <= i < Ns): hpre*m + x
+{
+    int m = 1;
+    while (2 * m <= i) m *= 2;
+    return hpre * m + (i - m);
+}
+template <int LOGC>
+FQ_HD void ntt_cross_fwd(rns2 (&x)[8], const fq_tw *__restrict__ cw /* psi_rev[0 .. C) */, u32 z = 0)
+{
+    constexpr int C = 1 << LOGC, R = 8 / C;
+#pragma unroll
+    for (int s = LOGC - 1; s >= 0; s--) {
+        const int m = 1 << (LOGC - 1 - s);
+#pragma unroll
+        for (int h0 = 0; h0 < C; h0++) {
+            if (h0 & (1 << s)) continue;
+            const int h1 = h0 | (1 << s);
+            const fq_tw w = cw[m + (h0 >> (s + 1))];
+#pragma unroll
+            for (int ri = 0; ri < R; ri++) {
+                const int e0 = h0 * R + ri, e1 = h1 * R + ri;
+                const u32 ua = r32_fold(x[e0].a, 2 * FQ_P1), va = r32_mul_shoup(x[e1].a, w.w1, w.ws1, FQ_P1);
+                const u32 ub = r32_fold(x[e0].b, 2 * FQ_P2), vb = r32_mul_shoup(x[e1].b, w.w2, w.ws2, FQ_P2);
+                x[e0].a = ua + va + z; x[e1].a = ua - va + z + 2 * FQ_P1;
+                x[e0].b = ub + vb + z; x[e1].b = ub - vb + z + 2 * FQ_P2;
+            }
+        }
+    }
+}
+template <int LOGC>
+FQ_HD void ntt_cross_inv(rns2 (&x)[8], const fq_tw *__restrict__ cw /* psi_rev[0 .. C), read mirrored */, u32 z = 0)
+{
+    constexpr int C = 1 << LOGC, R = 8 / C;
+#pragma unroll
+    for (int s = 0; s < LOGC; s++) {
+        const int m = 1 << (LOGC - 1 - s);
+#pragma unroll
+        for (int h0 = 0; h0 < C; h0++) {
+            if (h0 & (1 << s)) continue;
+            const int h1 = h0 | (1 << s);
+            const fq_tw w = cw[2 * m - 1 - (h0 >> (s + 1))];
+#pragma unroll
+            for (int ri = 0; ri < R; ri++) {
+                const int e0 = h0 * R + ri, e1 = h1 * R + ri;
+                const u32 ua = x[e0].a, va = x[e1].a, ub = x[e0].b, vb = x[e1].b;
+                x[e0].a = r32_fold(ua + va + z, 2 * FQ_P1);
+                x[e1].a = r32_mul_shoup(va - ua + 2 * FQ_P1, w.w1, w.ws1, FQ_P1);
+                x[e0].b = r32_fold(ub + vb + z, 2 * FQ_P2);
+                x[e1].b = r32_mul_shoup(vb - ub + 2 * FQ_P2, w.w2, w.ws2, FQ_P2);
+            }
+        }
+    }
+}
+
 #if defined(__CUDACC__)
 // ---- device drivers: transposes through two alternating swizzled buffers -------------------------------
 // `sync` is a callable that synchronises the T threads working on this polynomial.

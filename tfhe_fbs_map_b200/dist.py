@@ -46,10 +46,10 @@ class B200Engine:
         self.ct_words = backend.params.ct_words
         self.stream = torch_mod.cuda.current_stream().cuda_stream
 
-    def encrypt(self, bits: np.ndarray, inst_offset=0, total=None):
+    def encrypt(self, bits: np.ndarray, inst_offset=0, total=None, enc_seed=None):
         d_in = self.torch.from_numpy(np.ascontiguousarray(bits, dtype=np.uint8)).to(self.wires.device)
         self.be.encrypt_inputs(self.cp, d_in.data_ptr(), self.B, self.wires.data_ptr(), stream=self.stream,
-                               inst_offset=inst_offset, total=total or self.B)
+                               inst_offset=inst_offset, total=total or self.B, enc_seed=enc_seed)
         self.torch.cuda.current_stream().synchronize()
 
     def run_level(self, level, node_begin, node_end):
@@ -69,22 +69,38 @@ class B200Engine:
 
 class FusedB200Engine(B200Engine):
     """Node-sharded engine whose blind-rotation epilogue stores every output ciphertext into all peers' wire replicas
-    (peer-mapped NVLink stores): the compute step and the exchange are ONE kernel, the host only barriers per level.
-    The wire buffer is a cudaMalloc allocation of the library, shared between the per-GPU processes by CUDA IPC."""
+    (peer-mapped NVLink stores): the compute step and the exchange are ONE kernel, and the levels are ordered ON THE
+    DEVICE (per-level epoch flags in the peers' flag pages, ``fbs_set_peers``): the host neither synchronises nor barriers
+    between levels.  The wire buffer is a cudaMalloc allocation of the library, shared between the per-GPU processes by
+    CUDA IPC.  Use as a context manager (or call ``close()``): the peer binding is dropped even if a level raises."""
 
     fused = True
 
-    def __init__(self, backend, cprog, B, torch_mod, dist, world, rank):
+    def __init__(self, backend, cprog, B, torch_mod, dist, world, rank, handoff="device"):
+        """``handoff``: "device" (default) = per-level epoch flags, no host sync between levels; "host" = round-1 behaviour
+        kept for A/B measurements: ``torch.cuda.synchronize()`` + ``dist.barrier()`` after every level."""
+        assert handoff in ("device", "host")
         self.be, self.cp, self.B, self.torch = backend, cprog, B, torch_mod
         self.ct_words = backend.params.ct_words
         self.stream = torch_mod.cuda.current_stream().cuda_stream
         self.nbytes = backend.wires_bytes(cprog, B)
-        self.ptr = backend.wires_alloc(self.nbytes)
-        handles = [None] * world
-        dist.all_gather_object(handles, backend.ipc_export(self.ptr))
-        self.peer_ptrs = [backend.ipc_import(h) for r, h in enumerate(handles) if r != rank]
-        backend.set_peers(self.peer_ptrs)
-        self.dist, self.world, self.rank = dist, world, rank
+        self.dist, self.world, self.rank, self.handoff = dist, world, rank, handoff
+        self.ptr, self.peer_ptrs = backend.wires_alloc(self.nbytes), []
+        try:
+            handles = [None] * world
+            dist.all_gather_object(handles, backend.ipc_export(self.ptr))
+            self.peer_ptrs = [backend.ipc_import(h) for r, h in enumerate(handles) if r != rank]
+            backend.set_peers(self.ptr, self.nbytes, self.peer_ptrs, rank if handoff == "device" else -1)
+            dist.barrier()                     # every rank's flag page is zeroed before anybody signals
+        except Exception:
+            self.close(collective=False)
+            raise
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close(collective=exc[0] is None)
 
     class _Ptr:
         def __init__(self, p):
@@ -97,13 +113,19 @@ class FusedB200Engine(B200Engine):
     def wires(self):
         return FusedB200Engine._Ptr(self.ptr)
 
-    def encrypt(self, bits, inst_offset=0, total=None):
+    def encrypt(self, bits, inst_offset=0, total=None, enc_seed=None):
         d_in = self.torch.from_numpy(np.ascontiguousarray(bits, dtype=np.uint8)).cuda()
-        self.be.encrypt_inputs(self.cp, d_in.data_ptr(), self.B, self.ptr, stream=self.stream, inst_offset=inst_offset, total=total or self.B)
+        self.be.encrypt_inputs(self.cp, d_in.data_ptr(), self.B, self.ptr, stream=self.stream, inst_offset=inst_offset, total=total or self.B,
+                               enc_seed=enc_seed)
         self.torch.cuda.synchronize()
+        self.dist.barrier()                    # inputs are in place on every replica before any level starts
 
     def run_level(self, level, node_begin, node_end):
+        # called for EVERY level on every rank (also with an empty range): the call carries the level's wait + signal
         self.be.run_level(self.cp, level, self.B, self.ptr, node_begin, node_end, stream=self.stream)
+        if self.handoff == "host":
+            self.torch.cuda.synchronize()      # this rank's peer stores are complete ...
+            self.dist.barrier()                # ... and so are everybody else's
 
     def decrypt(self):
         n_out = len(self.cp.program.output_names)
@@ -112,16 +134,30 @@ class FusedB200Engine(B200Engine):
         self.torch.cuda.synchronize()
         return d_out.cpu().numpy()
 
-    def level_barrier(self):
-        self.torch.cuda.synchronize()          # this rank's peer stores are complete ...
-        self.dist.barrier()                    # ... and so are everybody else's
+    def finish(self):
+        """End of a run: this rank's last level has completed AND every peer's stores into this replica have landed."""
+        if self.handoff == "host":
+            return
+        self.be.run_level_sync(self.ptr, stream=self.stream)
+        self.torch.cuda.synchronize()
+        lost = self.be.sync_status()
+        if lost:
+            raise RuntimeError(f"device-side level hand-off timed out waiting for rank {lost - 1}")
 
-    def close(self):
-        self.be.set_peers([])
-        for p in self.peer_ptrs:
-            self.be.ipc_close(p)
-        self.dist.barrier()
-        self.be.wires_free(self.ptr)
+    def close(self, collective=True):
+        if self.ptr is None:
+            return
+        try:
+            self.torch.cuda.synchronize()
+        finally:
+            self.be.set_peers(None, 0, [], 0)
+            for p in self.peer_ptrs:
+                self.be.ipc_close(p)
+            self.peer_ptrs = []
+            if collective:
+                self.dist.barrier()            # nobody still stores into a buffer that is about to be freed
+            self.be.wires_free(self.ptr)
+            self.ptr = None
 
 
 def run_node_sharded(engine, program, dist, world: int, rank: int, in_place: bool = True):
@@ -136,12 +172,12 @@ def run_node_sharded(engine, program, dist, world: int, rank: int, in_place: boo
         b0, b1 = int(a["bs_level_ptr"][lv]), int(a["bs_level_ptr"][lv + 1])
         width = b1 - b0
         nb, ne, chunk = level_node_range(width, world, rank)
-        if ne > nb:
+        fused = getattr(engine, "fused", False) and world > 1
+        if ne > nb or fused:                     # fused: an empty range still waits for / signals the level on the device
             engine.run_level(lv, nb, ne)
         if world == 1:
             continue
-        if getattr(engine, "fused", False):      # outputs already sit in every replica: only order the levels
-            engine.level_barrier()
+        if fused:                                # outputs already sit in every replica, levels are ordered by device flags
             exchanged += chunk * world * engine.B * engine.ct_words
             continue
         first_slot = int(a["bs_slot"][b0])
@@ -153,6 +189,8 @@ def run_node_sharded(engine, program, dist, world: int, rank: int, in_place: boo
             parts = [engine.slot_view(first_slot + r * chunk, chunk) for r in range(world)]
             dist.all_gather(parts, mine.clone())
         exchanged += region.numel()
+    if getattr(engine, "fused", False) and world > 1:
+        engine.finish()
     return exchanged
 
 

@@ -32,7 +32,7 @@ class CProgDesc(ctypes.Structure):
     _P8 = ctypes.POINTER(ctypes.c_uint8)
     _fields_ = [("p", ctypes.c_int32), ("n_inputs", ctypes.c_int32), ("n_lincombs", ctypes.c_int32),
                 ("n_boots", ctypes.c_int32), ("n_levels", ctypes.c_int32), ("n_slots", ctypes.c_int32),
-                ("n_outputs", ctypes.c_int32), ("reserved", ctypes.c_int32),
+                ("n_outputs", ctypes.c_int32), ("contiguous_levels", ctypes.c_int32),
                 ("lc_level_ptr", _P32), ("bs_level_ptr", _P32),
                 ("lc_ptr", _P32), ("lc_slot", _P32), ("lc_coef", _P32), ("lc_const", _P32),
                 ("bs_lc", _P32), ("bs_slot", _P32), ("bs_tab_ptr", _P32), ("bs_tab", _P8), ("bs_mode", _P32),
@@ -94,6 +94,7 @@ class Program:
         d = CProgDesc()
         d.p, d.n_inputs, d.n_lincombs, d.n_boots = self.p, self.n_inputs, self.n_lincombs, self.n_boots
         d.n_levels, d.n_slots, d.n_outputs = self.n_levels, self.n_slots, len(self.output_names)
+        d.contiguous_levels = 1 if self.contiguous_levels else 0
         for name, _ in CProgDesc._fields_[8:]:
             arr = a[name]
             ct = ctypes.c_uint8 if arr.dtype == np.uint8 else ctypes.c_int32
