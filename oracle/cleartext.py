@@ -33,6 +33,27 @@ def lut_eval(env, input_values):
     return {name: wire[out.name] for name, out in env.outputs.items()}   # :225-229
 
 
+def lut_eval_literal(env, input_values):
+    """The reference's hot loop LITERALLY (fbs_exec_env.py:208-229): per-element Python lambda through ``np.fromiter`` for
+    every bootstrap (:218-220), ``np.sum(list(map(lambda ...)))`` for every lincomb (:215-217).  This is what the reference's
+    CPU path costs; ``lut_eval`` above is value-identical but vectorised.  Used for bench.py's config-1 baseline line when
+    /root/reference is not mounted (the GPU box)."""
+    wire_values = {"0": 0, "1": 1}
+    for instr in env.instructions:
+        k = _kind(instr)
+        if k == "Input":
+            val = np.array(input_values[instr.name]).reshape(-1)
+        elif k == "LinearProd":
+            val = np.sum(list(map(lambda cn: cn[0] * wire_values[cn[1].name], instr.coef_vals)), axis=0) + instr.const_coef
+        elif k == "Bootstrap":
+            table = instr.table
+            val = np.fromiter(map(lambda v: table[v], wire_values[instr.val.name]), dtype=int)
+        else:
+            raise AssertionError("Unknown instruction")
+        wire_values[instr.name] = val
+    return {name: wire_values[out.name] for name, out in env.outputs.items()}
+
+
 def bit_eval(env, input_values):
     wire = {"0": 0, "1": 1}                                           # bit_exec_env.py:174
     for instr in env.instructions:

@@ -175,6 +175,15 @@ template <class T> static int grow(T **p, size_t *cap, size_t need)
     *cap = want;
     return FBS_OK;
 }
+// Host -> device copy that has LANDED when it returns.  A plain cudaMemcpy from pageable memory may return once the data sits in
+// the staging buffer, before the DMA to the device completes; kernels on this library's NON-BLOCKING streams are not ordered
+// after the legacy default stream, so they could read stale memory (seen: the last ciphertexts of a parity-tap batch).
+static cudaError_t h2d_sync(void *dst, const void *src, size_t bytes)
+{
+    cudaError_t e = cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) return e;
+    return cudaStreamSynchronize(0);
+}
 static u32 bitrev32(u32 x, int bits) { u32 r = 0; for (int i = 0; i < bits; i++) { r = (r << 1) | (x & 1); x >>= 1; } return r; }
 
 // ------------------------------------------------------------------------------------------------------
@@ -254,21 +263,21 @@ static int ctx_create_impl(const fbs_params *params, int device, uint64_t seed, 
         u64 x1 = 1, x2 = 1;
         for (int x = 0; x < 2 * N; x++) { pp[x] = (x1 - 1) | ((x2 - 1) << 32); x1 = x1 * ps1 % FQ_P1; x2 = x2 * ps2 % FQ_P2; }   // psi^x - 1 (psi^x >= 1)
         CKR(dev_alloc(&c->d_psi_pow, 2 * (size_t)N));
-        CK(cudaMemcpy(c->d_psi_pow, pp.data(), 16 * (size_t)N, cudaMemcpyHostToDevice));
+        CK(h2d_sync(c->d_psi_pow, pp.data(), 16 * (size_t)N));
     }
     for (int i = 0; i < N; i++) {
         pr[i] = fq_tw{w[0][i], shoup32_host(w[0][i], FQ_P1), w[1][i], shoup32_host(w[1][i], FQ_P2)};
         pir[i] = fq_tw{wi[0][i], shoup32_host(wi[0][i], FQ_P1), wi[1][i], shoup32_host(wi[1][i], FQ_P2)};
     }
     CKR(dev_alloc(&c->d_psi_rev, N)); CKR(dev_alloc(&c->d_psi_inv_rev, N));
-    CK(cudaMemcpy(c->d_psi_rev, pr.data(), sizeof(fq_tw) * N, cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(c->d_psi_inv_rev, pir.data(), sizeof(fq_tw) * N, cudaMemcpyHostToDevice));
+    CK(h2d_sync(c->d_psi_rev, pr.data(), sizeof(fq_tw) * N));
+    CK(h2d_sync(c->d_psi_inv_rev, pir.data(), sizeof(fq_tw) * N));
     std::vector<u64> gb(8, 0), gk(8, 0);
     for (int j = 0; j < P.bsk_l; j++) gb[j] = fbs_gadget_host(P.bsk_beta, j);
     for (int j = 0; j < P.ks_l; j++) gk[j] = fbs_gadget_host(P.ks_beta, j);
     CKR(dev_alloc(&c->d_gad_bsk, 8)); CKR(dev_alloc(&c->d_gad_ks, 8));
-    CK(cudaMemcpy(c->d_gad_bsk, gb.data(), 64, cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(c->d_gad_ks, gk.data(), 64, cudaMemcpyHostToDevice));
+    CK(h2d_sync(c->d_gad_bsk, gb.data(), 64));
+    CK(h2d_sync(c->d_gad_ks, gk.data(), 64));
     *out = c;
     *partial = nullptr;
     return FBS_OK;
@@ -420,9 +429,9 @@ static int prog_load_impl(fbs_ctx *c, const fbs_prog_desc *d, fbs_prog *g)
         *pc.dst = g->d_i32 + off;
         off += (pc.n + 3) & ~(size_t)3;
     }
-    CK(cudaMemcpy(g->d_i32, host.data(), tot * 4, cudaMemcpyHostToDevice));
+    CK(h2d_sync(g->d_i32, host.data(), tot * 4));
     CKR(dev_alloc(&g->d_tab, (size_t)tabn + 16));
-    if (tabn) CK(cudaMemcpy(g->d_tab, d->bs_tab, tabn, cudaMemcpyHostToDevice));
+    if (tabn) CK(h2d_sync(g->d_tab, d->bs_tab, tabn));
     return FBS_OK;
 }
 extern "C" int fbs_prog_free(fbs_prog *g)
@@ -786,7 +795,7 @@ extern "C" int fbs_debug_ntt(fbs_ctx *c, uint64_t *polys, int64_t count, int32_t
     if (!nf) return fail(FBS_ERR_ARG, "no NTT kernel for this N");
     u64 *d_a = nullptr, *d_b = nullptr; const size_t words = (size_t)count * c->P.N;
     CKR(dev_alloc(&d_a, words)); CKR(dev_alloc(&d_b, words));
-    CK(cudaMemcpy(d_a, polys, words * 8, cudaMemcpyHostToDevice));
+    CK(h2d_sync(d_a, polys, words * 8));
     nf(d_a, d_b, inverse ? 1 : 0, c->d_psi_rev, c->d_psi_inv_rev, c->ninv[0], c->ninv[1], count, c->stream, c->P.k + 1);
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(c->stream));
@@ -801,8 +810,8 @@ extern "C" int fbs_debug_encrypt(fbs_ctx *c, int32_t p, const int32_t *msgs, con
     CK(cudaSetDevice(c->device));
     int32_t *d_m = nullptr; u64 *d_id = nullptr, *d_ct = nullptr; const size_t CT = ct_words(c);
     CKR(dev_alloc(&d_m, count)); CKR(dev_alloc(&d_id, count)); CKR(dev_alloc(&d_ct, (size_t)count * CT));
-    CK(cudaMemcpy(d_m, msgs, count * 4, cudaMemcpyHostToDevice));
-    if (ct_ids) CK(cudaMemcpy(d_id, ct_ids, count * 8, cudaMemcpyHostToDevice));
+    CK(h2d_sync(d_m, msgs, count * 4));
+    if (ct_ids) CK(h2d_sync(d_id, ct_ids, count * 8));
     EncArgs a{};
     a.msgs32 = d_m; a.ct_ids = ct_ids ? d_id : nullptr; a.out = d_ct; a.s_big = c->d_s_big; a.D = c->P.k * c->P.N; a.p = p;
     a.enc_seed = enc_seed; a.noise_scale = c->P.glwe_noise; a.B = 1; a.B_total = 1;
@@ -820,7 +829,7 @@ extern "C" int fbs_debug_decrypt(fbs_ctx *c, int32_t p, const uint64_t *cts, int
     CK(cudaSetDevice(c->device));
     u64 *d_ct = nullptr; int32_t *d_o = nullptr; const size_t CT = ct_words(c);
     CKR(dev_alloc(&d_ct, (size_t)count * CT)); CKR(dev_alloc(&d_o, count));
-    CK(cudaMemcpy(d_ct, cts, (size_t)count * CT * 8, cudaMemcpyHostToDevice));
+    CK(h2d_sync(d_ct, cts, (size_t)count * CT * 8));
     OutArgs a{};
     a.wires = d_ct; a.s_big = c->d_s_big; a.out32 = d_o; a.B = 1; a.D = c->P.k * c->P.N; a.p = p;
     k_decrypt<<<(unsigned)count, 256, 0, c->stream>>>(a);
@@ -845,7 +854,7 @@ extern "C" int fbs_debug_pbs(fbs_ctx *c, int32_t p, const uint64_t *in_cts, cons
         if ((rc = dev_alloc(&d_w, (size_t)2 * count * CT)) != FBS_OK) break;
         if ((rc = dev_alloc(&d_ks, (size_t)(count + 16) * (P.n + 1))) != FBS_OK) break;
         if ((rc = dev_alloc(&d_acc, (size_t)count * (P.k + 1) * P.N)) != FBS_OK) break;
-        if (cudaMemcpy(d_w, in_cts, (size_t)count * CT * 8, cudaMemcpyHostToDevice) != cudaSuccess) { rc = fail(FBS_ERR_CUDA, std::string("debug_pbs H2D: ") + cudaGetErrorString(cudaGetLastError())); break; }
+        if (h2d_sync(d_w, in_cts, (size_t)count * CT * 8) != cudaSuccess) { rc = fail(FBS_ERR_CUDA, std::string("debug_pbs H2D: ") + cudaGetErrorString(cudaGetLastError())); break; }
         if ((rc = run_level_impl(c, g, 0, -1, -1, 1, d_w, st, nullptr, d_ks, d_acc, false)) != FBS_OK) break;
         if (cudaStreamSynchronize(st) != cudaSuccess) { rc = fail(FBS_ERR_CUDA, std::string("debug_pbs: ") + cudaGetErrorString(cudaGetLastError())); break; }
         cudaError_t e = cudaMemcpy(out_cts, d_w + (size_t)count * CT, (size_t)count * CT * 8, cudaMemcpyDeviceToHost);
