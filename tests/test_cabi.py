@@ -47,6 +47,13 @@ def test_library_is_sm100a_with_tma(libpath):
     sass2 = subprocess.run(["cuobjdump", "-sass", "-fun", "_Z15k_blind_rotate2ILi11ELi1ELi2ELi2ELi2EEv6BRArgs", libpath],
                            capture_output=True, text=True).stdout
     assert "UBLKCP" in sass2 and "SYNCS.ARRIVE" in sass2 and "IMAD.HI.U32" in sass2
+    # the DEFAULT instantiation (set A3: three key bits per step, two bootstraps per CTA) and its one-bootstrap tail variant
+    for fun in ("_Z15k_blind_rotate2ILi11ELi1ELi2ELi2ELi3EEv6BRArgs", "_Z15k_blind_rotate2ILi11ELi1ELi1ELi1ELi3EEv6BRArgs"):
+        s3 = subprocess.run(["cuobjdump", "-sass", "-fun", fun, libpath], capture_output=True, text=True).stdout
+        assert "UBLKCP" in s3 and "SYNCS.ARRIVE" in s3 and "IMAD.WIDE.U32" in s3 and "IMAD.HI.U32" in s3, fun
+    # the cluster-split low-latency kernel: remote shared-memory stores with mbarrier completion (st.async), cluster barrier, TMA key ring
+    s4 = subprocess.run(["cuobjdump", "-sass", "-fun", "_Z17k_blind_rotate_clILi11ELi1ELi3ELi2EEv6BRArgs", libpath], capture_output=True, text=True).stdout
+    assert "UBLKCP" in s4 and "UCGABAR" in s4 and ("STAS" in s4 or "ST.ASYNC" in s4 or "STS.ASYNC" in s4), "cluster kernel: no async remote stores in SASS"
 
 
 def test_parameter_validation_needs_no_gpu(libpath):

@@ -92,8 +92,20 @@ static cudaError_t brc_prepare(size_t smem)
     return cudaFuncSetAttribute(k_blind_rotate_cl<LOGN, K, M, LOGC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 }
 template <int LOGN, int K, int M, int LOGC> static size_t brc_smem(int n) { return BRCCfg<LOGN, K, M, LOGC>::smem_bytes(n); }
-struct BRCVariant { int logN, k, unr, logC; size_t (*smem)(int n); br_launch_fn launch; cudaError_t (*prepare)(size_t smem); };
-#define BRCV(LOGN, K, M, LOGC) { LOGN, K, M, LOGC, brc_smem<LOGN, K, M, LOGC>, brc_launch<LOGN, K, M, LOGC>, brc_prepare<LOGN, K, M, LOGC> }
+// how many clusters of this kernel the device can hold at once (the hardware may strand SMs: 33 clusters of 4 on a 148-SM B200)
+template <int LOGN, int K, int M, int LOGC>
+static cudaError_t brc_max_clusters(size_t smem, int *out)
+{
+    using Cf = BRCCfg<LOGN, K, M, LOGC>;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(1 << LOGC); cfg.blockDim = dim3(Cf::THREADS); cfg.dynamicSmemBytes = smem;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 1 << LOGC; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    return cudaOccupancyMaxActiveClusters(out, k_blind_rotate_cl<LOGN, K, M, LOGC>, &cfg);
+}
+struct BRCVariant { int logN, k, unr, logC; size_t (*smem)(int n); br_launch_fn launch; cudaError_t (*prepare)(size_t smem); cudaError_t (*max_clusters)(size_t smem, int *out); };
+#define BRCV(LOGN, K, M, LOGC) { LOGN, K, M, LOGC, brc_smem<LOGN, K, M, LOGC>, brc_launch<LOGN, K, M, LOGC>, brc_prepare<LOGN, K, M, LOGC>, brc_max_clusters<LOGN, K, M, LOGC> }
 static const BRCVariant g_brc_variants[] = {
     BRCV(11, 1, 3, 1), BRCV(11, 1, 3, 2), BRCV(11, 1, 3, 3),      // sets A3 / toy5v: clusters of 2, 4, 8
     BRCV(11, 1, 2, 1), BRCV(11, 1, 2, 2), BRCV(11, 1, 2, 3),      // sets A2 / toy5u
@@ -117,7 +129,8 @@ struct fbs_ctx {
     bool have_keys = false;
     const BRVariant *br = nullptr; size_t br_smem = 0;        // widest variant (most bootstraps per CTA)
     const BRVariant *br1 = nullptr; size_t br1_smem = 0;      // one bootstrap per CTA, for launches with <= sm_count jobs
-    const BRCVariant *brc[4] = {}; size_t brc_smem[4] = {};   // [log2 C]: one bootstrap per cluster of C CTAs (launches with <= sm_count / C jobs)
+    const BRCVariant *brc[4] = {}; size_t brc_smem[4] = {};   // [log2 C]: one bootstrap per cluster of C CTAs ...
+    int brc_max[4] = {};                                      // ... for launches of at most this many jobs (co-resident clusters)
     int cluster_mode = 0;                                     // 0 auto, 1 never, 2 / 4 / 8 force that cluster size (fbs_ctx_set_cluster)
     u8 *d_s_lwe = nullptr, *d_s_big = nullptr;
     u64 *d_ksk = nullptr, *d_colsum = nullptr, *d_bsk = nullptr, *d_bsk_coef = nullptr;
@@ -239,7 +252,9 @@ static int ctx_create_impl(const fbs_params *params, int device, uint64_t seed, 
         const size_t sm = v.smem(P.n);
         if (sm > (size_t)prop.sharedMemPerBlockOptin) continue;
         CK(v.prepare((size_t)prop.sharedMemPerBlockOptin));
-        c->brc[v.logC] = &v; c->brc_smem[v.logC] = sm;
+        int mc = 0;
+        if (v.max_clusters(sm, &mc) != cudaSuccess || mc < 1) { cudaGetLastError(); continue; }
+        c->brc[v.logC] = &v; c->brc_smem[v.logC] = sm; c->brc_max[v.logC] = mc;
     }
     CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     for (auto &e : c->ev) CK(cudaEventCreate(&e));
@@ -548,7 +563,7 @@ static int run_level_impl(fbs_ctx *c, fbs_prog *g, int level, int nb, int ne, in
     // Fewer jobs than SMs: split each bootstrap over a cluster of C CTAs (largest C in {8, 4, 2} whose jobs * C CTAs still fit
     // one wave), cutting the latency of the level instead of idling SMs.  Results are bit-identical to the one-CTA kernels.
     int logC = 0;
-    if (c->cluster_mode == 0) { for (int lc = 3; lc >= 1; lc--) if (c->brc[lc] && (jobs << lc) <= c->sm_count) { logC = lc; break; } }
+    if (c->cluster_mode == 0) { for (int lc = 3; lc >= 1; lc--) if (c->brc[lc] && jobs <= c->brc_max[lc]) { logC = lc; break; } }
     else if (c->cluster_mode > 1) { for (int lc = 1; lc <= 3; lc++) if ((1 << lc) == c->cluster_mode && c->brc[lc]) logC = lc; }
     if (logC) CK(c->brc[logC]->launch(ba, jobs, c->brc_smem[logC], st));
     else if (c->br1 != c->br && tail > 0 && tail <= c->sm_count) {

@@ -159,8 +159,9 @@ __global__ void __launch_bounds__(256) k_bsk_body(u64 *bsk, int k, int N, int l,
 //                               transform's 1/N folded in), packed (mod p1 | mod p2 << 32), stored SWIZZLED for the
 //                               blind-rotate kernel
 //                       mode 3: key-unrolled BSK preprocessing: as mode 2 with the caller's scale 2^64/N (Montgomery form
-//                               twice: the key goes through two reductions), stored as [key pair][element e][c][u][v][tau]: the
-//                               words k_blind_rotate2 needs for one element are one contiguous slice (one bulk copy)
+//                               twice: the key goes through two reductions), stored as [key group][element e][tau >> 5][c][u][v][tau & 31]:
+//                               the words k_blind_rotate2 needs for one element are one contiguous slice (one bulk copy), and so are
+//                               the words of any contiguous range of 32-thread blocks (k_blind_rotate_cl: one CTA of a cluster)
 // ------------------------------------------------------------------------------------------------------
 template <int LOGN>
 __global__ void __launch_bounds__(NttPlan<LOGN>::T) k_ntt(const u64 *__restrict__ in, u64 *__restrict__ out, int mode,
@@ -203,7 +204,9 @@ __global__ void __launch_bounds__(NttPlan<LOGN>::T) k_ntt(const u64 *__restrict_
                 if (mode == 3) {                                          // polynomial (ggsw = 3t + c, u, v); id = 8*tau + e
                     const int G1 = g1 & 0xFF, ns = g1 >> 8;              // k+1 and GGSW per key group (3 or 7), packed by the host
                     const int pv = blockIdx.x % (G1 * G1), ggsw = blockIdx.x / (G1 * G1), t = ggsw / ns, c = ggsw % ns;
-                    out[(((size_t)t * 8 + e) * ns + c) * G1 * G1 * P::T + (size_t)pv * P::T + tau] = rns_pack(v);
+                    // [key group t][element e][block of 32 thread positions tau >> 5][c][pv][tau & 31]: everything a CTA -- or one CTA of a
+                    // cluster that owns a contiguous range of tau blocks -- needs for element e is ONE contiguous run (one bulk copy)
+                    out[((((size_t)t * 8 + e) * (P::T / 32) + (tau >> 5)) * ns * G1 * G1 + (size_t)c * G1 * G1 + pv) * 32 + (tau & 31)] = rns_pack(v);
                 }
                 else dst[P::swz(id)] = rns_pack(v);
             }
@@ -775,8 +778,8 @@ struct BR2Cfg {
 #endif
     static constexpr bool TWS = FBS_TW_SMEM != 0 && M == 2;       // NTT twiddle table in shared memory (16 B per entry); no room at M = 3
     static constexpr size_t tw_w = TWS ? 2 * (size_t)N : 0;
-    // Key slice = every key word the CTA needs for ONE of the 8 elements a thread holds: [c < NC][u < G][v < G][tau < T]; a step
-    // consumes 8 slices in element order.  HBM layout [key pair][element][c][u][v][tau]: one contiguous bulk copy per slice.
+    // Key slice = every key word the CTA needs for ONE of the 8 elements a thread holds: [tau >> 5][c < NC][u < G][v < G][tau & 31]; a
+    // step consumes 8 slices in element order.  HBM layout [key group][element][tau >> 5][c][u][v][tau & 31]: one bulk copy per slice.
     static constexpr size_t slice_w = NC * (size_t)G * G * T;
     static constexpr size_t fixed_b = 8 * (PB * s_w + psi_w + tw_w) + PB * 2048 + 256;   // ms rows budgeted for n < 1024
     static constexpr int R_fit = (int)((227 * 1024 - fixed_b) / (8 * slice_w));
@@ -880,10 +883,10 @@ __global__ void __launch_bounds__((PB / TP) * (K + 1) * (1 << LOGN) / 8, 1) k_bl
     for (int lb = 0; lb < LOGN; lb++) bo[lb] = P::tau_boff(tau, lb) | ((u32)g << SH);
     // NTT output position 8*tau + e holds the evaluation at psi^(2 brev(8 tau + e) + 1) = psi^(odd0 + (brev3(e) << (LOGN-2)))
     const u32 odd0 = 2u * (__brev((u32)tau) >> (32 - (LOGN - 3))) + 1u;
-    // key words of this thread inside a slice: ((c*G + u)*G + g)*T + tau, u = (g + og) mod G
+    // key words of this thread inside a slice: (((tau >> 5)*NC + c)*G*G + u*G + g)*32 + (tau & 31), u = (g + og) mod G
     u32 koff[G];
 #pragma unroll
-    for (int og = 0; og < G; og++) { int gg = g + og; if (gg >= G) gg -= G; koff[og] = (u32)(((gg * G + g) * T + tau) * 8); }
+    for (int og = 0; og < G; og++) { int gg = g + og; if (gg >= G) gg -= G; koff[og] = (u32)((((tau >> 5) * NC * G * G + gg * G + g) * 32 + (tau & 31)) * 8); }
     int slot = 0; u32 par = 0;                                    // ring position of the next slice to consume
 
     for (int t = 0; t < n_pairs; t++) {
@@ -979,7 +982,7 @@ __global__ void __launch_bounds__((PB / TP) * (K + 1) * (1 << LOGN) / 8, 1) k_bl
             for (int c = 0; c < NC; c++) {
                 rns2 kk[G];
 #pragma unroll
-                for (int og = 0; og < G; og++) kk[og] = rns_split(*(const u64 *)(ks + koff[og] + (size_t)c * G * G * T * 8));
+                for (int og = 0; og < G; og++) kk[og] = rns_split(*(const u64 *)(ks + koff[og] + (size_t)c * G * G * 32 * 8));
 #pragma unroll
                 for (int q = 0; q < TP; q++) {
                     const rns2 f = factor(q, c);
@@ -1060,8 +1063,8 @@ __global__ void __launch_bounds__((PB / TP) * (K + 1) * (1 << LOGN) / 8, 1) k_bl
 // Per step two all-to-all exchanges through DISTRIBUTED SHARED MEMORY (st.async into the destination CTA's inbox,
 // completion counted in bytes on that CTA's mbarrier): no cluster-wide barrier inside the loop, the data dependence is the
 // flow control (a CTA cannot send exchange k+1 before it has received everybody's exchange k, and everybody sent that only
-// after consuming what it received before).  The key is streamed by TMA as in k_blind_rotate2 (same HBM layout: per slice
-// NC*G*G runs of Ts words, issued by the lanes of warp 0), ring depth up to 8 slices = one whole step ahead.
+// after consuming what it received before).  The key is streamed by TMA as in k_blind_rotate2 (same HBM layout, blocked by 32
+// thread positions so that a CTA's share of a slice is one contiguous bulk copy), ring depth up to 8 slices = one whole step ahead.
 // Arithmetic, rounding and term order are those of k_blind_rotate2<M>: results are bit-identical.
 // ------------------------------------------------------------------------------------------------------
 template <int LOGN, int K, int M, int LOGC>
@@ -1072,7 +1075,7 @@ struct BRCCfg {
     static constexpr int N = 1 << LOGN, G = K + 1, C = 1 << LOGC, LOGNS = LOGN - LOGC, Ns = N >> LOGC, Ts = Ns / 8, R = 8 / C, T = N / 8;
     static_assert(Ts >= 32 && Ts % 32 == 0, "a polynomial's threads in a CTA are whole warps");
     static constexpr int THREADS = G * Ts;
-    static constexpr int RUNS = NC * G * G;                       // contiguous key runs (Ts words each) per slice
+    static constexpr int RUNS = NC * G * G;                       // key words per thread position and slice
     static constexpr size_t s_w = (size_t)G * Ns;                 // transpose scratch / digit spectra
     static constexpr size_t inbox_w = (size_t)G * 8 * Ts;         // one exchange direction
     static constexpr size_t psi_w = 2 * (size_t)N;
@@ -1096,19 +1099,18 @@ __device__ __forceinline__ void st_async_u64(u32 remote_addr, u64 v, u32 remote_
 {
     asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];" ::"r"(remote_addr), "l"(v), "r"(remote_bar) : "memory");
 }
-// acquire at cluster scope: pairs with the complete_tx of remote st.async.  The spin is bounded: a cluster whose exchange never
-// completes (a lost store would be a bug, not a load condition) traps after FBS_XCHG_TIMEOUT_NS instead of hanging the GPU.
+// Wait for an exchange inbox: the data arrives in THIS CTA's shared memory with the mbarrier's complete_tx, so the ordinary
+// (CTA-scope) acquire of try_wait covers it -- a cluster-scope acquire makes ptxas add CCTL.IVALL (an L1 invalidate that
+// shared memory does not need; measured 4.5 % of the stall samples, profiles/r2_cl4_v1_*).  The spin is bounded: a cluster
+// whose exchange never completes (a lost store would be a bug, not a load condition) traps after FBS_XCHG_TIMEOUT_NS instead of
+// hanging the GPU.
 #ifndef FBS_XCHG_TIMEOUT_NS
 #define FBS_XCHG_TIMEOUT_NS 4000000000ULL
 #endif
 __device__ __forceinline__ void mbar_wait_cluster(u64 *bar, u32 parity)
 {
-    u32 ok;
     u64 t0 = 0;
-    for (;;) {
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-        if (ok) return;
+    while (!mbar_try_wait(bar, parity)) {
         u64 t1;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
         if (t0 == 0) t0 = t1;
@@ -1159,15 +1161,13 @@ __global__ void __launch_bounds__((K + 1) * (1 << (LOGN - LOGC)) / 8, 1) k_blind
     }
     __syncthreads();
     cluster_sync_all();                                           // every CTA's barriers exist before anybody stores remotely
-    // key slice `sl` of this CTA: RUNS runs of Ts words, run i at bsk + (sl*RUNS + i)*T + h*Ts
-    auto issue_slice = [&](int sl, int slot) {                    // called by all lanes of warp 0
-        if (lane == 0) mbar_expect_tx(full + slot, (u32)(Cf::slice_w * 8));
-        __syncwarp();
+    // key slice `sl` of this CTA: the Ts/32 blocks of 32 thread positions it owns are contiguous in HBM: one bulk copy of slice_w words
+    auto issue_slice = [&](int sl, int slot) {                    // called by thread 0
         fence_proxy_async();
-        for (int i = lane; i < Cf::RUNS; i += 32)
-            tma_load_1d(RNG + (size_t)slot * Cf::slice_w + (size_t)i * Ts, a.bsk + ((size_t)sl * Cf::RUNS + i) * T + (size_t)h * Ts, (u32)(Ts * 8), full + slot);
+        mbar_expect_tx(full + slot, (u32)(Cf::slice_w * 8));
+        tma_load_1d(RNG + (size_t)slot * Cf::slice_w, a.bsk + ((size_t)sl * C + h) * Cf::slice_w, (u32)(Cf::slice_w * 8), full + slot);
     };
-    if (warp == 0) for (int sl = 0; sl < RING && sl < n_slices; sl++) issue_slice(sl, sl);
+    if (tid == 0) for (int sl = 0; sl < RING && sl < n_slices; sl++) issue_slice(sl, sl);
     // remote addresses of the inboxes / exchange barriers of every CTA of the cluster
     u32 r_inf[C], r_ini[C], r_xf[C], r_xi[C];
 #pragma unroll
@@ -1216,7 +1216,7 @@ __global__ void __launch_bounds__((K + 1) * (1 << (LOGN - LOGC)) / 8, 1) k_blind
     const u32 odd0 = 2u * (__brev((u32)tau_g) >> (32 - (LOGN - 3))) + 1u;
     u32 koff[G];
 #pragma unroll
-    for (int og = 0; og < G; og++) { int gg = g + og; if (gg >= G) gg -= G; koff[og] = (u32)(((gg * G + g) * Ts + tau) * 8); }
+    for (int og = 0; og < G; og++) { int gg = g + og; if (gg >= G) gg -= G; koff[og] = (u32)((((tau >> 5) * NC * G * G + gg * G + g) * 32 + (tau & 31)) * 8); }
     int slot = 0; u32 par = 0;
     const fq_tw *twf = (const fq_tw *)TWF, *twi = (const fq_tw *)TWI;
 
@@ -1251,13 +1251,9 @@ __global__ void __launch_bounds__((K + 1) * (1 << (LOGN - LOGC)) / 8, 1) k_blind
         auto release_slot = [&](int e) {
             __syncwarp();
             if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(empty + slot)) : "memory");
-            if (warp == 0) {
+            if (tid == 0) {
                 const int nxt = 8 * t + e + RING;
-                if (nxt < n_slices) {
-                    if (lane == 0) mbar_wait(empty + slot, par);
-                    __syncwarp();
-                    issue_slice(nxt, slot);
-                }
+                if (nxt < n_slices) { mbar_wait(empty + slot, par); issue_slice(nxt, slot); }
             }
             if (++slot == RING) { slot = 0; par ^= 1; }
         };
@@ -1303,7 +1299,7 @@ __global__ void __launch_bounds__((K + 1) * (1 << (LOGN - LOGC)) / 8, 1) k_blind
                 const rns2 f = factor(c);
 #pragma unroll
                 for (int og = 0; og < G; og++) {
-                    const rns2 kk = rns_split(*(const u64 *)(ks + koff[og] + (size_t)c * G * G * Ts * 8));
+                    const rns2 kk = rns_split(*(const u64 *)(ks + koff[og] + (size_t)c * G * G * 32 * 8));
                     if (c == 0) { pa[og] = r32_mulwide(f.a, kk.a); pb2[og] = r32_mulwide(f.b, kk.b); }
                     else { pa[og] = r32_madwide(f.a, kk.a, pa[og]); pb2[og] = r32_madwide(f.b, kk.b, pb2[og]); }
                 }

@@ -23,6 +23,8 @@ import sys
 import time
 import traceback
 
+import os
+
 import numpy as np
 
 from .bit_env import BitExecEnv
@@ -43,13 +45,21 @@ def build_parser():
     parser.add_argument("--verbose", "-v", action="count", default=0)
     # additions
     parser.add_argument("--exec", dest="exec_mode", choices=["clear", "b200", "none"], default="clear",
-                        help="self-check backend: cleartext CUDA kernel, encrypted TFHE on B200, or none")
+                        help="self-check backend: cleartext CUDA kernel (falls back to 'none' with a warning when no GPU / library is "
+                             "available, so the reference invocation `map_circuit FILE --fbs_size N` works on any host), encrypted TFHE "
+                             "on B200, or none")
     parser.add_argument("--batch", type=int, default=1000, help="random input vectors for the self-check")
-    parser.add_argument("--param-set", default="A", help="TFHE parameter set for --exec b200")
+    parser.add_argument("--param-set", default=None, help="TFHE parameter set for --exec b200 (default: the library default, A3)")
+    parser.add_argument("--gpus", type=int, default=1,
+                        help="--exec b200: GPUs to use (this process drives GPU 0..gpus-1 in turn for --shard instances; node sharding "
+                             "needs one process per GPU: launch with torchrun, see bench.py --shard nodes)")
+    parser.add_argument("--shard", choices=["instances", "nodes"], default="instances",
+                        help="--exec b200 with several GPUs: split the batch of input vectors (instances, no collective) or each level's "
+                             "bootstraps (nodes, under torchrun)")
     return parser
 
 
-EXTRA_KEYS = ("exec_mode", "batch", "param_set")
+EXTRA_KEYS = ("exec_mode", "batch", "param_set", "gpus", "shard")
 
 
 def main(argv=None):
@@ -76,9 +86,24 @@ def main(argv=None):
     input_vals = {inp.name: np.random.randint(0, 2, (args.batch)) for inp in bit_env.inputs}
     backend = None
     output_values1 = None
+    from . import params as _params
+    if args.param_set is None:
+        args.param_set = _params.DEFAULT_SET
+    backends = []
     if args.exec_mode != "none":
         from . import backend as _be
-        backend = _be.B200Backend(args.param_set, keygen=(args.exec_mode == "b200"))
+        try:
+            n_gpus = max(1, args.gpus) if args.exec_mode == "b200" and args.shard == "instances" else 1
+            backends = [_be.B200Backend(args.param_set, device=d, seed=0xC11 if n_gpus > 1 else None, keygen=(args.exec_mode == "b200"))
+                        for d in range(n_gpus)]
+            backend = backends[0]
+        except (RuntimeError, OSError) as ex:
+            if args.exec_mode == "b200":
+                raise                                                  # the encrypted executor has no CPU fallback
+            # --exec clear is only the self-check of the mapping: the reference CLI has no GPU dependency at all
+            print(f"warning: GPU self-check unavailable ({ex}); continuing with --exec none", file=sys.stderr)
+            args.exec_mode = "none"
+    if args.exec_mode != "none":
         output_values1 = bit_env.eval(input_vals, backend=backend)      # before mapping: the mapper mutates gate tables
 
     start = time.time()
@@ -100,11 +125,29 @@ def main(argv=None):
         t0 = time.time()
         if args.exec_mode == "b200":
             p = max(fbs_size, 2)
-            output_values2 = lut_env.eval(input_vals, fbs_size=p, backend=backend)
-            st = dict(backend.last_stats or {})
+            if args.shard == "nodes" and int(os.environ.get("WORLD_SIZE", "1")) <= 1 and args.gpus > 1:
+                print("warning: --shard nodes needs one process per GPU (torchrun); evaluating on one GPU", file=sys.stderr)
+            if len(backends) > 1:
+                # instance sharding from one process: contiguous slices of the batch, one per GPU, keys replicated by the seed
+                from .dist import instance_shard
+                from concurrent.futures import ThreadPoolExecutor
+                names = [i.name for i in bit_env.inputs]
+
+                def part(r):
+                    off, cnt = instance_shard(args.batch, len(backends), r)
+                    return lut_env.eval({nm: input_vals[nm][off:off + cnt] for nm in names}, fbs_size=p, backend=backends[r]) if cnt else None
+                with ThreadPoolExecutor(len(backends)) as pool:
+                    parts = [x for x in pool.map(part, range(len(backends))) if x is not None]
+                output_values2 = {k: (np.concatenate([np.atleast_1d(x[k]) for x in parts]) if isinstance(parts[0][k], np.ndarray) else parts[0][k])
+                                  for k in parts[0]}
+                st = dict(n_pbs=sum((b.last_stats or {}).get("n_pbs", 0) for b in backends),
+                          ms_total=max((b.last_stats or {}).get("ms_total", 0.0) for b in backends))
+            else:
+                output_values2 = lut_env.eval(input_vals, fbs_size=p, backend=backend)
+                st = dict(backend.last_stats or {})
             wall = time.time() - t0
             n_pbs = st.get("n_pbs", 0)
-            info = dict(exec="b200", param_set=args.param_set, batch=args.batch, n_pbs=n_pbs, wall_s=wall,
+            info = dict(exec="b200", param_set=args.param_set, gpus=len(backends), shard=args.shard, batch=args.batch, n_pbs=n_pbs, wall_s=wall,
                         pbs_per_s=n_pbs / max(st.get("ms_total", 0.0) * 1e-3, 1e-9), evals_per_s=args.batch / max(wall, 1e-9),
                         p_fail_per_pbs=backend.params.p_fail(p, stats["norm2_linprod"]))
             print(json.dumps(info))
