@@ -62,5 +62,19 @@ def test_cluster_split_matches_one_cta_kernels_full_size(pset):
             got = be.debug_pbs(p, cts, tables, lens, modes)
             for a, b, what in zip(base, got, ("out", "ks", "ms", "acc")):
                 assert np.array_equal(a, b), f"{pset} cluster mode {mode}: {what} differs from the one-CTA kernel"
+        # a full wave of paired CTAs plus a 30-job tail: in auto mode the tail runs cluster-split (4 CTAs per bootstrap)
+        count = 2 * be.info()["sm_count"] + 30
+        msgs = rng.integers(0, 2 * p, count).astype(np.int32)
+        low = rng.integers(0, 2, (count, p)).astype(np.uint8)
+        tables = np.concatenate([low, 1 - low], axis=1)
+        cts = be.debug_encrypt(p, msgs, np.arange(count, dtype=np.uint64), enc_seed=7)
+        lens, modes = np.full(count, 2 * p, np.uint8), np.ones(count, np.int32)
+        be.set_cluster(1)
+        base = be.debug_pbs(p, cts, tables, lens, modes)
+        be.set_cluster(0)
+        got = be.debug_pbs(p, cts, tables, lens, modes)
+        for a, b, what in zip(base, got, ("out", "ks", "ms", "acc")):
+            assert np.array_equal(a, b), f"{pset} cluster-split tail: {what} differs"
+        assert np.array_equal(be.debug_decrypt(p, got[0]), tables[np.arange(count), msgs])
     finally:
         be.close()

@@ -555,21 +555,27 @@ static int run_level_impl(fbs_ctx *c, fbs_prog *g, int level, int nb, int ne, in
     for (int pr = 0; pr < ba.n_peers; pr++) ba.peer_wires[pr] = c->peers[pr];
     ba.lc_begin = lc0; ba.n = n; ba.p = g->p; ba.beta = P.bsk_beta;
     const long long jobs = (long long)(node1 - node0) * B;
-    // Full waves run the widest variant (pb bootstraps per CTA, one CTA per SM).  A last partial wave of at most one job
-    // per SM goes to the one-bootstrap-per-CTA variant instead: it spreads over all SMs and finishes sooner than half-idle
-    // paired CTAs would (and starts as soon as SMs drain from the first launch).
     const long long wave = (long long)c->sm_count * c->br->pb, tail = jobs % wave;
     int n_br_launches = 1;
-    // Fewer jobs than SMs: split each bootstrap over a cluster of C CTAs (largest C in {8, 4, 2} whose jobs * C CTAs still fit
-    // one wave), cutting the latency of the level instead of idling SMs.  Results are bit-identical to the one-CTA kernels.
-    int logC = 0;
-    if (c->cluster_mode == 0) { for (int lc = 3; lc >= 1; lc--) if (c->brc[lc] && jobs <= c->brc_max[lc]) { logC = lc; break; } }
-    else if (c->cluster_mode > 1) { for (int lc = 1; lc <= 3; lc++) if ((1 << lc) == c->cluster_mode && c->brc[lc]) logC = lc; }
+    // Fewer jobs than SMs: split each bootstrap over a cluster of C CTAs, cutting the latency of the launch instead of idling SMs
+    // (measured, set A3: 3.0 ms one CTA, 1.87 ms C = 2, 1.34 ms C = 4, 1.38 ms C = 8 per bootstrap; profiles/r2_latency_*).
+    // Preference 4, 8, 2 among the sizes whose clusters are all co-resident.  Results are bit-identical to the one-CTA kernels.
+    auto pick_cluster = [&](long long nj) -> int {
+        if (c->cluster_mode == 0) { for (int lc : {2, 3, 1}) if (c->brc[lc] && nj <= c->brc_max[lc]) return lc; return 0; }
+        if (c->cluster_mode > 1) for (int lc = 1; lc <= 3; lc++) if ((1 << lc) == c->cluster_mode && c->brc[lc]) return lc;
+        return 0;
+    };
+    const int logC = pick_cluster(jobs);
     if (logC) CK(c->brc[logC]->launch(ba, jobs, c->brc_smem[logC], st));
     else if (c->br1 != c->br && tail > 0 && tail <= c->sm_count) {
+        // Full waves run the widest variant (pb bootstraps per CTA, one CTA per SM).  A last partial wave of at most one job per
+        // SM goes to a narrower kernel instead of half-idle paired CTAs: cluster-split if its clusters fit the chip, else one
+        // bootstrap per CTA (it starts as soon as SMs drain from the first launch).
         if (jobs > tail) { BRArgs bw = ba; CK(c->br->launch(bw, jobs - tail, c->br_smem, st)); n_br_launches = 2; }
         ba.job_begin = jobs - tail;
-        CK(c->br1->launch(ba, jobs, c->br1_smem, st));
+        const int tlc = c->cluster_mode == 0 ? pick_cluster(tail) : 0;
+        if (tlc) CK(c->brc[tlc]->launch(ba, jobs, c->brc_smem[tlc], st));
+        else CK(c->br1->launch(ba, jobs, c->br1_smem, st));
     } else CK(c->br->launch(ba, jobs, c->br_smem, st));
     if (rec) CK(cudaEventRecord(E[3], st));
     if (stats) { stats->n_pbs += jobs; stats->n_launches += 2 + n_br_launches; }
