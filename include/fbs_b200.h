@@ -68,10 +68,17 @@ typedef struct fbs_prog_desc {
     const int32_t *in_slot;       /* [n_inputs]                                                   */
     const int32_t *out_ptr;       /* [n_outputs+1] outputs are lincombs too (1-x, pass-through, const) */
     const int32_t *out_slot, *out_coef, *out_const;
+    /* Multi-value bootstrap: n_groups > 0 switches it on.  A group = the bootstraps of one level that share a
+     * lincomb (reference fbs_exec_env.py:93-100 de-duplicates LinearProds, which makes the sharing visible); they are contiguous
+     * because a level's bootstraps are sorted by lincomb.  One blind rotation per (group, instance) of a table-independent base
+     * polynomial, then one sparse polynomial product + sample extraction per table.  grp_first[g] = first bootstrap of group g
+     * (n_groups + 1 entries), grp_level_ptr[lv] = first group of level lv.  NULL / 0: one rotation per bootstrap. */
+    const int32_t *grp_level_ptr, *grp_first;
+    int32_t n_groups, reserved2;
 } fbs_prog_desc;
 
 typedef struct fbs_run_stats {
-    int64_t n_pbs;         /* bootstraps executed (nodes x instances)          */
+    int64_t n_pbs;         /* blind rotations executed (bootstrap nodes -- or multi-value groups -- x instances) */
     int64_t n_launches;    /* CUDA kernels launched by this call               */
     float ms_total;        /* device time of the call (CUDA events)            */
     float ms_encrypt, ms_lincomb, ms_keyswitch, ms_blind_rotate, ms_decrypt;
@@ -163,6 +170,9 @@ int fbs_debug_ntt(fbs_ctx *ctx, uint64_t *polys_host, int64_t count, int32_t inv
 /* one PBS per input ciphertext with every intermediate: ks [count][n+1] u64, ms [count][n+1] u16, acc [count][(k+1)N] */
 int fbs_debug_pbs(fbs_ctx *ctx, int32_t p, const uint64_t *in_cts, const uint8_t *tables, const uint8_t *tlen,
                   const int32_t *modes, int64_t count, uint64_t *out_cts, uint64_t *tap_ks, uint16_t *tap_ms, uint64_t *tap_acc);
+/* multi-value tap: count inputs, T tables each (tables [count*T][2p]); one rotation per input; out [count*T][kN+1], acc [count][(k+1)N] */
+int fbs_debug_pbs_multi(fbs_ctx *ctx, int32_t p, const uint64_t *in_cts, const uint8_t *tables, const uint8_t *tlen,
+                        const int32_t *modes, int64_t count, int32_t T, uint64_t *out_cts, uint64_t *tap_acc);
 int fbs_debug_encrypt(fbs_ctx *ctx, int32_t p, const int32_t *msgs, const uint64_t *ct_ids, int64_t count, uint64_t enc_seed, uint64_t *out_cts);
 int fbs_debug_decrypt(fbs_ctx *ctx, int32_t p, const uint64_t *cts, int64_t count, int32_t *out);
 

@@ -461,6 +461,63 @@ void ref_pbs(const ref_ctx *c, int p, const u64 *in, const u8 *table, int L, int
     free(ks); free(ms); free(tv); free(acc);
 }
 
+/* ---------------- multi-value bootstrap (several tables on ONE lincomb, fbs_exec_env.py:93-100) ---------
+ * One blind rotation serves every table f applied to the same input: rotate the table-independent base polynomial
+ *     TV0 = H * (1 + X + .. + X^(N-1)),   H = Delta * 2^-1 mod q      (so that (1 - X) * TV0 = 2H = Delta),
+ * then multiply the accumulator by the sparse small polynomial e_f with  Delta * e_f = (1 - X) * TV_f,  where
+ * TV_f[j] = F'(slot(j)), F'(x) = (2 tv[x] - s) * H, is the (negacyclic) step function of the table: e_f is non-zero only at
+ * the p slot boundaries j_x = ceil(N (2x - 1) / 2p), x = 1..p, with e_f[j_x] = tv[x] - tv[x-1] (x < p) and
+ * e_f[j_p] = -(tv[0] + tv[p-1] - s) (the wrap into the negated half).  ACC * e_f = GLWE(X^-mu * TV_f); sample-extract
+ * coefficient 0 and add s * H: the result encrypts tv[mu] * Delta exactly as the one-table bootstrap does (2 H = Delta mod q), with
+ * the blind-rotation noise multiplied by |e_f|^2 <= p + 3 (Carpov, Izabachene, Mollimard, "New techniques for multi-value
+ * input homomorphic evaluation and applications", CT-RSA 2019). */
+static u64 half_delta(int p) { return f_mul(delta_of(p), (GLP + 1) / 2); }          /* H = Delta / 2 mod q (q is odd) */
+void ref_base_test_poly(const ref_ctx *c, int p, u64 *tv) { for (int j = 0; j < c->P.N; j++) tv[j] = half_delta(p); }
+/* e_f as (position, coefficient) pairs; returns their number (<= p) */
+static int table_steps(int N, int p, const u8 *table, int L, int s, int *pos, int *coef)
+{
+    int cnt = 0;
+    for (int x = 1; x <= p; x++) {
+        int tx = (x < p) ? (x < L ? table[x] : 0) : 0, tp = (x - 1 < L) ? table[x - 1] : 0;
+        int e = (x < p) ? tx - tp : -((L > 0 ? table[0] : 0) + tp - s);
+        if (!e) continue;
+        pos[cnt] = (int)(((long long)N * (2 * x - 1) + 2 * p - 1) / (2 * p)); coef[cnt] = e; cnt++;
+    }
+    return cnt;
+}
+/* out = sample_extract( acc * e_f ) + s*H on the body */
+void ref_multi_extract(const ref_ctx *c, int p, const u64 *acc, const u8 *table, int L, int s, u64 *out)
+{
+    int k = c->P.k, N = c->P.N; int pos[128], coef[128];
+    int cnt = table_steps(N, p, table, L, s, pos, coef);
+    u64 *prod = calloc((size_t)(k + 1) * N, 8);
+    for (int v = 0; v <= k; v++) for (int j = 0; j < N; j++) {
+        u64 a = 0;
+        for (int t = 0; t < cnt; t++) {                                   /* (acc * X^pos)[j] = +-acc[(j - pos) mod N] */
+            int idx = j - pos[t]; u64 x = idx >= 0 ? acc[(size_t)v * N + idx] : f_neg(acc[(size_t)v * N + idx + N]);
+            u64 cf = f_from_i64(coef[t]);
+            a = f_add(a, f_mul(x, cf));
+        }
+        prod[(size_t)v * N + j] = a;
+    }
+    ref_sample_extract(c, prod, f_mul((u64)s, half_delta(p)), out);
+    free(prod);
+}
+/* one rotation, T tables: tables [T][tab_stride], outs [T][kN+1]; taps as ref_pbs (tap_acc = accumulator BEFORE the e_f products) */
+void ref_pbs_multi(const ref_ctx *c, int p, const u64 *in, const u8 *tables, int tab_stride, const u8 *tlen, const int32_t *modes, int T,
+                   u64 *outs, u64 *tap_acc)
+{
+    const ref_params *P = &c->P; int n = P->n, k = P->k, N = P->N; size_t CT = (size_t)k * N + 1;
+    u64 *ks = malloc((size_t)(n + 1) * 8); uint16_t *ms = malloc((size_t)(n + 1) * 2);
+    u64 *tv = malloc((size_t)N * 8), *acc = malloc((size_t)(k + 1) * N * 8);
+    ref_keyswitch(c, in, ks); ref_modswitch(c, ks, ms);
+    ref_base_test_poly(c, p, tv);
+    ref_blind_rotate(c, ms, tv, acc);
+    for (int t = 0; t < T; t++) ref_multi_extract(c, p, acc, tables + (size_t)t * tab_stride, tlen[t], modes ? modes[t] : 1, outs + (size_t)t * CT);
+    if (tap_acc) memcpy(tap_acc, acc, (size_t)(k + 1) * N * 8);
+    free(ks); free(ms); free(tv); free(acc);
+}
+
 /* `count` independent bootstraps (one ref_pbs each, OpenMP over the batch): the checker of the full-size batched parity
  * tests.  tables [count][tab_stride], out [count][kN+1], tap_acc [count][(k+1)N] or NULL. */
 void ref_pbs_batch(const ref_ctx *c, int p, const u64 *in, const u8 *tables, int tab_stride, const u8 *tlen, const int32_t *modes,
@@ -478,7 +535,7 @@ void ref_pbs_batch(const ref_ctx *c, int p, const u64 *in, const u8 *tables, int
 
 /* ---------------- levelised program (same flat descriptor as include/fbs_b200.h) ---------------- */
 typedef struct {
-    int32_t p, n_inputs, n_lincombs, n_boots, n_levels, n_slots, n_outputs, reserved;
+    int32_t p, n_inputs, n_lincombs, n_boots, n_levels, n_slots, n_outputs, reserved;   /* reserved: contiguous_levels of the product's descriptor (unused here) */
     const int32_t *lc_level_ptr, *bs_level_ptr;
     const int32_t *lc_ptr, *lc_slot, *lc_coef, *lc_const;
     const int32_t *bs_lc, *bs_slot, *bs_tab_ptr; const u8 *bs_tab; const int32_t *bs_mode;
@@ -488,8 +545,15 @@ typedef struct {
 
 /* Encrypted evaluation of B instances; in [n_inputs][B] bits, out [n_outputs][B] (values mod 2p).
  * Follows the cleartext interpreter's order of evaluation, fbs_exec_env.py:208-229, one level at a time. */
+int ref_eval_prog_mv(const ref_ctx *c, const ref_prog_desc *g, const u8 *in, int64_t B, int64_t inst_offset, int64_t B_total,
+                     u64 enc_seed, u8 *out, int threads, int multi_value);
 int ref_eval_prog(const ref_ctx *c, const ref_prog_desc *g, const u8 *in, int64_t B, int64_t inst_offset, int64_t B_total,
                   u64 enc_seed, u8 *out, int threads)
+{
+    return ref_eval_prog_mv(c, g, in, B, inst_offset, B_total, enc_seed, out, threads, 0);
+}
+int ref_eval_prog_mv(const ref_ctx *c, const ref_prog_desc *g, const u8 *in, int64_t B, int64_t inst_offset, int64_t B_total,
+                     u64 enc_seed, u8 *out, int threads, int multi_value)
 {
     int D = c->P.k * c->P.N; size_t CT = (size_t)D + 1; int p = g->p;
 #ifdef _OPENMP
@@ -510,10 +574,25 @@ int ref_eval_prog(const ref_ctx *c, const ref_prog_desc *g, const u8 *in, int64_
                 for (int o = 0; o < nops; o++) ops[o] = w + (size_t)g->lc_slot[g->lc_ptr[q] + o] * CT;
                 ref_lincomb(c, p, nops, ops, g->lc_coef + g->lc_ptr[q], g->lc_const[q], lc + (size_t)q * CT);
             }
-            for (int q = g->bs_level_ptr[lv]; q < g->bs_level_ptr[lv + 1]; q++) {
+            for (int q = g->bs_level_ptr[lv]; q < g->bs_level_ptr[lv + 1]; ) {
                 int L = g->bs_tab_ptr[q + 1] - g->bs_tab_ptr[q];
-                ref_pbs(c, p, lc + (size_t)g->bs_lc[q] * CT, g->bs_tab + g->bs_tab_ptr[q], L, g->bs_mode[q],
-                        w + (size_t)g->bs_slot[q] * CT, NULL, NULL, NULL);
+                if (!multi_value) {
+                    ref_pbs(c, p, lc + (size_t)g->bs_lc[q] * CT, g->bs_tab + g->bs_tab_ptr[q], L, g->bs_mode[q],
+                            w + (size_t)g->bs_slot[q] * CT, NULL, NULL, NULL);
+                    q++;
+                    continue;
+                }
+                /* multi-value: the maximal run of bootstraps on the same lincomb (they are sorted by lincomb) shares one rotation */
+                int q1 = q; while (q1 < g->bs_level_ptr[lv + 1] && g->bs_lc[q1] == g->bs_lc[q]) q1++;
+                int T = q1 - q; u8 tabs[64 * 64]; u8 lens[64]; int32_t md[64]; u64 *outs = malloc((size_t)T * CT * 8);
+                for (int t = 0; t < T; t++) {
+                    lens[t] = (u8)(g->bs_tab_ptr[q + t + 1] - g->bs_tab_ptr[q + t]); md[t] = g->bs_mode[q + t];
+                    memcpy(tabs + 64 * t, g->bs_tab + g->bs_tab_ptr[q + t], lens[t]);
+                }
+                ref_pbs_multi(c, p, lc + (size_t)g->bs_lc[q] * CT, tabs, 64, lens, md, T, outs, NULL);
+                for (int t = 0; t < T; t++) memcpy(w + (size_t)g->bs_slot[q + t] * CT, outs + (size_t)t * CT, CT * 8);
+                free(outs);
+                q = q1;
             }
         }
         u64 *o = malloc(CT * 8);

@@ -69,6 +69,8 @@ def lib():
         L.ref_sample_extract.argtypes = [vp, vp, u64, vp]
         L.ref_pbs.argtypes = [vp, i32, vp, vp, i32, i32, vp, vp, vp, vp]
         L.ref_pbs_batch.argtypes = [vp, i32, vp, vp, i32, vp, vp, i64, vp, vp, i32]
+        L.ref_pbs_multi.argtypes = [vp, i32, vp, vp, i32, vp, vp, i32, vp, vp]
+        L.ref_eval_prog_mv.argtypes = [vp, ctypes.POINTER(RefProgDesc), vp, i64, i64, i64, u64, vp, i32, i32]
         L.ref_ntt_fwd.argtypes = [vp, vp]
         L.ref_ntt_inv.argtypes = [vp, vp]
         L.ref_polymul_schoolbook.argtypes = [i32, vp, vp, vp]
@@ -188,7 +190,20 @@ class RefTFHE:
                              count, _p(out), None if acc is None else _p(acc), threads)
         return out, acc
 
-    def eval_prog(self, program, in_bits, inst_offset=0, total=None, enc_seed=0, threads=0):
+    def pbs_multi(self, p, ct, tables, tlens, modes=None):
+        """ONE blind rotation, several tables on the same input (multi-value bootstrap): (outs [T][kN+1], acc [k+1][N])."""
+        ps = self.ps
+        ct = np.ascontiguousarray(ct, np.uint64)
+        tables = np.ascontiguousarray(tables, np.uint8)
+        tlens = np.ascontiguousarray(tlens, np.uint8)
+        modes_a = None if modes is None else np.ascontiguousarray(modes, np.int32)
+        T = tables.shape[0]
+        outs = np.zeros((T, self.ct_words), np.uint64)
+        acc = np.zeros((ps.k + 1, ps.N), np.uint64)
+        self.L.ref_pbs_multi(self.ctx, p, _p(ct), _p(tables), tables.shape[1], _p(tlens), None if modes_a is None else _p(modes_a), T, _p(outs), _p(acc))
+        return outs, acc
+
+    def eval_prog(self, program, in_bits, inst_offset=0, total=None, enc_seed=0, threads=0, multi_value=False):
         """program: tfhe_fbs_map_b200.levelize.Program (only its flat arrays are used)."""
         a = program.arrays
         d = RefProgDesc()
@@ -201,5 +216,5 @@ class RefTFHE:
         in_bits = np.ascontiguousarray(in_bits, np.uint8)
         B = in_bits.shape[1]
         out = np.zeros((len(program.output_names), B), np.uint8)
-        self.L.ref_eval_prog(self.ctx, ctypes.byref(d), _p(in_bits), B, inst_offset, total or B, enc_seed, _p(out), threads)
+        self.L.ref_eval_prog_mv(self.ctx, ctypes.byref(d), _p(in_bits), B, inst_offset, total or B, enc_seed, _p(out), threads, 1 if multi_value else 0)
         return out

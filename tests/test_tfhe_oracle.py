@@ -104,3 +104,38 @@ def test_unrolled_parameter_model():
         for u in (a2, a3):
             assert a.p_fail(p, norm2) <= u.p_fail(p, norm2) < 1.5 * a.p_fail(p, norm2)
     assert params.estimate(15, 70)["param_set"] == params.DEFAULT_SET == "A3"
+
+
+def test_oracle_multi_value_bootstrap_decrypts_to_every_table():
+    """oracle/tfhe_ref.c: ref_pbs_multi (one blind rotation of the base polynomial, sparse product per table) decrypts to
+    table[m] for every table mode, and a whole program evaluated with multi-value groups equals the cleartext interpreter."""
+    from conftest import load_ref_mapped, selfcheck_inputs
+    from oracle import cleartext
+    from tfhe_fbs_map_b200 import levelize
+    from tfhe_fbs_map_b200.formats import read_lbf
+    ps = params.get("toy3")
+    ref = RefTFHE(ps, seed=3)
+    for p in (3, 7, 8):
+        rng = np.random.default_rng(p)
+        low = [int(x) for x in rng.integers(0, 2, p)]
+        cases = [(low, 1), (low + [1 - x for x in low], 1), ([0] + low[1:] + [0], 0), ([1] + low[1:] + [1], 2), (low[:max(1, p - 2)], 1)]
+        tabs = np.zeros((len(cases), 2 * p), np.uint8)
+        for i, (t, _) in enumerate(cases):
+            tabs[i, :len(t)] = t
+        for m in range(2 * p):
+            ct = ref.encrypt(p, np.array([m], np.int32), np.array([m]), 9)[0]
+            outs, _ = ref.pbs_multi(p, ct, tabs, np.array([len(t) for t, _ in cases], np.uint8), np.array([md for _, md in cases], np.int32))
+            dec = ref.decrypt(p, outs)
+            for i, (t, _) in enumerate(cases):
+                if m < len(t):
+                    assert dec[i] == t[m], (p, m, i)
+    e = next(x for x in load_ref_mapped() if x["circuit"] == "_2_input_gates" and x["p"] == 11 and x["mapper"] == "search")
+    env = read_lbf(e["lbf"])
+    prog = levelize(env, 11, multi_value=True)
+    assert (prog.n_boots, prog.n_groups, prog.n_rotations) == (10, 2, 2)
+    inputs = selfcheck_inputs(e["input_names"])
+    bits = np.array([inputs[nm][:4] for nm in prog.input_names], dtype=np.uint8)
+    got = ref.eval_prog(prog, bits, enc_seed=1, multi_value=True)
+    want = cleartext.lut_eval(env, {nm: bits[i] for i, nm in enumerate(prog.input_names)})
+    for nm in prog.output_names:
+        assert np.array_equal(got[prog.out_index[nm]], np.asarray(want[nm])), nm

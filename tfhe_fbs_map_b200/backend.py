@@ -21,7 +21,7 @@ EXPORTS = [
     "fbs_last_error", "fbs_abi_version", "fbs_ctx_create", "fbs_keygen", "fbs_ctx_destroy", "fbs_ctx_set_cluster", "fbs_ctx_info",
     "fbs_prog_load", "fbs_prog_free", "fbs_eval_bits", "fbs_wires_bytes", "fbs_encrypt_inputs", "fbs_run_level",
     "fbs_run", "fbs_decrypt_outputs", "fbs_pbs_batch", "fbs_clear_eval", "fbs_debug_get_keys", "fbs_debug_ntt",
-    "fbs_debug_pbs", "fbs_debug_encrypt", "fbs_debug_decrypt", "fbs_measure_int_peak",
+    "fbs_debug_pbs", "fbs_debug_pbs_multi", "fbs_debug_encrypt", "fbs_debug_decrypt", "fbs_measure_int_peak",
     "fbs_wires_alloc", "fbs_wires_free", "fbs_ipc_export", "fbs_ipc_import", "fbs_ipc_close", "fbs_set_peers", "fbs_level_sync", "fbs_sync_status",
 ]
 
@@ -71,6 +71,7 @@ def load_library(path: str | None = None):
         lib.fbs_debug_get_keys.argtypes = [vp, vp, vp, vp, vp]
         lib.fbs_debug_ntt.argtypes = [vp, vp, i64, i32]
         lib.fbs_debug_pbs.argtypes = [vp, i32, vp, vp, vp, vp, i64, vp, vp, vp, vp]
+        lib.fbs_debug_pbs_multi.argtypes = [vp, i32, vp, vp, vp, vp, i64, i32, vp, vp]
         lib.fbs_debug_encrypt.argtypes = [vp, i32, vp, vp, i64, u64, vp]
         lib.fbs_debug_decrypt.argtypes = [vp, i32, vp, i64, vp]
         lib.fbs_measure_int_peak.argtypes = [vp, ctypes.POINTER(ctypes.c_double)]
@@ -234,12 +235,12 @@ class B200Backend:
             pass
 
     # ------------------------------------------------------------------ programs
-    def compile(self, env, fbs_size=None, clear=False, shard_pad=1, reuse_slots=True) -> CompiledProgram:
-        key = (id(self), fbs_size, clear, shard_pad, reuse_slots, len(env.instructions), len(env.outputs))
+    def compile(self, env, fbs_size=None, clear=False, shard_pad=1, reuse_slots=True, multi_value=False) -> CompiledProgram:
+        key = (id(self), fbs_size, clear, shard_pad, reuse_slots, multi_value, len(env.instructions), len(env.outputs))
         cached = getattr(env, "_compiled", None)
         if cached is not None and cached[0] == key:
             return cached[1]
-        prog = levelize(env, fbs_size, reuse_slots=reuse_slots, shard_pad=shard_pad, clear=clear)
+        prog = levelize(env, fbs_size, reuse_slots=reuse_slots, shard_pad=shard_pad, clear=clear, multi_value=multi_value)
         cp = CompiledProgram(self, prog)
         try:
             env._compiled = (key, cp)
@@ -361,6 +362,22 @@ class B200Backend:
         self._check(self.lib.fbs_debug_pbs(self.ctx, p, _ptr(in_cts), _ptr(tables), _ptr(tlens), _ptr(modes_a), count,
                                            _ptr(out), _ptr(ks), _ptr(ms), _ptr(acc)))
         return out, ks, ms, acc
+
+
+    def debug_pbs_multi(self, p, in_cts, tables, tlens, modes=None):
+        """Multi-value bootstrap tap: ``count`` input ciphertexts, T tables EACH (tables [count][T][2p], tlens / modes [count][T]),
+        one blind rotation per input: (out [count][T][kN+1], acc [count][k+1][N] = accumulator before the per-table products)."""
+        P = self.params
+        in_cts = np.ascontiguousarray(in_cts, dtype=np.uint64)
+        tables = np.ascontiguousarray(tables, dtype=np.uint8)
+        count, T = tables.shape[0], tables.shape[1]
+        assert tables.shape[2] == 2 * p and in_cts.shape[0] == count
+        tlens = np.ascontiguousarray(tlens, dtype=np.uint8).reshape(count, T)
+        modes_a = None if modes is None else np.ascontiguousarray(modes, dtype=np.int32).reshape(count, T)
+        out = np.zeros((count, T, P.ct_words), np.uint64)
+        acc = np.zeros((count, P.k + 1, P.N), np.uint64)
+        self._check(self.lib.fbs_debug_pbs_multi(self.ctx, p, _ptr(in_cts), _ptr(tables), _ptr(tlens), _ptr(modes_a), count, T, _ptr(out), _ptr(acc)))
+        return out, acc
 
 
 _default = {}

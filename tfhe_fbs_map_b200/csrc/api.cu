@@ -157,6 +157,7 @@ struct fbs_ctx {
     // staging for host-buffer calls
     u8 *d_io = nullptr; size_t cap_io = 0;
     u64 *d_wires = nullptr; size_t cap_wires = 0;
+    u64 *d_mvacc = nullptr; size_t cap_mvacc = 0;              // multi-value bootstrap: accumulators between rotation and finishing
     u8 *d_clear_io = nullptr; size_t cap_clear_io = 0;         // fbs_clear_eval scratch
     int32_t *d_clear_lcv = nullptr; size_t cap_clear_lcv = 0;
 };
@@ -165,6 +166,8 @@ struct fbs_prog {
     int32_t p = 0, n_inputs = 0, n_lincombs = 0, n_boots = 0, n_levels = 0, n_slots = 0, n_outputs = 0;
     bool contiguous_levels = false;                       // slots are never recycled: node sub-ranges of a level may run alone
     std::vector<int32_t> lc_level_ptr, bs_level_ptr, bs_lc;
+    int32_t n_groups = 0; std::vector<int32_t> grp_level_ptr, grp_first;     // multi-value bootstrap (n_groups > 0)
+    int32_t *d_grp_first = nullptr;
     int max_lc_per_level = 0;
     int32_t *d_i32 = nullptr; u8 *d_tab = nullptr;        // one arena for all int32 arrays
     int32_t *d_lc_level_ptr, *d_bs_level_ptr, *d_lc_ptr, *d_lc_slot, *d_lc_coef, *d_lc_const, *d_bs_lc, *d_bs_slot,
@@ -336,7 +339,7 @@ extern "C" int fbs_ctx_destroy(fbs_ctx *c)
     if (!c) return FBS_OK;
     cudaSetDevice(c->device);
     void *ptrs[] = {c->d_kbt, c->d_s_lwe, c->d_s_big, c->d_ksk, c->d_colsum, c->d_bsk, c->d_bsk_coef, c->d_psi_rev, c->d_psi_inv_rev, c->d_psi_pow,
-                    c->d_gad_bsk, c->d_gad_ks, c->d_digits, c->d_body, c->d_ms, c->d_io, c->d_wires, c->d_clear_io, c->d_clear_lcv, c->d_sync_err};
+                    c->d_gad_bsk, c->d_gad_ks, c->d_digits, c->d_body, c->d_ms, c->d_io, c->d_wires, c->d_clear_io, c->d_clear_lcv, c->d_sync_err, c->d_mvacc};
     for (void *p : ptrs) if (p) cudaFree(p);
     for (auto &e : c->ev) if (e) cudaEventDestroy(e);
     for (auto &e : c->ev_pool) if (e) cudaEventDestroy(e);
@@ -447,6 +450,24 @@ static int prog_load_impl(fbs_ctx *c, const fbs_prog_desc *d, fbs_prog *g)
     CK(h2d_sync(g->d_i32, host.data(), tot * 4));
     CKR(dev_alloc(&g->d_tab, (size_t)tabn + 16));
     if (tabn) CK(h2d_sync(g->d_tab, d->bs_tab, tabn));
+    if (d->n_groups > 0) {
+        // multi-value: groups partition every level's bootstraps into runs that share one lincomb
+        if (!d->grp_level_ptr || !d->grp_first || csr_total(d->grp_level_ptr, d->n_levels) != d->n_groups || csr_total(d->grp_first, d->n_groups) != d->n_boots)
+            return fail(FBS_ERR_ARG, "fbs_prog_load: group pointers must be monotone from 0 and end at n_groups / n_boots");
+        g->n_groups = d->n_groups;
+        g->grp_level_ptr.assign(d->grp_level_ptr, d->grp_level_ptr + d->n_levels + 1);
+        g->grp_first.assign(d->grp_first, d->grp_first + d->n_groups + 1);
+        for (int lv = 0; lv < d->n_levels; lv++) {
+            if (g->grp_first[g->grp_level_ptr[lv]] != g->bs_level_ptr[lv] && g->grp_level_ptr[lv] < g->grp_level_ptr[lv + 1]) return fail(FBS_ERR_ARG, "fbs_prog_load: groups do not start at the level's first bootstrap");
+            if (g->grp_level_ptr[lv] == g->grp_level_ptr[lv + 1] && g->bs_level_ptr[lv] != g->bs_level_ptr[lv + 1]) return fail(FBS_ERR_ARG, "fbs_prog_load: level with bootstraps but no group");
+            for (int gi = g->grp_level_ptr[lv]; gi < g->grp_level_ptr[lv + 1]; gi++) {
+                if (g->grp_first[gi + 1] <= g->grp_first[gi] || g->grp_first[gi + 1] > g->bs_level_ptr[lv + 1]) return fail(FBS_ERR_ARG, "fbs_prog_load: empty group or group across levels");
+                for (int q = g->grp_first[gi]; q < g->grp_first[gi + 1]; q++) if (g->bs_lc[q] != g->bs_lc[g->grp_first[gi]]) return fail(FBS_ERR_ARG, "fbs_prog_load: bootstraps of a group must share their lincomb");
+            }
+        }
+        CKR(dev_alloc(&g->d_grp_first, (size_t)d->n_groups + 1));
+        CK(h2d_sync(g->d_grp_first, g->grp_first.data(), ((size_t)d->n_groups + 1) * 4));
+    }
     return FBS_OK;
 }
 extern "C" int fbs_prog_free(fbs_prog *g)
@@ -455,6 +476,7 @@ extern "C" int fbs_prog_free(fbs_prog *g)
     cudaSetDevice(g->ctx->device);
     if (g->d_i32) cudaFree(g->d_i32);
     if (g->d_tab) cudaFree(g->d_tab);
+    if (g->d_grp_first) cudaFree(g->d_grp_first);
     delete g;
     return FBS_OK;
 }
@@ -520,6 +542,8 @@ static int run_level_impl(fbs_ctx *c, fbs_prog *g, int level, int nb, int ne, in
     if (nb == ne) return FBS_OK;
     const fbs_params &P = c->P;
     const int D = P.k * P.N, n = P.n;
+    const bool multi = g->n_groups > 0;
+    if (multi && !whole) return fail(FBS_ERR_ARG, "fbs_run_level: a multi-value program runs whole levels (node sub-ranges are not supported)");
     const int node0 = b0 + nb, node1 = b0 + ne;
     const int lc0 = g->bs_lc[node0], lc1 = g->bs_lc[node1 - 1] + 1;     // bootstraps are sorted by lincomb
     const long long M = (long long)(lc1 - lc0) * B, tiles = (M + 15) / 16, mtiles = (M + KS_BM - 1) / KS_BM;
@@ -550,11 +574,15 @@ static int run_level_impl(fbs_ctx *c, fbs_prog *g, int level, int nb, int ne, in
     BRArgs ba{};
     ba.ms = c->d_ms; ba.bsk = c->d_bsk; ba.psi_rev = c->d_psi_rev; ba.psi_inv_rev = c->d_psi_inv_rev; ba.psi_pow = c->d_psi_pow;
     ba.bs_lc = g->d_bs_lc; ba.bs_slot = g->d_bs_slot; ba.bs_tab_ptr = g->d_bs_tab_ptr; ba.bs_mode = g->d_bs_mode; ba.bs_tab = g->d_tab;
-    ba.wires = wires; ba.tap_acc = tap_acc; ba.B = B; ba.jobs = (long long)(node1 - node0) * B; ba.node_begin = node0;
+    // multi-value: one job per (group, instance); the kernels index groups and leave the accumulators in d_mvacc for k_multi_extract
+    const int grp0 = multi ? g->grp_level_ptr[level] : 0, grp1 = multi ? g->grp_level_ptr[level + 1] : 0;
+    const long long jobs = multi ? (long long)(grp1 - grp0) * B : (long long)(node1 - node0) * B;
+    if (multi && !tap_acc) { CKR(grow(&c->d_mvacc, &c->cap_mvacc, (size_t)jobs * (P.k + 1) * P.N)); tap_acc = c->d_mvacc; }
+    ba.wires = wires; ba.tap_acc = tap_acc; ba.B = B; ba.jobs = jobs; ba.node_begin = multi ? grp0 : node0;
+    ba.grp_first = multi ? g->d_grp_first : nullptr;
     ba.n_peers = fused ? c->n_peers : 0;      // peers are bound to the registered buffer only (never to c->d_wires or a tap buffer)
     for (int pr = 0; pr < ba.n_peers; pr++) ba.peer_wires[pr] = c->peers[pr];
     ba.lc_begin = lc0; ba.n = n; ba.p = g->p; ba.beta = P.bsk_beta;
-    const long long jobs = (long long)(node1 - node0) * B;
     const long long wave = (long long)c->sm_count * c->br->pb, tail = jobs % wave;
     int n_br_launches = 1;
     // Fewer jobs than SMs: split each bootstrap over a cluster of C CTAs, cutting the latency of the launch instead of idling SMs
@@ -577,6 +605,15 @@ static int run_level_impl(fbs_ctx *c, fbs_prog *g, int level, int nb, int ne, in
         if (tlc) CK(c->brc[tlc]->launch(ba, jobs, c->brc_smem[tlc], st));
         else CK(c->br1->launch(ba, jobs, c->br1_smem, st));
     } else CK(c->br->launch(ba, jobs, c->br_smem, st));
+    if (multi) {
+        MVArgs ma{};
+        ma.acc = tap_acc; ma.grp_first = g->d_grp_first; ma.bs_slot = g->d_bs_slot; ma.bs_tab_ptr = g->d_bs_tab_ptr; ma.bs_mode = g->d_bs_mode; ma.bs_tab = g->d_tab;
+        ma.wires = wires; ma.B = B; ma.grp_begin = grp0; ma.N = P.N; ma.K = P.k; ma.p = g->p;
+        ma.n_peers = ba.n_peers; for (int pr = 0; pr < ba.n_peers; pr++) ma.peer_wires[pr] = ba.peer_wires[pr];
+        k_multi_extract<<<(unsigned)jobs, 256, 0, st>>>(ma);
+        CK(cudaGetLastError());
+        n_br_launches++;
+    }
     if (rec) CK(cudaEventRecord(E[3], st));
     if (stats) { stats->n_pbs += jobs; stats->n_launches += 2 + n_br_launches; }
     if (timed && stats) {
@@ -885,6 +922,52 @@ extern "C" int fbs_debug_pbs(fbs_ctx *c, int32_t p, const uint64_t *in_cts, cons
         if (e != cudaSuccess) rc = fail(FBS_ERR_CUDA, std::string("debug_pbs copies: ") + cudaGetErrorString(e));
     } while (0);
     if (d_w) cudaFree(d_w); if (d_ks) cudaFree(d_ks); if (d_acc) cudaFree(d_acc);
+    fbs_prog_free(g);
+    return rc;
+}
+
+// multi-value tap: a one-level program with `count` inputs, identity lincombs, T tables per lincomb, groups = the lincombs
+extern "C" int fbs_debug_pbs_multi(fbs_ctx *c, int32_t p, const uint64_t *in_cts, const uint8_t *tables, const uint8_t *tlen, const int32_t *modes,
+                                   int64_t count, int32_t T, uint64_t *out_cts, uint64_t *tap_acc)
+{
+    if (!c || !in_cts || !tables || !tlen || !out_cts || count < 1 || count > 4096 || T < 1 || T > 64) return fail(FBS_ERR_ARG, "fbs_debug_pbs_multi: bad argument");
+    if (!c->have_keys) return fail(FBS_ERR_STATE, "fbs_debug_pbs_multi before fbs_keygen");
+    CK(cudaSetDevice(c->device));
+    const int n = (int)count, nb = n * T;
+    std::vector<int32_t> lvl = {0, n}, blvl = {0, nb}, lc_ptr(n + 1), lc_slot(n), lc_coef(n, 1), lc_const(n, 0), bs_lc(nb), bs_slot(nb), tab_ptr(nb + 1), mode(nb), in_slot(n),
+                         out_ptr(nb + 1), out_slot(nb), out_coef(nb, 1), out_const(nb, 0), glvl = {0, n}, gfirst(n + 1);
+    std::vector<u8> tab;
+    tab_ptr[0] = 0;
+    for (int i = 0; i < n; i++) { lc_ptr[i] = i; lc_slot[i] = i; in_slot[i] = i; gfirst[i] = i * T; }
+    lc_ptr[n] = n; gfirst[n] = nb;
+    for (int q = 0; q < nb; q++) {
+        bs_lc[q] = q / T; bs_slot[q] = n + q; out_ptr[q] = q; out_slot[q] = n + q; mode[q] = modes ? modes[q] : 1;
+        for (int t = 0; t < tlen[q]; t++) tab.push_back(tables[(size_t)q * 2 * p + t]);
+        tab_ptr[q + 1] = (int)tab.size();
+    }
+    out_ptr[nb] = nb;
+    fbs_prog_desc d{};
+    d.p = p; d.n_inputs = n; d.n_lincombs = n; d.n_boots = nb; d.n_levels = 1; d.n_slots = n + nb; d.n_outputs = nb; d.contiguous_levels = 1;
+    d.lc_level_ptr = lvl.data(); d.bs_level_ptr = blvl.data(); d.lc_ptr = lc_ptr.data(); d.lc_slot = lc_slot.data(); d.lc_coef = lc_coef.data();
+    d.lc_const = lc_const.data(); d.bs_lc = bs_lc.data(); d.bs_slot = bs_slot.data(); d.bs_tab_ptr = tab_ptr.data(); d.bs_tab = tab.data();
+    d.bs_mode = mode.data(); d.in_slot = in_slot.data(); d.out_ptr = out_ptr.data(); d.out_slot = out_slot.data(); d.out_coef = out_coef.data(); d.out_const = out_const.data();
+    d.n_groups = n; d.grp_level_ptr = glvl.data(); d.grp_first = gfirst.data();
+    fbs_prog *g = nullptr;
+    CKR(fbs_prog_load(c, &d, &g));
+    const size_t CT = ct_words(c); const fbs_params &P = c->P; cudaStream_t st = c->stream;
+    u64 *d_w = nullptr, *d_acc = nullptr;
+    int rc = FBS_OK;
+    do {
+        if ((rc = dev_alloc(&d_w, (size_t)(n + nb) * CT)) != FBS_OK) break;
+        if ((rc = dev_alloc(&d_acc, (size_t)count * (P.k + 1) * P.N)) != FBS_OK) break;
+        if (h2d_sync(d_w, in_cts, (size_t)count * CT * 8) != cudaSuccess) { rc = fail(FBS_ERR_CUDA, "debug_pbs_multi H2D"); break; }
+        if ((rc = run_level_impl(c, g, 0, -1, -1, 1, d_w, st, nullptr, nullptr, d_acc, false)) != FBS_OK) break;
+        if (cudaStreamSynchronize(st) != cudaSuccess) { rc = fail(FBS_ERR_CUDA, std::string("debug_pbs_multi: ") + cudaGetErrorString(cudaGetLastError())); break; }
+        cudaError_t e = cudaMemcpy(out_cts, d_w + (size_t)count * CT, (size_t)nb * CT * 8, cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess && tap_acc) e = cudaMemcpy(tap_acc, d_acc, (size_t)count * (P.k + 1) * P.N * 8, cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) rc = fail(FBS_ERR_CUDA, std::string("debug_pbs_multi copies: ") + cudaGetErrorString(e));
+    } while (0);
+    if (d_w) cudaFree(d_w); if (d_acc) cudaFree(d_acc);
     fbs_prog_free(g);
     return rc;
 }

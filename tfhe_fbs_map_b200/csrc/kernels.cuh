@@ -479,7 +479,12 @@ struct BRArgs {
     u32 zero;                           // always 0; unknown to ptxas, see ntt.cuh (pins adds to the ALU pipe)
     int n_peers;                        // node-sharded multi-GPU: replicas of the wire buffer on the other GPUs
     u64 *peer_wires[8];                 // (peer-mapped pointers, same layout): the sample-extract epilogue stores to all
+    // multi-value bootstrap: jobs are (group, instance); the rotation starts from the table-independent base
+    // polynomial and leaves the accumulator in tap_acc for k_multi_extract (no sample extraction here)
+    const int32_t *grp_first;           // nullptr: ordinary bootstrap, node = node_begin + job / B
 };
+// H = Delta / 2 mod q (q is odd): coefficient of the base test polynomial and unit of the table-mode offset of a multi-value bootstrap
+__device__ __forceinline__ u64 fbs_half_delta(int p) { return fq_mul(fbs_delta(p), (FQ_Q + 1) / 2); }
 // TP = bootstraps carried by each thread (1, or PB: every thread works on all PB bootstraps of the CTA, so twiddle loads,
 // BSK reads, index arithmetic and barriers are shared between them and the instruction-level parallelism doubles).
 template <int LOGN, int K, int L, bool BSK_SMEM, int PB, int TP>
@@ -530,6 +535,7 @@ __global__ void __launch_bounds__((PB / TP) * (K + 1) * (1 << LOGN) / 8, 1) k_bl
         live[q] = job[q] < a.jobs;
         if (!live[q]) job[q] = a.jobs - 1;
         node[q] = a.node_begin + (int)(job[q] / a.B);
+        if (a.grp_first) node[q] = a.grp_first[node[q]];           // multi-value: first bootstrap of the group (they share the lincomb)
         inst[q] = job[q] % a.B;
         const u16 *ms = a.ms + ((size_t)(a.bs_lc[node[q]] - a.lc_begin) * a.B + inst[q]) * (size_t)(n + 1);
         tab0[q] = a.bs_tab_ptr[node[q]]; tabL[q] = a.bs_tab_ptr[node[q] + 1] - tab0[q]; mode[q] = a.bs_mode[node[q]];
@@ -563,7 +569,7 @@ __global__ void __launch_bounds__((PB / TP) * (K + 1) * (1 << LOGN) / 8, 1) k_bl
                 int x = (int)((2LL * src * p + N) / (2LL * N));
                 if (x >= p) { x -= p; neg = !neg; }
                 const u64 tvx = (x < tabL[q]) ? (u64)__ldg(a.bs_tab + tab0[q] + x) : 0;
-                const u64 F = fq_sub(fq_mul(tvx, delta), off);
+                const u64 F = a.grp_first ? fbs_half_delta(p) : fq_sub(fq_mul(tvx, delta), off);
                 val = neg ? fq_neg(F) : F;
             }
             acc[q * PW + j] = rns_pack(rns_from_int(val));
@@ -729,14 +735,14 @@ __global__ void __launch_bounds__((PB / TP) * (K + 1) * (1 << LOGN) / 8, 1) k_bl
         const size_t CT = (size_t)K * N + 1;
         const size_t off = ((size_t)a.bs_slot[node[q]] * a.B + inst[q]) * CT;
         u64 *out = a.wires + off;
-        for (int w = ptid; w < K * N; w += C::PT) {
+        for (int w = ptid; w < K * N && !a.grp_first; w += C::PT) {
             const int u = w / N, j = w % N;
             const rns2 v = rns_unpack(A[(size_t)u * N + (j == 0 ? 0 : N - j)]);
             const u64 val = rns_to_int(j == 0 ? v : rns_neg(v));
             out[w] = val;
             for (int pr = 0; pr < a.n_peers; pr++) a.peer_wires[pr][off + w] = val;
         }
-        if (ptid == 0) {
+        if (ptid == 0 && !a.grp_first) {
             const u64 val = fq_add(rns_to_int(rns_unpack(A[(size_t)K * N])), fq_mul((u64)mode[q], fbs_delta(p) >> 1));
             out[(size_t)K * N] = val;
             for (int pr = 0; pr < a.n_peers; pr++) a.peer_wires[pr][off + (size_t)K * N] = val;
@@ -818,6 +824,7 @@ __global__ void __launch_bounds__((PB / TP) * (K + 1) * (1 << LOGN) / 8, 1) k_bl
         live[q] = job[q] < a.jobs;
         if (!live[q]) job[q] = a.jobs - 1;
         node[q] = a.node_begin + (int)(job[q] / a.B);
+        if (a.grp_first) node[q] = a.grp_first[node[q]];           // multi-value: first bootstrap of the group (they share the lincomb)
         inst[q] = job[q] % a.B;
         const u16 *ms = a.ms + ((size_t)(a.bs_lc[node[q]] - a.lc_begin) * a.B + inst[q]) * (size_t)(n + 1);
         tab0[q] = a.bs_tab_ptr[node[q]]; tabL[q] = a.bs_tab_ptr[node[q] + 1] - tab0[q]; mode[q] = a.bs_mode[node[q]];
@@ -859,7 +866,7 @@ __global__ void __launch_bounds__((PB / TP) * (K + 1) * (1 << LOGN) / 8, 1) k_bl
                 int x = (int)((2LL * src * p + N) / (2LL * N));
                 if (x >= p) { x -= p; neg = !neg; }
                 const u64 tvx = (x < tabL[q]) ? (u64)__ldg(a.bs_tab + tab0[q] + x) : 0;
-                const u64 F = fq_sub(fq_mul(tvx, delta), off);
+                const u64 F = a.grp_first ? fbs_half_delta(p) : fq_sub(fq_mul(tvx, delta), off);
                 val = neg ? fq_neg(F) : F;
             }
             av[q][e] = rns_from_int(val);
@@ -1034,14 +1041,14 @@ __global__ void __launch_bounds__((PB / TP) * (K + 1) * (1 << LOGN) / 8, 1) k_bl
         const size_t CT = (size_t)K * N + 1;
         const size_t off = ((size_t)a.bs_slot[node[q]] * a.B + inst[q]) * CT;
         u64 *out = a.wires + off;
-        for (int w = ptid; w < K * N; w += C::PT) {
+        for (int w = ptid; w < K * N && !a.grp_first; w += C::PT) {
             const int u = w / N, j = w % N;
             const rns2 v = rns_unpack(A[(size_t)u * N + (j == 0 ? 0 : N - j)]);
             const u64 val = rns_to_int(j == 0 ? v : rns_neg(v));
             out[w] = val;
             for (int pr = 0; pr < a.n_peers; pr++) a.peer_wires[pr][off + w] = val;
         }
-        if (ptid == 0) {
+        if (ptid == 0 && !a.grp_first) {
             const u64 val = fq_add(rns_to_int(rns_unpack(A[(size_t)K * N])), fq_mul((u64)mode[q], fbs_delta(p) >> 1));
             out[(size_t)K * N] = val;
             for (int pr = 0; pr < a.n_peers; pr++) a.peer_wires[pr][off + (size_t)K * N] = val;
@@ -1138,7 +1145,7 @@ __global__ void __launch_bounds__((K + 1) * (1 << (LOGN - LOGC)) / 8, 1) k_blind
     const int n_pairs = (n + M - 1) / M, n_slices = 8 * n_pairs;
 
     const long long job = a.job_begin + (long long)(blockIdx.x >> LOGC);      // grid = exactly C CTAs per job
-    const int node = a.node_begin + (int)(job / a.B);
+    const int node = a.grp_first ? a.grp_first[a.node_begin + (int)(job / a.B)] : a.node_begin + (int)(job / a.B);
     const long long inst = job % a.B;
     {
         const u16 *ms = a.ms + ((size_t)(a.bs_lc[node] - a.lc_begin) * a.B + inst) * (size_t)(n + 1);
@@ -1194,7 +1201,7 @@ __global__ void __launch_bounds__((K + 1) * (1 << (LOGN - LOGC)) / 8, 1) k_blind
                 int x = (int)((2LL * src * p + N) / (2LL * N));
                 if (x >= p) { x -= p; neg = !neg; }
                 const u64 tvx = (x < tabL) ? (u64)__ldg(a.bs_tab + tab0 + x) : 0;
-                const u64 F = fq_sub(fq_mul(tvx, delta), off);
+                const u64 F = a.grp_first ? fbs_half_delta(p) : fq_sub(fq_mul(tvx, delta), off);
                 val = neg ? fq_neg(F) : F;
             }
             av[e] = rns_from_int(val);
@@ -1342,7 +1349,8 @@ __global__ void __launch_bounds__((K + 1) * (1 << (LOGN - LOGC)) / 8, 1) k_blind
 #pragma unroll
         for (int e = 0; e < 8; e++) {
             const int j = (e / R) * Ns + h * (Ns / C) + (e % R) * Ts + tau;
-            if (g < K) {                                             // mask: out[g*N + jj] = (jj == 0 ? a_0 : -a_{N-jj}), jj = (N - j) mod N
+            if (a.grp_first) {                                       // multi-value: k_multi_extract finishes from tap_acc
+            } else if (g < K) {                                      // mask: out[g*N + jj] = (jj == 0 ? a_0 : -a_{N-jj}), jj = (N - j) mod N
                 const int jj = (j == 0) ? 0 : N - j;
                 const u64 val = rns_to_int(j == 0 ? av[e] : rns_neg(av[e]));
                 out[(size_t)g * N + jj] = val;
@@ -1356,6 +1364,62 @@ __global__ void __launch_bounds__((K + 1) * (1 << (LOGN - LOGC)) / 8, 1) k_blind
         }
     }
     cluster_sync_all();                                           // nobody leaves while a neighbour may still address its shared memory
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Multi-value bootstrap, finishing step (oracle/tfhe_ref.c: ref_multi_extract).  The blind rotation of a
+// (group, instance) job left ACC = GLWE(X^-mu * TV0), TV0 = H (1 + X + .. + X^(N-1)), as integers mod q in acc[job][(K+1)][N].
+// For every table f of the group: out_f = SampleExtract(ACC * e_f) + s*H, where e_f is the sparse polynomial with
+// Delta e_f = (1 - X) TV_f: at most p non-zero coefficients in {-2..2} at the slot boundaries j_x = ceil(N (2x - 1) / 2p).
+// One CTA per job; the sums are at most p terms per output word.
+// ------------------------------------------------------------------------------------------------------
+struct MVArgs {
+    const u64 *acc; const int32_t *grp_first, *bs_slot, *bs_tab_ptr, *bs_mode; const u8 *bs_tab;
+    u64 *wires; long long B; int grp_begin, N, K, p;
+    int n_peers; u64 *peer_wires[8];
+};
+__global__ void __launch_bounds__(256) k_multi_extract(MVArgs a)
+{
+    __shared__ int s_pos[128], s_coef[128], s_cnt;
+    const long long job = blockIdx.x;
+    const int gi = a.grp_begin + (int)(job / a.B), N = a.N, K = a.K, p = a.p;
+    const long long inst = job % a.B;
+    const u64 *acc = a.acc + (size_t)job * (K + 1) * N;
+    const size_t CT = (size_t)K * N + 1;
+    for (int q = a.grp_first[gi]; q < a.grp_first[gi + 1]; q++) {
+        const int t0 = a.bs_tab_ptr[q], L = a.bs_tab_ptr[q + 1] - t0, s = a.bs_mode[q];
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int cnt = 0;
+            for (int x = 1; x <= p; x++) {
+                const int tx = (x < p && x < L) ? a.bs_tab[t0 + x] : 0, tp = (x - 1 < L) ? a.bs_tab[t0 + x - 1] : 0;
+                const int e = (x < p) ? tx - tp : -((int)a.bs_tab[t0] + tp - s);
+                if (!e) continue;
+                s_pos[cnt] = (int)(((long long)N * (2 * x - 1) + 2 * p - 1) / (2 * p)); s_coef[cnt] = e; cnt++;
+            }
+            s_cnt = cnt;
+        }
+        __syncthreads();
+        const int cnt = s_cnt;
+        const size_t off = ((size_t)a.bs_slot[q] * a.B + inst) * CT;
+        for (int w = threadIdx.x; w <= K * N; w += 256) {
+            const int u = w / N, jj = w % N;                       // w == K*N: the body = coefficient 0 of polynomial K
+            const int i = (jj == 0) ? 0 : N - jj;                  // extracted mask word jj is -(ACC_u e_f)[N - jj] (jj > 0)
+            u64 sum = 0;
+            for (int t = 0; t < cnt; t++) {
+                const int idx = i - s_pos[t];
+                const u64 x = idx >= 0 ? acc[(size_t)u * N + idx] : fq_neg(acc[(size_t)u * N + idx + N]);
+                const int cf = s_coef[t];
+                const u64 term = (cf == 2 || cf == -2) ? fq_add(x, x) : x;
+                sum = cf > 0 ? fq_add(sum, term) : fq_sub(sum, term);
+            }
+            u64 val;
+            if (w == K * N) val = fq_add(sum, fq_mul((u64)s, fbs_half_delta(p)));
+            else val = (jj == 0) ? sum : fq_neg(sum);
+            a.wires[off + w] = val;
+            for (int pr = 0; pr < a.n_peers; pr++) a.peer_wires[pr][off + w] = val;
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------------------

@@ -37,7 +37,9 @@ class CProgDesc(ctypes.Structure):
                 ("lc_ptr", _P32), ("lc_slot", _P32), ("lc_coef", _P32), ("lc_const", _P32),
                 ("bs_lc", _P32), ("bs_slot", _P32), ("bs_tab_ptr", _P32), ("bs_tab", _P8), ("bs_mode", _P32),
                 ("in_slot", _P32),
-                ("out_ptr", _P32), ("out_slot", _P32), ("out_coef", _P32), ("out_const", _P32)]
+                ("out_ptr", _P32), ("out_slot", _P32), ("out_coef", _P32), ("out_const", _P32),
+                # multi-value bootstrap (appended: older mirrors of the descriptor are a prefix): groups of bootstraps on one lincomb
+                ("grp_level_ptr", _P32), ("grp_first", _P32), ("n_groups", ctypes.c_int32), ("reserved2", ctypes.c_int32)]
 
 
 def table_mode(table, p):
@@ -88,6 +90,13 @@ class Program:
     shard_pad: int = 1
     n_boots: int = 0
     n_lincombs: int = 0
+    multi_value: bool = False      # bootstraps that share a lincomb are evaluated by ONE blind rotation
+    n_groups: int = 0              # = number of blind rotations per instance when multi_value
+
+    @property
+    def n_rotations(self) -> int:
+        """Blind rotations per instance: one per bootstrap, or one per (level, lincomb) group with multi_value."""
+        return self.n_groups if self.multi_value else self.n_boots
 
     def c_desc(self) -> CProgDesc:
         a = self.arrays
@@ -95,7 +104,12 @@ class Program:
         d.p, d.n_inputs, d.n_lincombs, d.n_boots = self.p, self.n_inputs, self.n_lincombs, self.n_boots
         d.n_levels, d.n_slots, d.n_outputs = self.n_levels, self.n_slots, len(self.output_names)
         d.contiguous_levels = 1 if self.contiguous_levels else 0
-        for name, _ in CProgDesc._fields_[8:]:
+        d.n_groups = self.n_groups if self.multi_value else 0
+        for name, tp in CProgDesc._fields_[8:]:
+            if name in ("n_groups", "reserved2"):
+                continue
+            if name in ("grp_level_ptr", "grp_first") and not self.multi_value:
+                continue                          # NULL: ordinary one-rotation-per-bootstrap program
             arr = a[name]
             ct = ctypes.c_uint8 if arr.dtype == np.uint8 else ctypes.c_int32
             setattr(d, name, arr.ctypes.data_as(ctypes.POINTER(ct)))
@@ -116,8 +130,10 @@ def _flatten(node, scale, acc, const):
 
 
 def levelize(env, p: int | None = None, reuse_slots: bool = True, shard_pad: int = 1, clear: bool = False,
-             preserve_inputs: bool = False) -> Program:
-    """Build the program.  ``reuse_slots``: liveness-based slot reuse (instance-sharded / single GPU);
+             preserve_inputs: bool = False, multi_value: bool = False) -> Program:
+    """Build the program.  ``multi_value``: bootstraps of a level that share a lincomb (reference fbs_exec_env.py:93-100 makes the
+    sharing visible by de-duplicating LinearProds) become one group = ONE blind rotation + one cheap finishing step per table.
+    ``reuse_slots``: liveness-based slot reuse (instance-sharded / single GPU);
     ``shard_pad`` > 1: level-contiguous slots padded to a multiple of ``shard_pad`` nodes per level so a
     level's outputs can be all-gathered in place across ``shard_pad`` ranks (node-sharded mode);
     ``preserve_inputs``: never recycle the input slots, so the same encrypted inputs can be run repeatedly."""
@@ -280,4 +296,15 @@ def levelize(env, p: int | None = None, reuse_slots: bool = True, shard_pad: int
     # true counts (arrays may have been padded to length 1)
     prog.n_boots = len(boots_sorted)
     prog.n_lincombs = len(lc_rows)
+    # groups: maximal runs of a level's bootstraps (sorted by lincomb) on the same lincomb
+    grp_first, grp_level_ptr = [], [0]
+    for lv in range(n_levels):
+        for q in range(bs_level_ptr[lv], bs_level_ptr[lv + 1]):
+            if q == bs_level_ptr[lv] or bs_lc[q] != bs_lc[q - 1]:
+                grp_first.append(q)
+        grp_level_ptr.append(len(grp_first))
+    prog.n_groups = len(grp_first)
+    grp_first.append(len(boots_sorted))
+    prog.arrays["grp_first"], prog.arrays["grp_level_ptr"] = i32(grp_first), i32(grp_level_ptr)
+    prog.multi_value = bool(multi_value) and not clear
     return prog

@@ -255,15 +255,18 @@ class LutExecEnv:
                 res[name] = out_mat[prog.out_index[name]].astype(np.int64)
         return res
 
-    def eval(self, input_values, fbs_size=None, backend=None):
+    def eval(self, input_values, fbs_size=None, backend=None, multi_value=False):
         """Encrypted evaluation on the GPU; same contract as reference fbs_exec_env.py:208-229.
 
         ``fbs_size`` (p) defaults to the smallest p for which every table is realisable; ``backend`` is a
         :class:`tfhe_fbs_map_b200.backend.B200Backend` (keys + device), default = process-wide backend.
+        ``multi_value``: evaluate all tables that share a LinearProd (the builder's de-duplication, reference :93-100) with ONE
+        blind rotation (multi-value bootstrap); same decrypted results, fewer rotations, slightly more noise
+        (``ParamSet.p_fail(p, norm2, mv_norm2=p + 3)``).
         """
         from . import backend as _be
         be = backend if backend is not None else _be.default_backend()
-        prog = be.compile(self, fbs_size)
+        prog = be.compile(self, fbs_size, multi_value=multi_value)
         _, mat, B = self._gather_inputs(input_values)
         out = be.eval_bits(prog, mat)
         return self._format_outputs(prog, out)

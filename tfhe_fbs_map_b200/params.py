@@ -98,10 +98,12 @@ class ParamSet:
         v_ms = (1.0 / 12.0 + self.n / 24.0) / (2.0 * self.N) ** 2
         return dict(v_br=v_br, v_ks=v_ks, v_ms=v_ms, v_in=norm2 * v_br + v_ks + v_ms)
 
-    def p_fail(self, p: int, norm2: float = 1.0) -> float:
-        """Per-PBS failure probability for message space Z_p with the patched bound q/(4p)."""
-        v = self.variances(norm2)["v_in"]
-        return math.erfc((1.0 / (4.0 * p)) / math.sqrt(2.0 * v))
+    def p_fail(self, p: int, norm2: float = 1.0, mv_norm2: float = 1.0) -> float:
+        """Per-PBS failure probability for message space Z_p with the patched bound q/(4p).  ``mv_norm2``: squared norm of the
+        table polynomial e_f of a multi-value bootstrap (multiplies the blind-rotation noise; at most p + 3, 1 = ordinary PBS)."""
+        v = self.variances(norm2)
+        v_in = norm2 * mv_norm2 * v["v_br"] + v["v_ks"] + v["v_ms"]
+        return math.erfc((1.0 / (4.0 * p)) / math.sqrt(2.0 * v_in))
 
     def as_dict(self) -> dict:
         return asdict(self)

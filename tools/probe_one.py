@@ -3,7 +3,8 @@ import sys
 import numpy as np
 sys.path.insert(0, ".")
 from tfhe_fbs_map_b200.backend import B200Backend
-name, count, mode = sys.argv[1], int(sys.argv[2]), int(sys.argv[3])
+from tfhe_fbs_map_b200 import params
+name, count, mode = sys.argv[1] or params.DEFAULT_SET, int(sys.argv[2]), int(sys.argv[3])
 reps = int(sys.argv[4]) if len(sys.argv) > 4 else 3
 be = B200Backend(name, device=0, seed=5)
 be.set_cluster(mode)
