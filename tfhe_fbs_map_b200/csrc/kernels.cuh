@@ -567,7 +567,7 @@ __global__ void __launch_bounds__((PB / TP) * (K + 1) * (1 << LOGN) / 8, 1) k_bl
                 if (src >= 2 * N) src -= 2 * N;
                 if (src >= N) { src -= N; neg = true; }
                 int x = (int)((2LL * src * p + N) / (2LL * N));
-                if (x >= p) { x -= p; neg = !neg; }
+                if (x >= p) { x -= p; neg = neg != (a.grp_first == nullptr); }     // half slot: the table's step function is negated there, the multi-value base polynomial is not
                 const u64 tvx = (x < tabL[q]) ? (u64)__ldg(a.bs_tab + tab0[q] + x) : 0;
                 const u64 F = a.grp_first ? fbs_half_delta(p) : fq_sub(fq_mul(tvx, delta), off);
                 val = neg ? fq_neg(F) : F;
@@ -864,7 +864,7 @@ __global__ void __launch_bounds__((PB / TP) * (K + 1) * (1 << LOGN) / 8, 1) k_bl
                 if (src >= 2 * N) src -= 2 * N;
                 if (src >= N) { src -= N; neg = true; }
                 int x = (int)((2LL * src * p + N) / (2LL * N));
-                if (x >= p) { x -= p; neg = !neg; }
+                if (x >= p) { x -= p; neg = neg != (a.grp_first == nullptr); }     // half slot: the table's step function is negated there, the multi-value base polynomial is not
                 const u64 tvx = (x < tabL[q]) ? (u64)__ldg(a.bs_tab + tab0[q] + x) : 0;
                 const u64 F = a.grp_first ? fbs_half_delta(p) : fq_sub(fq_mul(tvx, delta), off);
                 val = neg ? fq_neg(F) : F;
@@ -1199,7 +1199,7 @@ __global__ void __launch_bounds__((K + 1) * (1 << (LOGN - LOGC)) / 8, 1) k_blind
                 if (src >= 2 * N) src -= 2 * N;
                 if (src >= N) { src -= N; neg = true; }
                 int x = (int)((2LL * src * p + N) / (2LL * N));
-                if (x >= p) { x -= p; neg = !neg; }
+                if (x >= p) { x -= p; neg = neg != (a.grp_first == nullptr); }     // half slot: the table's step function is negated there, the multi-value base polynomial is not
                 const u64 tvx = (x < tabL) ? (u64)__ldg(a.bs_tab + tab0 + x) : 0;
                 const u64 F = a.grp_first ? fbs_half_delta(p) : fq_sub(fq_mul(tvx, delta), off);
                 val = neg ? fq_neg(F) : F;
