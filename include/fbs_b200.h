@@ -11,6 +11,10 @@
  * negative error code and never throws/aborts; fbs_last_error() returns the message of the calling
  * thread's last failure.  "dev" pointers are CUDA device pointers on the context's device; `stream` is a
  * cudaStream_t passed as void* (NULL = default stream).  One context per host thread.
+ *
+ * SECURITY CAVEAT: benchmark harness.  Keys, masks and noise come from a counter-based splitmix64 construction keyed by
+ * the seeds passed in (shared with the test oracle): NOT a cryptographically secure generator.  The caller
+ * must never reuse an (enc_seed, instance id) pair: ciphertexts that share it share mask and noise.
  */
 #ifndef FBS_B200_H
 #define FBS_B200_H
