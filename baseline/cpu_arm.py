@@ -11,14 +11,36 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB = os.path.join(_HERE, "libcpu_pbs.so")
 
 
+def _host_tag():
+    """Identity of this host's CPU: the library is compiled with -march=native, so a copy built elsewhere (it travels with the
+    repository snapshot to the GPU box) must be rebuilt when the CPU differs."""
+    import hashlib
+    try:
+        with open("/proc/cpuinfo") as f:
+            txt = f.read()
+        model = next((ln.split(":", 1)[1].strip() for ln in txt.splitlines() if ln.startswith("model name")), "")
+        flags = next((ln.split(":", 1)[1].strip() for ln in txt.splitlines() if ln.startswith("flags")), "")
+        return model + " " + hashlib.sha1(flags.encode()).hexdigest()[:12]
+    except OSError:
+        return "unknown"
+
+
 def build(force=False):
     src = os.path.join(_HERE, "cpu_pbs.cpp")
-    if force or not os.path.exists(LIB) or os.path.getmtime(LIB) < os.path.getmtime(src):
+    tag_file = LIB + ".host"
+    tag = _host_tag()
+    try:
+        built_for = open(tag_file).read()
+    except OSError:
+        built_for = None
+    if force or not os.path.exists(LIB) or os.path.getmtime(LIB) < os.path.getmtime(src) or built_for != tag:
         env = dict(os.environ)
         env.pop("CC", None); env.pop("CXX", None)
         r = subprocess.run(["make", "-C", _HERE, "-B", "libcpu_pbs.so"], env=env, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("CPU arm build failed:\n" + r.stdout + r.stderr)
+        with open(tag_file, "w") as f:
+            f.write(tag)
     return LIB
 
 

@@ -170,6 +170,55 @@ def test_error_paths(ctxs):
     nk.close()
 
 
+def test_malformed_programs_and_unsafe_sub_ranges_are_refused(ctxs):
+    """fbs_prog_load validates every CSR / level pointer array and the table values before anything is allocated, and
+    fbs_run_level refuses a node sub-range on a program whose slots are recycled (it would corrupt live wires)."""
+    import ctypes
+    import torch
+    from tfhe_fbs_map_b200.backend import FbsError
+    be, _ = ctxs("toy3")
+    env = read_golden_lbf("adder8_p15.lbf")
+    prog = levelize(env, 15)                                   # reuse_slots=True: NOT contiguous
+    cp = be.load(prog)
+    B = 2
+    wires = torch.empty(be.wires_bytes(cp, B) // 8, dtype=torch.int64, device="cuda")
+    d_in = torch.zeros((prog.n_inputs, B), dtype=torch.uint8, device="cuda")
+    be.encrypt_inputs(cp, d_in.data_ptr(), B, wires.data_ptr())
+    width0 = int(prog.arrays["bs_level_ptr"][1] - prog.arrays["bs_level_ptr"][0])
+    assert width0 >= 2
+    with pytest.raises(FbsError, match="contiguous_levels"):
+        be.run_level(cp, 0, B, wires.data_ptr(), 0, 1)
+    be.run_level(cp, 0, B, wires.data_ptr(), 0, width0)        # the whole level by explicit range is fine
+    be.run_level(cp, 0, B, wires.data_ptr())
+    torch.cuda.synchronize()
+
+    def broken(**patch):
+        p2 = levelize(env, 15)
+        for k, f in patch.items():
+            p2.arrays[k] = np.ascontiguousarray(f(p2.arrays[k].copy()))
+        return p2
+
+    def bump_last(a):
+        a[-1] += 1
+        return a
+
+    def descending(a):
+        a[1], a[2] = a[2] + 5, a[1]
+        return a
+
+    def big_entry(a):
+        a[0] = 200
+        return a
+
+    def bad_mode(a):
+        a[0] = -1
+        return a
+    for patch in (dict(lc_ptr=descending), dict(bs_tab_ptr=descending), dict(bs_level_ptr=bump_last), dict(lc_level_ptr=bump_last),
+                  dict(out_ptr=descending), dict(bs_tab=big_entry), dict(bs_mode=bad_mode)):
+        with pytest.raises(FbsError):
+            be.load(broken(**patch))
+
+
 def test_fused_peer_store_epilogue_single_gpu(ctxs):
     """The sample-extract epilogue writes each output ciphertext into every registered peer replica.  With one GPU the
     'peers' are two more buffers on the same device: after a run all three must hold identical bootstrap outputs."""
