@@ -227,6 +227,47 @@ def reference_literal(cores, B=100000):
                 lookups_per_s_all_cores=n_fbs * B * cores / tall, evals_per_s_all_cores=B * cores / tall)
 
 
+def run_config1(args, ps):
+    """BASELINE configs[0]: the reference's own CPU path (cleartext LutExecEnv.eval, fbs_exec_env.py:208-229) on the smallest
+    generated circuit, 1 core and all cores; when a GPU is present also the same program through this library."""
+    cores = host_cores()
+    lit = reference_literal(cores)
+    line = dict(metric="cleartext FBS look-ups/sec", value=lit["lookups_per_s_all_cores"], unit="look-ups/s", n_gpus=0, steps=1, warmup=0,
+                higher_is_better=True, data="synthetic (uniform random input bits)", impl="reference",
+                config=dict(workload="half_adder_p15_search_cleartext", desc="BASELINE configs[0]: smallest circuit of experiments/generate_benchmarks.py "
+                            "(half_adder, 2 FBS, 1 level) mapped with --fbs_size 15 --mapper search, cleartext LutExecEnv.eval", batch=lit["batch"]),
+                cpu_baseline=dict(lit, value=lit["lookups_per_s_all_cores"], unit="look-ups/s", kind="reference" if "imported" in lit["implementation"] else "port",
+                                  sample=f"{lit['batch']} random input vectors per process, {cores} processes"))
+    try:
+        import torch
+        if torch.cuda.is_available():
+            from tfhe_fbs_map_b200.backend import B200Backend
+            from tfhe_fbs_map_b200.formats import read_lbf
+            entries = json.load(open(os.path.join(ROOT, "tests", "golden", "ref_mapped.json")))
+            e = next(x for x in entries if x["circuit"] == "half_adder" and x["p"] == 15 and x["mapper"] == "search")
+            env = read_lbf(e["lbf"])
+            be = B200Backend(ps, device=0, seed=args.seed)
+            rng = np.random.default_rng(1)
+            B = 1 << 20
+            iv = {nm: rng.integers(0, 2, B) for nm in e["input_names"]}
+            env.eval_clear(iv, backend=be)
+            t0 = time.time(); got = env.eval_clear(iv, backend=be); dt = time.time() - t0
+            from oracle import cleartext
+            want = cleartext.lut_eval(env, iv)
+            ok = all(np.array_equal(np.asarray(got[k]), np.asarray(want[k])) for k in want)
+            Be = 4096
+            ive = {nm: v[:Be] for nm, v in iv.items()}
+            env.eval(ive, fbs_size=15, backend=be)
+            t0 = time.time(); gote = env.eval(ive, fbs_size=15, backend=be); dte = time.time() - t0
+            oke = all(np.array_equal(np.asarray(gote[k]), np.asarray(want[k])[:Be]) for k in want)
+            line["gpu"] = dict(cleartext_kernel_lookups_per_s=e["stats"]["nb_bootstrap"] * B / dt, cleartext_kernel_batch=B, cleartext_kernel_matches_oracle=ok,
+                               encrypted_pbs_per_s=e["stats"]["nb_bootstrap"] * Be / dte, encrypted_batch=Be, encrypted_matches_cleartext=oke,
+                               note="wall clock through the Python API incl. host<->device copies (and encrypt/decrypt for the encrypted run)", param_set=ps.name)
+    except Exception as ex:
+        line["gpu"] = f"unavailable: {ex}"
+    print(json.dumps(line))
+
+
 def cpu_baseline(ps, wl, seed, threads=0):
     """cpu_baseline object of the bench line: the tuned CPU arm on a bounded sample of the same workload, all host cores."""
     cores = threads or host_cores()
@@ -422,6 +463,10 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-nodes", action="store_true", help="skip the node-sharded 64x64 multiplier object ('nodes') of the line")
     ap.add_argument("--nodes-batches", default="1,64", help="instance batches of the node-sharded object")
+    ap.add_argument("--config1", action="store_true",
+                    help="BASELINE configs[0] as its own line: smallest generated circuit (half_adder), --fbs_size 15 --mapper search, "
+                         "cleartext LutExecEnv.eval on random inputs on the host cores; next to it the same program on the GPU (cleartext "
+                         "look-up kernel and encrypted)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -433,6 +478,10 @@ def main():
     if args.batch is None:
         args.batch = wl.get("batch", 296)
 
+    if args.config1:
+        if rank == 0:
+            run_config1(args, ps)
+        return
     if args.impl == "reference":
         run_reference(args, wl, ps, rank, world)
         return

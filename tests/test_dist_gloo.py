@@ -125,3 +125,67 @@ def test_node_sharded_levels_world2_gloo(circuit, p):
         assert words > 0
         for nm in prog.output_names:
             assert np.array_equal(out[prog.out_index[nm]], want[str(nm)]), (rank, nm)
+
+
+class FakeFusedEngine(OracleEngine):
+    """CPU stand-in for dist.FusedB200Engine: `fused = True` makes run_node_sharded call run_level for EVERY level on every rank
+    (empty ranges too: on the GPU the call carries the level's device-side wait + signal) and finish() once per run.  The "peer
+    stores" are an all-gather inside run_level, so a rank that skipped a level would dead-lock -- exactly what the real
+    hand-off would do."""
+    fused = True
+
+    def __init__(self, ref, program, B, world, rank):
+        super().__init__(ref, program, B)
+        self.world, self.rank, self.calls, self.finished = world, rank, [], 0
+
+    def run_level(self, level, nb, ne):
+        self.calls.append((level, nb, ne))
+        if ne > nb:
+            super().run_level(level, nb, ne)
+        a = self.prog.arrays
+        b0, b1 = int(a["bs_level_ptr"][level]), int(a["bs_level_ptr"][level + 1])
+        chunk = -(-(b1 - b0) // self.world)
+        first = int(a["bs_slot"][b0])
+        parts = [self.slot_view(first + r * chunk, chunk) for r in range(self.world)]
+        dist.all_gather(parts, parts[self.rank].clone())
+
+    def finish(self):
+        self.finished += 1
+
+
+def _fused_worker(rank, world, port, lbf, p, names, B, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from oracle.tfhe_ref import RefTFHE
+        ref = RefTFHE(params.get("toy3"), seed=31)
+        prog = levelize(read_lbf(lbf), p, shard_pad=world)
+        eng = FakeFusedEngine(ref, prog, B, world, rank)
+        inputs = selfcheck_inputs(names)
+        bits = np.array([inputs[nm][:B] for nm in prog.input_names], dtype=np.uint8)
+        eng.encrypt(bits)
+        run_node_sharded(eng, prog, dist, world, rank)
+        ret[rank] = (eng.decrypt(), eng.calls, eng.finished)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_fused_exchange_control_flow_world2_gloo():
+    """Host logic of the fused node-sharded mode (tfhe_fbs_map_b200/dist.py): every rank issues every level -- aes_sbox has a level
+    of width 1, so rank 1's range is empty there -- and closes the run with finish(); outputs equal the reference's."""
+    e = next(x for x in load_ref_mapped() if x["circuit"] == "aes_sbox" and x["p"] == 11 and x["mapper"] == "search" and not x.get("strict"))
+    B, world = 1, 2
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_fused_worker, args=(world, port, e["lbf"], 11, e["input_names"], B, ret), nprocs=world, join=True)
+    want = unpack_outputs(e, batch=B)
+    prog = levelize(read_lbf(e["lbf"]), 11, shard_pad=world)
+    assert min(prog.level_widths) == 1
+    for rank in range(world):
+        out, calls, finished = ret[rank]
+        assert [c[0] for c in calls] == list(range(prog.n_levels)) and finished == 1
+        for nm in prog.output_names:
+            assert np.array_equal(out[prog.out_index[nm]], want[str(nm)]), (rank, nm)
+    assert any(nb == ne for _, nb, ne in ret[1][1]), "rank 1 should have had an empty range at the width-1 level"

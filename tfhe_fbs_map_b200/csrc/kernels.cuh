@@ -332,11 +332,18 @@ __global__ void __launch_bounds__(256) k_lincomb_decomp(LCArgs a)
             const int lc = s_lc[mm];
             if (lc < 0) continue;
             const long long inst = s_inst[mm];
-            u64 acc = 0;
+            // sum_o c_o x_o with small integer coefficients: accumulate the exact 128-bit integer (|c| < 2^31, x < 2^60, <= 64 operands:
+            // < 2^97), a negative coefficient multiplies q - x; ONE reduction mod q per word instead of one modular multiply per operand
+            u64 lo = 0, hi = 0;
             for (int o = a.lc_ptr[lc]; o < a.lc_ptr[lc + 1]; o++) {
-                const u64 x = a.wires[((size_t)a.lc_slot[o] * a.B + inst) * CT + i];
-                acc = fq_add(acc, fq_mul(x, fq_from_i64(a.lc_coef[o])));
+                u64 x = __ldg(a.wires + ((size_t)a.lc_slot[o] * a.B + inst) * CT + i);
+                const int cf = a.lc_coef[o];
+                if (cf < 0) x = fq_neg(x);
+                const u64 m = (u64)(cf < 0 ? -(long long)cf : (long long)cf);
+                const u64 pl = x * m, ph = __umul64hi(x, m);
+                lo += pl; hi += ph + (lo < pl ? 1 : 0);
             }
+            u64 acc = fq_reduce128(lo, hi);
             if (i == a.D) {
                 acc = fq_add(acc, fq_mul(fq_from_i64(a.lc_const[lc]), fbs_delta(a.p)));
                 a.body[tile * 16 + mm] = acc;
