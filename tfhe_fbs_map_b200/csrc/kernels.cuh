@@ -789,7 +789,12 @@ struct BR2Cfg {
 #ifndef FBS_TW_SMEM
 #define FBS_TW_SMEM 1
 #endif
-    static constexpr bool TWS = FBS_TW_SMEM != 0 && M == 2;       // NTT twiddle table in shared memory (16 B per entry); no room at M = 3
+#ifndef FBS_TW_SMEM_PB1
+#define FBS_TW_SMEM_PB1 0
+#endif
+    // NTT twiddle table in shared memory (16 B per entry): at M = 2 always; at M = 3 the two-bootstrap CTA has no room for it, the
+    // one-bootstrap tail variant has (experiment FBS_TW_SMEM_PB1)
+    static constexpr bool TWS = FBS_TW_SMEM != 0 && (M == 2 || (FBS_TW_SMEM_PB1 != 0 && PB == 1));
     static constexpr size_t tw_w = TWS ? 2 * (size_t)N : 0;
     // Key slice = every key word the CTA needs for ONE of the 8 elements a thread holds: [tau >> 5][c < NC][u < G][v < G][tau & 31]; a
     // step consumes 8 slices in element order.  HBM layout [key group][element][tau >> 5][c][u][v][tau & 31]: one bulk copy per slice.
