@@ -116,3 +116,29 @@ def test_outputs_as_lincombs():
     assert got[prog.out_index["neg"]].tolist() == [1, 0, 0, 1]
     assert got[prog.out_index["pass"]].tolist() == [0, 0, 1, 1]
     assert got[prog.out_index["one"]].tolist() == [1, 1, 1, 1]
+
+
+@pytest.mark.parametrize("circuit,p,want", [("_2_input_gates", 15, (10, 2)), ("_2_input_gates", 11, (10, 2)), ("full_adder", 15, None)])
+def test_multi_value_groups_partition_every_level(circuit, p, want):
+    """levelize(multi_value=True): groups = maximal runs of a level's bootstraps on one lincomb (reference fbs_exec_env.py:93-100
+    de-duplicates LinearProds, so tables on equal lincombs share it); they partition the level and never cross levels."""
+    e = next(x for x in load_ref_mapped() if x["circuit"] == circuit and x["p"] == p and x["mapper"] == "search")
+    from tfhe_fbs_map_b200.formats import read_lbf
+    prog = levelize(read_lbf(e["lbf"]), p, multi_value=True)
+    a = prog.arrays
+    gf, gl = a["grp_first"], a["grp_level_ptr"]
+    assert prog.multi_value and prog.n_rotations == prog.n_groups == len(gf) - 1 and gf[0] == 0 and gf[-1] == prog.n_boots
+    if want:
+        assert (prog.n_boots, prog.n_groups) == want
+    for lv in range(prog.n_levels):
+        assert gf[gl[lv]] == a["bs_level_ptr"][lv] or gl[lv] == gl[lv + 1]
+        for g in range(gl[lv], gl[lv + 1]):
+            q0, q1 = gf[g], gf[g + 1]
+            assert q0 < q1 <= a["bs_level_ptr"][lv + 1]
+            assert len(set(a["bs_lc"][q0:q1])) == 1
+            if g + 1 < gl[lv + 1]:
+                assert a["bs_lc"][q1] != a["bs_lc"][q0]
+    d = prog.c_desc()
+    assert d.n_groups == prog.n_groups
+    plain = levelize(read_lbf(e["lbf"]), p)
+    assert not plain.multi_value and plain.c_desc().n_groups == 0 and plain.n_rotations == plain.n_boots

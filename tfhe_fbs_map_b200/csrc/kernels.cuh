@@ -790,10 +790,10 @@ struct BR2Cfg {
 #define FBS_TW_SMEM 1
 #endif
 #ifndef FBS_TW_SMEM_PB1
-#define FBS_TW_SMEM_PB1 0
+#define FBS_TW_SMEM_PB1 1      /* measured: 2.968 -> 2.937 ms per wave of 148 one-bootstrap CTAs */
 #endif
     // NTT twiddle table in shared memory (16 B per entry): at M = 2 always; at M = 3 the two-bootstrap CTA has no room for it, the
-    // one-bootstrap tail variant has (experiment FBS_TW_SMEM_PB1)
+    // one-bootstrap tail variant has (FBS_TW_SMEM_PB1)
     static constexpr bool TWS = FBS_TW_SMEM != 0 && (M == 2 || (FBS_TW_SMEM_PB1 != 0 && PB == 1));
     static constexpr size_t tw_w = TWS ? 2 * (size_t)N : 0;
     // Key slice = every key word the CTA needs for ONE of the 8 elements a thread holds: [tau >> 5][c < NC][u < G][v < G][tau & 31]; a
