@@ -62,6 +62,9 @@ template <int LOGN, int K, int PB, int TP, int M> static size_t br2_smem(int n) 
 #ifndef FBS_SETA_TP
 #define FBS_SETA_TP 2     /* bootstraps per thread in the set-A kernel: 2 = every thread carries both bootstraps of its CTA */
 #endif
+#ifndef FBS_AUTO_PRIME_SPLIT
+#define FBS_AUTO_PRIME_SPLIT 0     /* auto mode prefers the packed (0) or the prime-split (1) cluster kernel of a size */
+#endif
 static const BRVariant g_br_variants[] = {
     BRV(11, 1, 1, true, 2, FBS_SETA_TP),   // set A: two bootstraps per CTA share the TMA-streamed BSK row (192 KB shared memory)
     BRV(11, 1, 1, true, 1, 1),             // set A, one bootstrap per CTA: used when a launch has no more jobs than SMs
@@ -74,41 +77,48 @@ static const BRVariant g_br_variants[] = {
     BRV2(9, 1, 2, 2, 3),                           // toy3v
 };
 
-// cluster-split low-latency kernels (one bootstrap over C = 2^LOGC CTAs), for launches that would leave SMs idle
-template <int LOGN, int K, int M, int LOGC>
-static cudaError_t brc_launch(const BRArgs &a, long long jobs, size_t smem, cudaStream_t st)
+// cluster-split low-latency kernels (one bootstrap over C = 2^LOGC CTAs), for launches that would leave SMs idle; PS = prime-split
+// variant (two threads per ring element, one per RNS prime: k_blind_rotate_cs)
+template <int LOGN, int K, int M, int LOGC, bool PS>
+static void brc_config(cudaLaunchConfig_t &cfg, cudaLaunchAttribute *at, unsigned clusters, size_t smem, cudaStream_t st)
 {
     using Cf = BRCCfg<LOGN, K, M, LOGC>;
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)((jobs - a.job_begin) << LOGC)); cfg.blockDim = dim3(Cf::THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
-    cudaLaunchAttribute at[1];
+    cfg = cudaLaunchConfig_t{};
+    cfg.gridDim = dim3(clusters << LOGC); cfg.blockDim = dim3((PS ? 2 : 1) * Cf::THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
     at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 1 << LOGC; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, k_blind_rotate_cl<LOGN, K, M, LOGC>, a);
 }
-template <int LOGN, int K, int M, int LOGC>
+template <int LOGN, int K, int M, int LOGC, bool PS>
+static cudaError_t brc_launch(const BRArgs &a, long long jobs, size_t smem, cudaStream_t st)
+{
+    cudaLaunchConfig_t cfg; cudaLaunchAttribute at[1];
+    brc_config<LOGN, K, M, LOGC, PS>(cfg, at, (unsigned)(jobs - a.job_begin), smem, st);
+    if constexpr (PS) return cudaLaunchKernelEx(&cfg, k_blind_rotate_cs<LOGN, K, M, LOGC>, a);
+    else return cudaLaunchKernelEx(&cfg, k_blind_rotate_cl<LOGN, K, M, LOGC>, a);
+}
+template <int LOGN, int K, int M, int LOGC, bool PS>
 static cudaError_t brc_prepare(size_t smem)
 {
-    return cudaFuncSetAttribute(k_blind_rotate_cl<LOGN, K, M, LOGC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if constexpr (PS) return cudaFuncSetAttribute(k_blind_rotate_cs<LOGN, K, M, LOGC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    else return cudaFuncSetAttribute(k_blind_rotate_cl<LOGN, K, M, LOGC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 }
 template <int LOGN, int K, int M, int LOGC> static size_t brc_smem(int n) { return BRCCfg<LOGN, K, M, LOGC>::smem_bytes(n); }
 // how many clusters of this kernel the device can hold at once (the hardware may strand SMs: 33 clusters of 4 on a 148-SM B200)
-template <int LOGN, int K, int M, int LOGC>
+template <int LOGN, int K, int M, int LOGC, bool PS>
 static cudaError_t brc_max_clusters(size_t smem, int *out)
 {
-    using Cf = BRCCfg<LOGN, K, M, LOGC>;
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(1 << LOGC); cfg.blockDim = dim3(Cf::THREADS); cfg.dynamicSmemBytes = smem;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 1 << LOGC; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-    cfg.attrs = at; cfg.numAttrs = 1;
-    return cudaOccupancyMaxActiveClusters(out, k_blind_rotate_cl<LOGN, K, M, LOGC>, &cfg);
+    cudaLaunchConfig_t cfg; cudaLaunchAttribute at[1];
+    brc_config<LOGN, K, M, LOGC, PS>(cfg, at, 1, smem, nullptr);
+    if constexpr (PS) return cudaOccupancyMaxActiveClusters(out, k_blind_rotate_cs<LOGN, K, M, LOGC>, &cfg);
+    else return cudaOccupancyMaxActiveClusters(out, k_blind_rotate_cl<LOGN, K, M, LOGC>, &cfg);
 }
-struct BRCVariant { int logN, k, unr, logC; size_t (*smem)(int n); br_launch_fn launch; cudaError_t (*prepare)(size_t smem); cudaError_t (*max_clusters)(size_t smem, int *out); };
-#define BRCV(LOGN, K, M, LOGC) { LOGN, K, M, LOGC, brc_smem<LOGN, K, M, LOGC>, brc_launch<LOGN, K, M, LOGC>, brc_prepare<LOGN, K, M, LOGC>, brc_max_clusters<LOGN, K, M, LOGC> }
+struct BRCVariant { int logN, k, unr, logC; bool ps; size_t (*smem)(int n); br_launch_fn launch; cudaError_t (*prepare)(size_t smem); cudaError_t (*max_clusters)(size_t smem, int *out); };
+#define BRCV(LOGN, K, M, LOGC, PS) { LOGN, K, M, LOGC, PS, brc_smem<LOGN, K, M, LOGC>, brc_launch<LOGN, K, M, LOGC, PS>, brc_prepare<LOGN, K, M, LOGC, PS>, brc_max_clusters<LOGN, K, M, LOGC, PS> }
 static const BRCVariant g_brc_variants[] = {
-    BRCV(11, 1, 3, 1), BRCV(11, 1, 3, 2), BRCV(11, 1, 3, 3),      // sets A3 / toy5v: clusters of 2, 4, 8
-    BRCV(11, 1, 2, 1), BRCV(11, 1, 2, 2), BRCV(11, 1, 2, 3),      // sets A2 / toy5u
+    BRCV(11, 1, 3, 1, false), BRCV(11, 1, 3, 2, false), BRCV(11, 1, 3, 3, false),      // sets A3 / toy5v: clusters of 2, 4, 8
+    BRCV(11, 1, 2, 1, false), BRCV(11, 1, 2, 2, false), BRCV(11, 1, 2, 3, false),      // sets A2 / toy5u
+    BRCV(11, 1, 3, 1, true), BRCV(11, 1, 3, 2, true), BRCV(11, 1, 3, 3, true),         // prime-split twins
+    BRCV(11, 1, 2, 1, true), BRCV(11, 1, 2, 2, true), BRCV(11, 1, 2, 3, true),
 };
 
 typedef void (*ntt_launch_fn)(const u64 *, u64 *, int, const fq_tw *, const fq_tw *, u32, u32, long long, cudaStream_t, int);
@@ -129,9 +139,9 @@ struct fbs_ctx {
     bool have_keys = false;
     const BRVariant *br = nullptr; size_t br_smem = 0;        // widest variant (most bootstraps per CTA)
     const BRVariant *br1 = nullptr; size_t br1_smem = 0;      // one bootstrap per CTA, for launches with <= sm_count jobs
-    const BRCVariant *brc[4] = {}; size_t brc_smem[4] = {};   // [log2 C]: one bootstrap per cluster of C CTAs ...
-    int brc_max[4] = {};                                      // ... for launches of at most this many jobs (co-resident clusters)
-    int cluster_mode = 0;                                     // 0 auto, 1 never, 2 / 4 / 8 force that cluster size (fbs_ctx_set_cluster)
+    const BRCVariant *brc[2][4] = {}; size_t brc_smem[2][4] = {};   // [prime-split][log2 C]: one bootstrap per cluster of C CTAs ...
+    int brc_max[2][4] = {};                                   // ... for launches of at most this many jobs (co-resident clusters)
+    int cluster_mode = 0;                                     // 0 auto, 1 never, 2 / 4 / 8 force that cluster size, 12 / 14 / 18 its prime-split twin
     u8 *d_s_lwe = nullptr, *d_s_big = nullptr;
     u64 *d_ksk = nullptr, *d_colsum = nullptr, *d_bsk = nullptr, *d_bsk_coef = nullptr;
     u8 *d_kbt = nullptr;                                       // byte-transposed KSK for the tensor-core key switch
@@ -257,7 +267,7 @@ static int ctx_create_impl(const fbs_params *params, int device, uint64_t seed, 
         CK(v.prepare((size_t)prop.sharedMemPerBlockOptin));
         int mc = 0;
         if (v.max_clusters(sm, &mc) != cudaSuccess || mc < 1) { cudaGetLastError(); continue; }
-        c->brc[v.logC] = &v; c->brc_smem[v.logC] = sm; c->brc_max[v.logC] = mc;
+        c->brc[v.ps][v.logC] = &v; c->brc_smem[v.ps][v.logC] = sm; c->brc_max[v.ps][v.logC] = mc;
     }
     CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     for (auto &e : c->ev) CK(cudaEventCreate(&e));
@@ -349,10 +359,11 @@ extern "C" int fbs_ctx_destroy(fbs_ctx *c)
 }
 extern "C" int fbs_ctx_set_cluster(fbs_ctx *c, int32_t mode)
 {
-    if (!c || !(mode == 0 || mode == 1 || mode == 2 || mode == 4 || mode == 8)) return fail(FBS_ERR_ARG, "fbs_ctx_set_cluster: mode must be 0 (auto), 1 (off), 2, 4 or 8");
+    const bool ok = mode == 0 || mode == 1 || mode == 2 || mode == 4 || mode == 8 || mode == 12 || mode == 14 || mode == 18;
+    if (!c || !ok) return fail(FBS_ERR_ARG, "fbs_ctx_set_cluster: mode must be 0 (auto), 1 (off), 2, 4, 8 or 12, 14, 18 (prime-split)");
     if (mode > 1) {
-        int lc = mode == 2 ? 1 : mode == 4 ? 2 : 3;
-        if (!c->brc[lc]) return fail(FBS_ERR_ARG, "fbs_ctx_set_cluster: no cluster kernel of that size for this parameter set");
+        const int sz = mode % 10, lc = sz == 2 ? 1 : sz == 4 ? 2 : 3;
+        if (!c->brc[mode > 10][lc]) return fail(FBS_ERR_ARG, "fbs_ctx_set_cluster: no cluster kernel of that size for this parameter set");
     }
     c->cluster_mode = mode;
     return FBS_OK;
@@ -588,13 +599,20 @@ static int run_level_impl(fbs_ctx *c, fbs_prog *g, int level, int nb, int ne, in
     // Fewer jobs than SMs: split each bootstrap over a cluster of C CTAs, cutting the latency of the launch instead of idling SMs
     // (measured, set A3: 3.0 ms one CTA, 1.87 ms C = 2, 1.34 ms C = 4, 1.38 ms C = 8 per bootstrap; profiles/r2_latency_*).
     // Preference 4, 8, 2 among the sizes whose clusters are all co-resident.  Results are bit-identical to the one-CTA kernels.
-    auto pick_cluster = [&](long long nj) -> int {
-        if (c->cluster_mode == 0) { for (int lc : {2, 3, 1}) if (c->brc[lc] && nj <= c->brc_max[lc]) return lc; return 0; }
-        if (c->cluster_mode > 1) for (int lc = 1; lc <= 3; lc++) if ((1 << lc) == c->cluster_mode && c->brc[lc]) return lc;
+    auto pick_cluster = [&](long long nj) -> int {              // returns log2 C (+ 8 for the prime-split twin), 0 = none
+        if (c->cluster_mode == 0) {
+            for (int lc : {2, 3, 1}) for (int ps : {FBS_AUTO_PRIME_SPLIT, 1 - FBS_AUTO_PRIME_SPLIT}) if (c->brc[ps][lc] && nj <= c->brc_max[ps][lc]) return lc + 8 * ps;
+            return 0;
+        }
+        if (c->cluster_mode > 1) {
+            const int ps = c->cluster_mode > 10, sz = c->cluster_mode % 10;
+            for (int lc = 1; lc <= 3; lc++) if ((1 << lc) == sz && c->brc[ps][lc]) return lc + 8 * ps;
+        }
         return 0;
     };
+    auto launch_cluster = [&](int code, const BRArgs &args) { const int ps = code >> 3, lc = code & 7; return c->brc[ps][lc]->launch(args, jobs, c->brc_smem[ps][lc], st); };
     const int logC = pick_cluster(jobs);
-    if (logC) CK(c->brc[logC]->launch(ba, jobs, c->brc_smem[logC], st));
+    if (logC) CK(launch_cluster(logC, ba));
     else if (c->br1 != c->br && tail > 0 && tail <= c->sm_count) {
         // Full waves run the widest variant (pb bootstraps per CTA, one CTA per SM).  A last partial wave of at most one job per
         // SM goes to a narrower kernel instead of half-idle paired CTAs: cluster-split if its clusters fit the chip, else one
@@ -602,7 +620,7 @@ static int run_level_impl(fbs_ctx *c, fbs_prog *g, int level, int nb, int ne, in
         if (jobs > tail) { BRArgs bw = ba; CK(c->br->launch(bw, jobs - tail, c->br_smem, st)); n_br_launches = 2; }
         ba.job_begin = jobs - tail;
         const int tlc = c->cluster_mode == 0 ? pick_cluster(tail) : 0;
-        if (tlc) CK(c->brc[tlc]->launch(ba, jobs, c->brc_smem[tlc], st));
+        if (tlc) CK(launch_cluster(tlc, ba));
         else CK(c->br1->launch(ba, jobs, c->br1_smem, st));
     } else CK(c->br->launch(ba, jobs, c->br_smem, st));
     if (multi) {

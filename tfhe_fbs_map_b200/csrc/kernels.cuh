@@ -1379,6 +1379,257 @@ __global__ void __launch_bounds__((K + 1) * (1 << (LOGN - LOGC)) / 8, 1) k_blind
 }
 
 // ------------------------------------------------------------------------------------------------------
+// K2s: cluster-split AND prime-split blind rotation.  Same decomposition of one bootstrap over C CTAs as
+// k_blind_rotate_cl, but the two residues (mod p1, mod p2) of every ring element live in two THREADS (adjacent lanes) instead
+// of one: 2x the threads (two warps per scheduler at C = 4), every thread does the butterflies and point-wise products of one
+// prime only.  The transforms, point-wise products and exchanges are independent per prime; only the gadget digit (needs the CRT
+// of both residues: one shuffle with the partner lane) and the sample extraction couple them.  Shared-memory data stays in
+// the packed layout (mod p1 | mod p2 << 32): a thread touches its 32-bit half, a warp = 16 positions x 2 primes touches the same
+// 128 bytes a half-warp of the packed kernels does (conflict-free with the same swizzle).  Bit-identical results.
+// ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void st_async_u32(u32 remote_addr, u32 v, u32 remote_bar)
+{
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(remote_addr), "r"(v), "r"(remote_bar) : "memory");
+}
+template <int LOGN, int K, int M, int LOGC>
+__global__ void __launch_bounds__(2 * (K + 1) * (1 << (LOGN - LOGC)) / 8, 1) k_blind_rotate_cs(BRArgs a)
+{
+    using Cf = BRCCfg<LOGN, K, M, LOGC>;
+    using P = NttPlan<Cf::LOGNS>;
+    constexpr int NC = Cf::NC, N = Cf::N, G = Cf::G, C = Cf::C, Ns = Cf::Ns, Ts = Cf::Ts, R = Cf::R, T = Cf::T, RING = Cf::RING, LOGNS = Cf::LOGNS;
+    constexpr int THREADS = 2 * Cf::THREADS;
+    static_assert(Ts >= 16 && Ts % 16 == 0, "a warp holds 16 thread positions x 2 primes");
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int tid = threadIdx.x, l = tid & 1, g = (tid >> 1) / Ts, tau = (tid >> 1) % Ts, lane = tid & 31;
+    const u32 pr = l ? FQ_P2 : FQ_P1, pinv = l ? FQ_P2_INVNEG : FQ_P1_INVNEG, pr2 = 2 * pr;
+    const int h = (int)cluster_ctarank();
+    const int tau_g = h * Ts + tau;
+    u64 *S = (u64 *)smem_raw;
+    u64 *INF = S + Cf::s_w, *INI = INF + Cf::inbox_w;
+    u64 *PSI = INI + Cf::inbox_w;
+    u64 *TWF = PSI + Cf::psi_w, *TWI = TWF + Cf::tw_w;
+    u64 *RNG = TWI + Cf::tw_w;
+    u64 *full = RNG + (size_t)RING * Cf::slice_w, *empty = full + RING, *xbar = empty + RING;
+    u16 *s_ms = (u16 *)(xbar + 2);
+    const int n = a.n, p = a.p;
+    const int n_pairs = (n + M - 1) / M, n_slices = 8 * n_pairs;
+
+    const long long job = a.job_begin + (long long)(blockIdx.x >> LOGC);
+    const int node = a.grp_first ? a.grp_first[a.node_begin + (int)(job / a.B)] : a.node_begin + (int)(job / a.B);
+    const long long inst = job % a.B;
+    {
+        const u16 *ms = a.ms + ((size_t)(a.bs_lc[node] - a.lc_begin) * a.B + inst) * (size_t)(n + 1);
+        for (int i = tid; i <= n; i += THREADS) s_ms[i] = ms[i];
+    }
+    const int tab0 = a.bs_tab_ptr[node], tabL = a.bs_tab_ptr[node + 1] - tab0, mode = a.bs_mode[node];
+    auto psw = [](u32 x) { return x ^ (((x >> 4) ^ (x >> 8)) & 15u); };
+    for (int i = tid; i < 2 * N; i += THREADS) PSI[psw((u32)i)] = a.psi_pow[i];
+    for (int i = 1 + tid; i < Ns; i += THREADS) {
+        ((uint4 *)TWF)[i] = __ldg((const uint4 *)a.psi_rev + ntt_local_src(i, C + h));
+        ((uint4 *)TWI)[i] = __ldg((const uint4 *)a.psi_rev + ntt_local_src(i, 2 * C - 1 - h));
+    }
+    u32 cw[C], cws[C];                                            // cross-stage twiddles psi_rev[1 .. C) of this thread's prime
+#pragma unroll
+    for (int i = 1; i < C; i++) fq_tw_load1<false>(a.psi_rev + i, l, cw[i], cws[i]);
+    cw[0] = cw[1]; cws[0] = cws[1];
+    if (tid == 0) {
+        for (int r = 0; r < RING; r++) { mbar_init(full + r, 1); mbar_init(empty + r, THREADS / 32); }
+        mbar_init(xbar, 1); mbar_init(xbar + 1, 1);
+    }
+    __syncthreads();
+    cluster_sync_all();
+    auto issue_slice = [&](int sl, int slot) {                    // called by thread 0
+        fence_proxy_async();
+        mbar_expect_tx(full + slot, (u32)(Cf::slice_w * 8));
+        tma_load_1d(RNG + (size_t)slot * Cf::slice_w, a.bsk + ((size_t)sl * C + h) * Cf::slice_w, (u32)(Cf::slice_w * 8), full + slot);
+    };
+    if (tid == 0) for (int sl = 0; sl < RING && sl < n_slices; sl++) issue_slice(sl, sl);
+    u32 r_inf[C], r_ini[C], r_xf[C], r_xi[C];
+#pragma unroll
+    for (int c = 0; c < C; c++) {
+        r_inf[c] = mapa_shared(smem_u32(INF), (u32)c); r_ini[c] = mapa_shared(smem_u32(INI), (u32)c);
+        r_xf[c] = mapa_shared(smem_u32(xbar), (u32)c); r_xi[c] = mapa_shared(smem_u32(xbar + 1), (u32)c);
+    }
+    const u32 half = 4u * (u32)l;                                 // this thread's half of every packed word
+    const u32 send_off = (u32)((((g * 8 + h * R) * Ts) + tau) * 8) + half;
+    const u32 inbox_bytes = (u32)(Cf::inbox_w * 8);
+    // ---- accumulator init: register e = hh*R + ri holds coefficient j = hh*Ns + h*(Ns/C) + ri*Ts + tau of polynomial g, residue of prime l
+    u32 av[8];
+    {
+        const u64 delta = fbs_delta(p), off = fq_mul((u64)mode, delta >> 1);
+        const int bt = s_ms[n];
+#pragma unroll
+        for (int e = 0; e < 8; e++) {
+            const int j = (e / R) * Ns + h * (Ns / C) + (e % R) * Ts + tau;
+            u64 val = 0;
+            if (g == K) {
+                int src = j + bt;
+                bool neg = false;
+                if (src >= 2 * N) src -= 2 * N;
+                if (src >= N) { src -= N; neg = true; }
+                int x = (int)((2LL * src * p + N) / (2LL * N));
+                if (x >= p) { x -= p; neg = neg != (a.grp_first == nullptr); }
+                const u64 tvx = (x < tabL) ? (u64)__ldg(a.bs_tab + tab0 + x) : 0;
+                const u64 F = a.grp_first ? fbs_half_delta(p) : fq_sub(fq_mul(tvx, delta), off);
+                val = neg ? fq_neg(F) : F;
+            }
+            av[e] = (u32)(val % pr);
+        }
+    }
+    const int bar_g = 1 + g;
+    auto gsync = [bar_g] { bar_sync_named(bar_g, 2 * Ts); };
+    const int bar_x = 1 + G + (tau >> 4);
+    auto xsync = [bar_x] { bar_sync_named(bar_x, G * 32); };
+    static_assert(1 + G + Ts / 16 <= 16, "named barriers");
+    const int beta = a.beta;
+    const u64 rc = 1ULL << (62 - beta);
+    constexpr int SH = LOGNS + 3;
+    unsigned char *Sb = (unsigned char *)S + half;
+    u32 bo[LOGNS];
+#pragma unroll
+    for (int lb = 0; lb < LOGNS; lb++) bo[lb] = P::tau_boff(tau, lb) | ((u32)g << SH);
+    static_assert(P::idx(1, 1, P::inv_lb(P::NPASS - 1)) == 1 + Ts && P::idx(1, 1, P::fwd_lb(0)) == 1 + Ts, "local transforms start / end with register e at local index tau + e*Ts");
+    const u32 odd0 = 2u * (__brev((u32)tau_g) >> (32 - (LOGN - 3))) + 1u;
+    u32 koff[G];
+#pragma unroll
+    for (int og = 0; og < G; og++) { int gg = g + og; if (gg >= G) gg -= G; koff[og] = (u32)((((tau >> 5) * NC * G * G + gg * G + g) * 32 + (tau & 31)) * 8) + half; }
+    int slot = 0; u32 par = 0;
+    const fq_tw *twf = (const fq_tw *)TWF, *twi = (const fq_tw *)TWI;
+    const unsigned char *INFb = (const unsigned char *)INF + half, *INIb = (const unsigned char *)INI + half, *PSIb = (const unsigned char *)PSI + half;
+
+    for (int t = 0; t < n_pairs; t++) {
+        const u32 xpar = (u32)(t & 1);
+        // ---- decompose (the digit needs both residues: one shuffle with the partner lane), cross butterflies, forward exchange
+        u32 dg[8];
+#pragma unroll
+        for (int e = 0; e < 8; e++) {
+            const u32 other = __shfl_xor_sync(0xffffffffu, av[e], 1);
+            rns2 v; v.a = l ? other : av[e]; v.b = l ? av[e] : other;
+            const u32 d = (u32)fbs_digit1_t(rns_crt_hi(v), v.a, beta, rc);
+            dg[e] = d + pr;
+        }
+        ntt_cross_fwd_1p<LOGC>(dg, cw, cws, pr, a.zero);
+        if (tid == 0) mbar_expect_tx(xbar, inbox_bytes);
+#pragma unroll
+        for (int e = 0; e < 8; e++) st_async_u32(r_inf[e / R] + send_off + (u32)((e % R) * Ts * 8), dg[e], r_xf[e / R]);
+        mbar_wait_cluster(xbar, xpar);
+#pragma unroll
+        for (int e = 0; e < 8; e++) dg[e] = *(const u32 *)(INFb + ((size_t)(g * 8 + e) * Ts + tau) * 8);
+        ntt_fwd1p_from<LOGNS, 0, 4, decltype(gsync), true>(dg, tau, Sb, bo, twf, l, pr, gsync, true, a.zero);
+#pragma unroll
+        for (int e = 0; e < 8; e++) {
+            dg[e] = r32_fold(dg[e], pr2);
+            *(u32 *)(Sb + (bo[0] ^ P::elem_boff(e, 0))) = dg[e];
+        }
+        u32 x[8];
+        auto release_slot = [&](int e) {
+            __syncwarp();
+            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(empty + slot)) : "memory");
+            if (tid == 0) {
+                const int nxt = 8 * t + e + RING;
+                if (nxt < n_slices) { mbar_wait(empty + slot, par); issue_slice(nxt, slot); }
+            }
+            if (++slot == RING) { slot = 0; par ^= 1; }
+        };
+        constexpr bool fast_psi = (LOGN - 2 >= 9) && (LOGN + 1 <= 12);
+        constexpr u32 HMUL = 8u * ((1u << (LOGN - 2)) | (fast_psi ? (1u << (LOGN - 2 - 8)) : 0u));
+        u32 PK[NC];
+        {
+            u32 ai[M];
+#pragma unroll
+            for (int i = 0; i < M; i++) ai[i] = (M * t + i < n) ? s_ms[M * t + i] : 0u;
+#pragma unroll
+            for (int c = 0; c < NC; c++) {
+                u32 E = 0;
+#pragma unroll
+                for (int i = 0; i < M; i++) if ((fbs_unroll_mask(M, c) >> i) & 1) E += ai[i];
+                const u32 x0 = (E * odd0) & (2 * N - 1);
+                if constexpr (fast_psi) {
+                    const u32 lo = x0 & ((1u << (LOGN - 2)) - 1);
+                    PK[c] = (8u * (lo ^ (((lo >> 4) ^ (lo >> 8)) & 15u))) | ((x0 >> (LOGN - 2)) << 16) | ((E & 7u) << 20);
+                } else PK[c] = x0 | ((E & 7u) << 20);
+            }
+        }
+        xsync();
+#pragma unroll
+        for (int e = 0; e < 8; e++) {
+            const u32 o = bo[0] ^ P::elem_boff(e, 0);
+            constexpr int BR3[8] = {0, 4, 2, 6, 1, 5, 3, 7};
+            mbar_wait(full + slot, par);
+            const unsigned char *ks = (const unsigned char *)(RNG + (size_t)slot * Cf::slice_w);
+            auto factor = [&](int c) -> u32 {
+                const u32 pk = PK[c];
+                if constexpr (fast_psi) {
+                    const u32 hh = ((pk >> 16) + (u32)BR3[e] * (pk >> 20)) & 7u;
+                    return *(const u32 *)(PSIb + ((pk & 0xFFFFu) ^ (hh * HMUL)));
+                } else {
+                    const u32 xi = ((pk & 0xFFFFu) + (((u32)BR3[e] * (pk >> 20)) << (LOGN - 2))) & (2 * N - 1);
+                    return *(const u32 *)(PSIb + 8u * psw(xi));
+                }
+            };
+            u64 pa[G];
+#pragma unroll
+            for (int c = 0; c < NC; c++) {
+                const u32 f = factor(c);
+#pragma unroll
+                for (int og = 0; og < G; og++) {
+                    const u32 kk = *(const u32 *)(ks + koff[og] + (size_t)c * G * G * 32 * 8);
+                    pa[og] = (c == 0) ? r32_mulwide(f, kk) : r32_madwide(f, kk, pa[og]);
+                }
+            }
+            u64 oa = 0;
+#pragma unroll
+            for (int og = 0; og < G; og++) {
+                const u32 ba = r32_redc(pa[og], pr, pinv);
+                int gg = g + og; if (gg >= G) gg -= G;
+                const u32 xg = (og == 0) ? 0u : (G == 2) ? (1u << SH) : ((u32)(g ^ gg) << SH);
+                const u32 d = *(const u32 *)(Sb + (o ^ xg));
+                oa = (og == 0) ? r32_mulwide(d, ba) : r32_madwide(d, ba, oa);
+            }
+            x[e] = r32_fold(r32_redc(oa, pr, pinv), pr2);
+            release_slot(e);
+        }
+        auto after_pass0 = [&] { xsync(); };
+        ntt_inv1p_from<LOGNS, 0, 4, decltype(after_pass0), decltype(gsync), true>(x, tau, Sb, bo, twi, l, pr, after_pass0, gsync, a.zero);
+        if (tid == 0) mbar_expect_tx(xbar + 1, inbox_bytes);
+#pragma unroll
+        for (int e = 0; e < 8; e++) st_async_u32(r_ini[e / R] + send_off + (u32)((e % R) * Ts * 8), x[e], r_xi[e / R]);
+        mbar_wait_cluster(xbar + 1, xpar);
+#pragma unroll
+        for (int e = 0; e < 8; e++) x[e] = *(const u32 *)(INIb + ((size_t)(g * 8 + e) * Ts + tau) * 8);
+        ntt_cross_inv_1p<LOGC>(x, cw, cws, pr, a.zero);
+#pragma unroll
+        for (int e = 0; e < 8; e++) av[e] = r32_csub(r32_fold(av[e] + x[e] + a.zero, pr2), pr);
+    }
+    // ---- K3: sample extraction from the registers; the two lanes of a position share the 8 words (even e: lane of p1, odd e: lane of p2)
+    {
+        const size_t CT = (size_t)K * N + 1;
+        const size_t off = ((size_t)a.bs_slot[node] * a.B + inst) * CT;
+        u64 *out = a.wires + off;
+#pragma unroll
+        for (int e = 0; e < 8; e++) {
+            const u32 other = __shfl_xor_sync(0xffffffffu, av[e], 1);
+            if ((e & 1) != l) continue;
+            rns2 v; v.a = l ? other : av[e]; v.b = l ? av[e] : other;
+            const int j = (e / R) * Ns + h * (Ns / C) + (e % R) * Ts + tau;
+            if (a.grp_first) {
+            } else if (g < K) {
+                const int jj = (j == 0) ? 0 : N - j;
+                const u64 val = rns_to_int(j == 0 ? v : rns_neg(v));
+                out[(size_t)g * N + jj] = val;
+                for (int prr = 0; prr < a.n_peers; prr++) a.peer_wires[prr][off + (size_t)g * N + jj] = val;
+            } else if (j == 0) {
+                const u64 val = fq_add(rns_to_int(v), fq_mul((u64)mode, fbs_delta(p) >> 1));
+                out[(size_t)K * N] = val;
+                for (int prr = 0; prr < a.n_peers; prr++) a.peer_wires[prr][off + (size_t)K * N] = val;
+            }
+            if (a.tap_acc) a.tap_acc[(size_t)job * G * N + (size_t)g * N + j] = rns_to_int(v);
+        }
+    }
+    cluster_sync_all();
+}
+
+// ------------------------------------------------------------------------------------------------------
 // Multi-value bootstrap, finishing step (oracle/tfhe_ref.c: ref_multi_extract).  The blind rotation of a
 // (group, instance) job left ACC = GLWE(X^-mu * TV0), TV0 = H (1 + X + .. + X^(N-1)), as integers mod q in acc[job][(K+1)][N].
 // For every table f of the group: out_f = SampleExtract(ACC * e_f) + s*H, where e_f is the sparse polynomial with

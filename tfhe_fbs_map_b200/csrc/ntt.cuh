@@ -51,6 +51,12 @@ struct NttPlan {
         for (int i = 0; i < N; i++) if ((owner(i, lb0) >> 5) != (owner(i, lb1) >> 5)) return false;
         return true;
     }
+    // the same with 2^wlog thread positions per warp (prime-split kernels: a warp = 16 positions x 2 primes)
+    FQ_HDM static constexpr bool intra_warp_w(int lb0, int lb1, int wlog)
+    {
+        for (int i = 0; i < N; i++) if ((owner(i, lb0) >> wlog) != (owner(i, lb1) >> wlog)) return false;
+        return true;
+    }
     FQ_HDM static constexpr u32 tau_boff(int tau, int lb) { return 8u * (u32)swz(idx(tau, 0, lb)); }
     FQ_HDM static constexpr u32 elem_boff(int e, int lb) { return 8u * (u32)swz(idx(0, e, lb)); }
 };
@@ -211,6 +217,113 @@ FQ_HD void ntt_cross_inv(rns2 (&x)[8], const fq_tw *__restrict__ cw /* psi_rev[0
     }
 }
 
+// ---- prime-split passes: a thread transforms the residues of ONE prime (l = 0: p1, l = 1: p2) of its 8 positions ----------
+// Same index / twiddle logic as ntt_fwd_pass_n / ntt_inv_pass_n; the two residues of a position live in two threads (adjacent
+// lanes), which doubles the threads per bootstrap and halves every thread's butterfly and point-wise work (k_blind_rotate_cs).
+template <bool TWS = false>
+FQ_HD void fq_tw_load1(const fq_tw *p, int l, u32 &w, u32 &ws)
+{
+#if defined(__CUDA_ARCH__)
+    if constexpr (TWS) {
+        asm("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(w), "=r"(ws) : "r"((u32)__cvta_generic_to_shared(p) + 8u * (u32)l));
+    } else {
+        const uint2 v = __ldg(reinterpret_cast<const uint2 *>(p) + l);
+        w = v.x; ws = v.y;
+    }
+#else
+    w = l ? p->w2 : p->w1; ws = l ? p->ws2 : p->ws1;
+#endif
+}
+template <int LOGN, int PASS, bool TWS = false>
+FQ_HD void ntt_fwd_pass_1p(u32 (&x)[8], int tau, const fq_tw *__restrict__ psi_rev, int l, u32 p, u32 z = 0)
+{
+    using P = NttPlan<LOGN>;
+    constexpr int hi = P::fwd_hi(PASS), lb = P::fwd_lb(PASS);
+    const int th = tau >> lb;
+    const u32 p2 = 2 * p;
+#pragma unroll
+    for (int q = 2; q >= 0; q--) {
+        if (lb + q > hi) continue;
+        const int bit = lb + q, m = 1 << (LOGN - 1 - bit);
+#pragma unroll
+        for (int e0 = 0; e0 < 8; e0++) {
+            if (e0 & (1 << q)) continue;
+            const int e1 = e0 | (1 << q);
+            u32 w, ws;
+            fq_tw_load1<TWS>(psi_rev + m + ((th << (2 - q)) | (e0 >> (q + 1))), l, w, ws);
+            const u32 u = r32_fold(x[e0], p2), v = r32_mul_shoup(x[e1], w, ws, p);
+            x[e0] = u + v + z; x[e1] = u - v + z + p2;
+        }
+    }
+}
+template <int LOGN, int PASS, bool TWS = false>
+FQ_HD void ntt_inv_pass_1p(u32 (&x)[8], int tau, const fq_tw *__restrict__ psi_rev /* forward table, read mirrored */, int l, u32 p, u32 z = 0)
+{
+    using P = NttPlan<LOGN>;
+    constexpr int lo = P::inv_lo(PASS), lb = P::inv_lb(PASS);
+    const int th = tau >> lb;
+    const u32 p2 = 2 * p;
+#pragma unroll
+    for (int q = 0; q < 3; q++) {
+        if (lb + q < lo) continue;
+        const int bit = lb + q, m = 1 << (LOGN - 1 - bit);
+#pragma unroll
+        for (int e0 = 0; e0 < 8; e0++) {
+            if (e0 & (1 << q)) continue;
+            const int e1 = e0 | (1 << q);
+            const int ti = (th << (2 - q)) | (e0 >> (q + 1));
+            u32 w, ws;
+            fq_tw_load1<TWS>(psi_rev + (2 * m - 1 - ti), l, w, ws);
+            const u32 u = x[e0], v = x[e1];
+            x[e0] = r32_fold(u + v + z, p2);
+            x[e1] = r32_mul_shoup(v - u + p2, w, ws, p);
+        }
+    }
+}
+template <int LOGC>
+FQ_HD void ntt_cross_fwd_1p(u32 (&x)[8], const u32 (&cw)[1 << LOGC], const u32 (&cws)[1 << LOGC], u32 p, u32 z = 0)
+{
+    constexpr int C = 1 << LOGC, R = 8 / C;
+    const u32 p2 = 2 * p;
+#pragma unroll
+    for (int s = LOGC - 1; s >= 0; s--) {
+        const int m = 1 << (LOGC - 1 - s);
+#pragma unroll
+        for (int h0 = 0; h0 < C; h0++) {
+            if (h0 & (1 << s)) continue;
+            const int h1 = h0 | (1 << s), ti = m + (h0 >> (s + 1));
+#pragma unroll
+            for (int ri = 0; ri < R; ri++) {
+                const int e0 = h0 * R + ri, e1 = h1 * R + ri;
+                const u32 u = r32_fold(x[e0], p2), v = r32_mul_shoup(x[e1], cw[ti], cws[ti], p);
+                x[e0] = u + v + z; x[e1] = u - v + z + p2;
+            }
+        }
+    }
+}
+template <int LOGC>
+FQ_HD void ntt_cross_inv_1p(u32 (&x)[8], const u32 (&cw)[1 << LOGC], const u32 (&cws)[1 << LOGC], u32 p, u32 z = 0)
+{
+    constexpr int C = 1 << LOGC, R = 8 / C;
+    const u32 p2 = 2 * p;
+#pragma unroll
+    for (int s = 0; s < LOGC; s++) {
+        const int m = 1 << (LOGC - 1 - s);
+#pragma unroll
+        for (int h0 = 0; h0 < C; h0++) {
+            if (h0 & (1 << s)) continue;
+            const int h1 = h0 | (1 << s), ti = 2 * m - 1 - (h0 >> (s + 1));
+#pragma unroll
+            for (int ri = 0; ri < R; ri++) {
+                const int e0 = h0 * R + ri, e1 = h1 * R + ri;
+                const u32 u = x[e0], v = x[e1];
+                x[e0] = r32_fold(u + v + z, p2);
+                x[e1] = r32_mul_shoup(v - u + p2, cw[ti], cws[ti], p);
+            }
+        }
+    }
+}
+
 #if defined(__CUDACC__)
 // ---- device drivers: transposes through two alternating swizzled buffers -------------------------------
 // `sync` is a callable that synchronises the T threads working on this polynomial.
@@ -294,6 +407,42 @@ __device__ __forceinline__ void ntt_inv1_from(rns2 (&x)[NB][8], int tau, unsigne
             for (int b = 0; b < NB; b++) x[b][e] = rns_unpack(*(const u64 *)(buf + b * stride + o));
         }
         ntt_inv1_from<LOGN, PASS + 1, NB, Sync, Sync, TWS>(x, tau, buf, stride, bo, psi_rev, sync, sync, z);
+    }
+}
+
+// ---- prime-split drivers: as ntt_fwd1_from / ntt_inv1_from with one bootstrap per thread and 32-bit accesses to the packed scratch
+// (`buf` already points at this thread's half of the words: + 4*l); WLOG = log2 of the thread positions per warp (4: a warp
+// holds 16 positions x 2 primes)
+template <int LOGN, int PASS, int WLOG, class Sync, bool TWS = true>
+__device__ __forceinline__ void ntt_fwd1p_from(u32 (&x)[8], int tau, unsigned char *buf, const u32 (&bo)[LOGN], const fq_tw *tw, int l, u32 p, Sync sync, bool buf_free, u32 z = 0)
+{
+    using P = NttPlan<LOGN>;
+    ntt_fwd_pass_1p<LOGN, PASS, TWS>(x, tau, tw, l, p, z);
+    if constexpr (PASS + 1 < P::NPASS) {
+        constexpr int lb0 = P::fwd_lb(PASS), lb1 = P::fwd_lb(PASS + 1);
+        if (!buf_free) sync();
+#pragma unroll
+        for (int e = 0; e < 8; e++) *(u32 *)(buf + (bo[lb0] ^ P::elem_boff(e, lb0))) = x[e];
+        if constexpr (P::intra_warp_w(lb0, lb1, WLOG)) __syncwarp(); else sync();
+#pragma unroll
+        for (int e = 0; e < 8; e++) x[e] = *(const u32 *)(buf + (bo[lb1] ^ P::elem_boff(e, lb1)));
+        ntt_fwd1p_from<LOGN, PASS + 1, WLOG, Sync, TWS>(x, tau, buf, bo, tw, l, p, sync, true, z);
+    }
+}
+template <int LOGN, int PASS, int WLOG, class Sync0, class Sync, bool TWS = true>
+__device__ __forceinline__ void ntt_inv1p_from(u32 (&x)[8], int tau, unsigned char *buf, const u32 (&bo)[LOGN], const fq_tw *tw, int l, u32 p, Sync0 after_pass0, Sync sync, u32 z = 0)
+{
+    using P = NttPlan<LOGN>;
+    ntt_inv_pass_1p<LOGN, PASS, TWS>(x, tau, tw, l, p, z);
+    if constexpr (PASS == 0) after_pass0();
+    if constexpr (PASS + 1 < P::NPASS) {
+        constexpr int lb0 = P::inv_lb(PASS), lb1 = P::inv_lb(PASS + 1);
+#pragma unroll
+        for (int e = 0; e < 8; e++) *(u32 *)(buf + (bo[lb0] ^ P::elem_boff(e, lb0))) = x[e];
+        if constexpr (P::intra_warp_w(lb0, lb1, WLOG)) __syncwarp(); else sync();
+#pragma unroll
+        for (int e = 0; e < 8; e++) x[e] = *(const u32 *)(buf + (bo[lb1] ^ P::elem_boff(e, lb1)));
+        ntt_inv1p_from<LOGN, PASS + 1, WLOG, Sync, Sync, TWS>(x, tau, buf, bo, tw, l, p, sync, sync, z);
     }
 }
 
