@@ -62,9 +62,6 @@ template <int LOGN, int K, int PB, int TP, int M> static size_t br2_smem(int n) 
 #ifndef FBS_SETA_TP
 #define FBS_SETA_TP 2     /* bootstraps per thread in the set-A kernel: 2 = every thread carries both bootstraps of its CTA */
 #endif
-#ifndef FBS_AUTO_PRIME_SPLIT
-#define FBS_AUTO_PRIME_SPLIT 0     /* auto mode prefers the packed (0) or the prime-split (1) cluster kernel of a size */
-#endif
 static const BRVariant g_br_variants[] = {
     BRV(11, 1, 1, true, 2, FBS_SETA_TP),   // set A: two bootstraps per CTA share the TMA-streamed BSK row (192 KB shared memory)
     BRV(11, 1, 1, true, 1, 1),             // set A, one bootstrap per CTA: used when a launch has no more jobs than SMs
@@ -596,12 +593,14 @@ static int run_level_impl(fbs_ctx *c, fbs_prog *g, int level, int nb, int ne, in
     ba.lc_begin = lc0; ba.n = n; ba.p = g->p; ba.beta = P.bsk_beta;
     const long long wave = (long long)c->sm_count * c->br->pb, tail = jobs % wave;
     int n_br_launches = 1;
-    // Fewer jobs than SMs: split each bootstrap over a cluster of C CTAs, cutting the latency of the launch instead of idling SMs
-    // (measured, set A3: 3.0 ms one CTA, 1.87 ms C = 2, 1.34 ms C = 4, 1.38 ms C = 8 per bootstrap; profiles/r2_latency_*).
-    // Preference 4, 8, 2 among the sizes whose clusters are all co-resident.  Results are bit-identical to the one-CTA kernels.
+    // Fewer jobs than SMs: split each bootstrap over a cluster of C CTAs, cutting the latency of the launch instead of idling SMs.
+    // Measured, set A3, per bootstrap (profiles/r2_latency_A3_1gpu_v3.jsonl): one CTA 3.0 ms; packed clusters C = 2 / 4 / 8: 1.87 /
+    // 1.34 / 1.38 ms; prime-split clusters C = 2 / 4 / 8: 2.02 / 1.20 / 0.93 ms (1.14 ms with 33 of them, two CTAs per SM).
+    // Preference: the fastest kind whose clusters are all co-resident.  Results are bit-identical to the one-CTA kernels.
     auto pick_cluster = [&](long long nj) -> int {              // returns log2 C (+ 8 for the prime-split twin), 0 = none
         if (c->cluster_mode == 0) {
-            for (int lc : {2, 3, 1}) for (int ps : {FBS_AUTO_PRIME_SPLIT, 1 - FBS_AUTO_PRIME_SPLIT}) if (c->brc[ps][lc] && nj <= c->brc_max[ps][lc]) return lc + 8 * ps;
+            static const int pref[][2] = {{1, 3}, {1, 2}, {0, 2}, {0, 3}, {0, 1}, {1, 1}};     // {prime-split, log2 C}
+            for (auto &pc : pref) if (c->brc[pc[0]][pc[1]] && nj <= c->brc_max[pc[0]][pc[1]]) return pc[1] + 8 * pc[0];
             return 0;
         }
         if (c->cluster_mode > 1) {
