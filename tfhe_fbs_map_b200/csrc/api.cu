@@ -75,47 +75,42 @@ static const BRVariant g_br_variants[] = {
 };
 
 // cluster-split low-latency kernels (one bootstrap over C = 2^LOGC CTAs), for launches that would leave SMs idle; PS = prime-split
-// variant (two threads per ring element, one per RNS prime: k_blind_rotate_cs)
-template <int LOGN, int K, int M, int LOGC, bool PS>
-static void brc_config(cudaLaunchConfig_t &cfg, cudaLaunchAttribute *at, unsigned clusters, size_t smem, cudaStream_t st)
-{
-    using Cf = BRCCfg<LOGN, K, M, LOGC>;
-    cfg = cudaLaunchConfig_t{};
-    cfg.gridDim = dim3(clusters << LOGC); cfg.blockDim = dim3((PS ? 2 : 1) * Cf::THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
-    at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 1 << LOGC; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-    cfg.attrs = at; cfg.numAttrs = 1;
-}
-template <int LOGN, int K, int M, int LOGC, bool PS>
-static cudaError_t brc_launch(const BRArgs &a, long long jobs, size_t smem, cudaStream_t st)
-{
-    cudaLaunchConfig_t cfg; cudaLaunchAttribute at[1];
-    brc_config<LOGN, K, M, LOGC, PS>(cfg, at, (unsigned)(jobs - a.job_begin), smem, st);
-    if constexpr (PS) return cudaLaunchKernelEx(&cfg, k_blind_rotate_cs<LOGN, K, M, LOGC>, a);
-    else return cudaLaunchKernelEx(&cfg, k_blind_rotate_cl<LOGN, K, M, LOGC>, a);
-}
-template <int LOGN, int K, int M, int LOGC, bool PS>
-static cudaError_t brc_prepare(size_t smem)
-{
-    if constexpr (PS) return cudaFuncSetAttribute(k_blind_rotate_cs<LOGN, K, M, LOGC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    else return cudaFuncSetAttribute(k_blind_rotate_cl<LOGN, K, M, LOGC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-}
-template <int LOGN, int K, int M, int LOGC> static size_t brc_smem(int n) { return BRCCfg<LOGN, K, M, LOGC>::smem_bytes(n); }
-// how many clusters of this kernel the device can hold at once (the hardware may strand SMs: 33 clusters of 4 on a 148-SM B200)
-template <int LOGN, int K, int M, int LOGC, bool PS>
-static cudaError_t brc_max_clusters(size_t smem, int *out)
-{
-    cudaLaunchConfig_t cfg; cudaLaunchAttribute at[1];
-    brc_config<LOGN, K, M, LOGC, PS>(cfg, at, 1, smem, nullptr);
-    if constexpr (PS) return cudaOccupancyMaxActiveClusters(out, k_blind_rotate_cs<LOGN, K, M, LOGC>, &cfg);
-    else return cudaOccupancyMaxActiveClusters(out, k_blind_rotate_cl<LOGN, K, M, LOGC>, &cfg);
-}
-struct BRCVariant { int logN, k, unr, logC; bool ps; size_t (*smem)(int n); br_launch_fn launch; cudaError_t (*prepare)(size_t smem); cudaError_t (*max_clusters)(size_t smem, int *out); };
-#define BRCV(LOGN, K, M, LOGC, PS) { LOGN, K, M, LOGC, PS, brc_smem<LOGN, K, M, LOGC>, brc_launch<LOGN, K, M, LOGC, PS>, brc_prepare<LOGN, K, M, LOGC, PS>, brc_max_clusters<LOGN, K, M, LOGC, PS> }
+// variant (two threads per ring element, one per RNS prime: k_blind_rotate_cs); OCC = CTAs per SM its shared memory / registers are
+// sized for (2: twice the co-resident clusters, shallower key ring, 128 registers)
+template <int LOGN, int K, int M, int LOGC, bool PS, int OCC> struct BrcKernel {
+    using Cf = BRCCfg<LOGN, K, M, LOGC, OCC>;
+    static auto fn() { if constexpr (PS) return k_blind_rotate_cs<LOGN, K, M, LOGC, OCC>; else return k_blind_rotate_cl<LOGN, K, M, LOGC>; }
+    static void config(cudaLaunchConfig_t &cfg, cudaLaunchAttribute *at, unsigned clusters, size_t smem, cudaStream_t st)
+    {
+        cfg = cudaLaunchConfig_t{};
+        cfg.gridDim = dim3(clusters << LOGC); cfg.blockDim = dim3((PS ? 2 : 1) * Cf::THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+        at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 1 << LOGC; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+    }
+    static cudaError_t launch(const BRArgs &a, long long jobs, size_t smem, cudaStream_t st)
+    {
+        cudaLaunchConfig_t cfg; cudaLaunchAttribute at[1];
+        config(cfg, at, (unsigned)(jobs - a.job_begin), smem, st);
+        return cudaLaunchKernelEx(&cfg, fn(), a);
+    }
+    static cudaError_t prepare(size_t smem) { return cudaFuncSetAttribute(fn(), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); }
+    static size_t smem(int n) { return Cf::smem_bytes(n); }
+    // how many clusters of this kernel the device can hold at once (the hardware may strand SMs: 33 clusters of 4 on a 148-SM B200)
+    static cudaError_t max_clusters(size_t smem, int *out)
+    {
+        cudaLaunchConfig_t cfg; cudaLaunchAttribute at[1];
+        config(cfg, at, 1, smem, nullptr);
+        return cudaOccupancyMaxActiveClusters(out, fn(), &cfg);
+    }
+};
+struct BRCVariant { int logN, k, unr, logC; bool ps; int occ; size_t (*smem)(int n); br_launch_fn launch; cudaError_t (*prepare)(size_t smem); cudaError_t (*max_clusters)(size_t smem, int *out); };
+#define BRCV(LOGN, K, M, LOGC, PS, OCC) { LOGN, K, M, LOGC, PS, OCC, BrcKernel<LOGN, K, M, LOGC, PS, OCC>::smem, BrcKernel<LOGN, K, M, LOGC, PS, OCC>::launch, BrcKernel<LOGN, K, M, LOGC, PS, OCC>::prepare, BrcKernel<LOGN, K, M, LOGC, PS, OCC>::max_clusters }
 static const BRCVariant g_brc_variants[] = {
-    BRCV(11, 1, 3, 1, false), BRCV(11, 1, 3, 2, false), BRCV(11, 1, 3, 3, false),      // sets A3 / toy5v: clusters of 2, 4, 8
-    BRCV(11, 1, 2, 1, false), BRCV(11, 1, 2, 2, false), BRCV(11, 1, 2, 3, false),      // sets A2 / toy5u
-    BRCV(11, 1, 3, 1, true), BRCV(11, 1, 3, 2, true), BRCV(11, 1, 3, 3, true),         // prime-split twins
-    BRCV(11, 1, 2, 1, true), BRCV(11, 1, 2, 2, true), BRCV(11, 1, 2, 3, true),
+    BRCV(11, 1, 3, 1, false, 1), BRCV(11, 1, 3, 2, false, 1), BRCV(11, 1, 3, 3, false, 1),      // sets A3 / toy5v: clusters of 2, 4, 8
+    BRCV(11, 1, 2, 1, false, 1), BRCV(11, 1, 2, 2, false, 1), BRCV(11, 1, 2, 3, false, 1),      // sets A2 / toy5u
+    BRCV(11, 1, 3, 1, true, 1), BRCV(11, 1, 3, 2, true, 1), BRCV(11, 1, 3, 3, true, 1),         // prime-split twins
+    BRCV(11, 1, 2, 1, true, 1), BRCV(11, 1, 2, 2, true, 1), BRCV(11, 1, 2, 3, true, 1),
+    BRCV(11, 1, 3, 2, true, 2), BRCV(11, 1, 2, 2, true, 2),                                       // prime-split clusters of 4, two CTAs per SM
 };
 
 typedef void (*ntt_launch_fn)(const u64 *, u64 *, int, const fq_tw *, const fq_tw *, u32, u32, long long, cudaStream_t, int);
@@ -136,9 +131,10 @@ struct fbs_ctx {
     bool have_keys = false;
     const BRVariant *br = nullptr; size_t br_smem = 0;        // widest variant (most bootstraps per CTA)
     const BRVariant *br1 = nullptr; size_t br1_smem = 0;      // one bootstrap per CTA, for launches with <= sm_count jobs
-    const BRCVariant *brc[2][4] = {}; size_t brc_smem[2][4] = {};   // [prime-split][log2 C]: one bootstrap per cluster of C CTAs ...
-    int brc_max[2][4] = {};                                   // ... for launches of at most this many jobs (co-resident clusters)
-    int cluster_mode = 0;                                     // 0 auto, 1 never, 2 / 4 / 8 force that cluster size, 12 / 14 / 18 its prime-split twin
+    // [kind][log2 C], kind 0 = packed, 1 = prime-split, 2 = prime-split sized for two CTAs per SM: one bootstrap per cluster of C CTAs ...
+    const BRCVariant *brc[3][4] = {}; size_t brc_smem[3][4] = {};
+    int brc_max[3][4] = {};                                   // ... for launches of at most this many jobs (co-resident clusters)
+    int cluster_mode = 0;                                     // 0 auto, 1 never, 2 / 4 / 8 force that cluster size, 12 / 14 / 18 prime-split, 24 prime-split 2 CTAs/SM
     u8 *d_s_lwe = nullptr, *d_s_big = nullptr;
     u64 *d_ksk = nullptr, *d_colsum = nullptr, *d_bsk = nullptr, *d_bsk_coef = nullptr;
     u8 *d_kbt = nullptr;                                       // byte-transposed KSK for the tensor-core key switch
@@ -264,7 +260,8 @@ static int ctx_create_impl(const fbs_params *params, int device, uint64_t seed, 
         CK(v.prepare((size_t)prop.sharedMemPerBlockOptin));
         int mc = 0;
         if (v.max_clusters(sm, &mc) != cudaSuccess || mc < 1) { cudaGetLastError(); continue; }
-        c->brc[v.ps][v.logC] = &v; c->brc_smem[v.ps][v.logC] = sm; c->brc_max[v.ps][v.logC] = mc;
+        const int kind = v.ps ? v.occ : 0;
+        c->brc[kind][v.logC] = &v; c->brc_smem[kind][v.logC] = sm; c->brc_max[kind][v.logC] = mc;
     }
     CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     for (auto &e : c->ev) CK(cudaEventCreate(&e));
@@ -356,11 +353,11 @@ extern "C" int fbs_ctx_destroy(fbs_ctx *c)
 }
 extern "C" int fbs_ctx_set_cluster(fbs_ctx *c, int32_t mode)
 {
-    const bool ok = mode == 0 || mode == 1 || mode == 2 || mode == 4 || mode == 8 || mode == 12 || mode == 14 || mode == 18;
-    if (!c || !ok) return fail(FBS_ERR_ARG, "fbs_ctx_set_cluster: mode must be 0 (auto), 1 (off), 2, 4, 8 or 12, 14, 18 (prime-split)");
+    const bool ok = mode == 0 || mode == 1 || mode == 2 || mode == 4 || mode == 8 || mode == 12 || mode == 14 || mode == 18 || mode == 24;
+    if (!c || !ok) return fail(FBS_ERR_ARG, "fbs_ctx_set_cluster: mode must be 0 (auto), 1 (off), 2, 4, 8, or 12, 14, 18 (prime-split), 24 (prime-split, 2 CTAs per SM)");
     if (mode > 1) {
         const int sz = mode % 10, lc = sz == 2 ? 1 : sz == 4 ? 2 : 3;
-        if (!c->brc[mode > 10][lc]) return fail(FBS_ERR_ARG, "fbs_ctx_set_cluster: no cluster kernel of that size for this parameter set");
+        if (!c->brc[mode / 10][lc]) return fail(FBS_ERR_ARG, "fbs_ctx_set_cluster: no cluster kernel of that kind for this parameter set");
     }
     c->cluster_mode = mode;
     return FBS_OK;
@@ -597,19 +594,19 @@ static int run_level_impl(fbs_ctx *c, fbs_prog *g, int level, int nb, int ne, in
     // Measured, set A3, per bootstrap (profiles/r2_latency_A3_1gpu_v3.jsonl): one CTA 3.0 ms; packed clusters C = 2 / 4 / 8: 1.87 /
     // 1.34 / 1.38 ms; prime-split clusters C = 2 / 4 / 8: 2.02 / 1.20 / 0.93 ms (1.14 ms with 33 of them, two CTAs per SM).
     // Preference: the fastest kind whose clusters are all co-resident.  Results are bit-identical to the one-CTA kernels.
-    auto pick_cluster = [&](long long nj) -> int {              // returns log2 C (+ 8 for the prime-split twin), 0 = none
+    auto pick_cluster = [&](long long nj) -> int {              // returns log2 C + 8 * kind (0 packed, 1 prime-split, 2 prime-split x2), 0 = none
         if (c->cluster_mode == 0) {
-            static const int pref[][2] = {{1, 3}, {1, 2}, {0, 2}, {0, 3}, {0, 1}, {1, 1}};     // {prime-split, log2 C}
+            static const int pref[][2] = {{1, 3}, {1, 2}, {0, 2}, {2, 2}, {0, 3}, {0, 1}, {1, 1}};     // {kind, log2 C}
             for (auto &pc : pref) if (c->brc[pc[0]][pc[1]] && nj <= c->brc_max[pc[0]][pc[1]]) return pc[1] + 8 * pc[0];
             return 0;
         }
         if (c->cluster_mode > 1) {
-            const int ps = c->cluster_mode > 10, sz = c->cluster_mode % 10;
-            for (int lc = 1; lc <= 3; lc++) if ((1 << lc) == sz && c->brc[ps][lc]) return lc + 8 * ps;
+            const int kind = c->cluster_mode / 10, sz = c->cluster_mode % 10;
+            for (int lc = 1; lc <= 3; lc++) if ((1 << lc) == sz && c->brc[kind][lc]) return lc + 8 * kind;
         }
         return 0;
     };
-    auto launch_cluster = [&](int code, const BRArgs &args) { const int ps = code >> 3, lc = code & 7; return c->brc[ps][lc]->launch(args, jobs, c->brc_smem[ps][lc], st); };
+    auto launch_cluster = [&](int code, const BRArgs &args) { const int kind = code >> 3, lc = code & 7; return c->brc[kind][lc]->launch(args, jobs, c->brc_smem[kind][lc], st); };
     const int logC = pick_cluster(jobs);
     if (logC) CK(launch_cluster(logC, ba));
     else if (c->br1 != c->br && tail > 0 && tail <= c->sm_count) {

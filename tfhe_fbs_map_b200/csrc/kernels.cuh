@@ -1086,7 +1086,7 @@ __global__ void __launch_bounds__((PB / TP) * (K + 1) * (1 << LOGN) / 8, 1) k_bl
 // thread positions so that a CTA's share of a slice is one contiguous bulk copy), ring depth up to 8 slices = one whole step ahead.
 // Arithmetic, rounding and term order are those of k_blind_rotate2<M>: results are bit-identical.
 // ------------------------------------------------------------------------------------------------------
-template <int LOGN, int K, int M, int LOGC>
+template <int LOGN, int K, int M, int LOGC, int OCC = 1>         // OCC: CTAs per SM the shared-memory budget (key ring depth) is sized for
 struct BRCCfg {
     static_assert(M == 2 || M == 3, "two or three key bits per step");
     static_assert(LOGC >= 1 && LOGC <= 3, "cluster of 2, 4 or 8 CTAs");
@@ -1101,7 +1101,7 @@ struct BRCCfg {
     static constexpr size_t tw_w = 2 * (size_t)Ns;                // one local twiddle table (16 B entries)
     static constexpr size_t slice_w = (size_t)RUNS * Ts;
     static constexpr size_t fixed_b = 8 * (s_w + 2 * inbox_w + psi_w + 2 * tw_w) + 2048 + 256;
-    static constexpr int R_fit = (int)((227 * 1024 - fixed_b) / (8 * slice_w));
+    static constexpr int R_fit = (int)(((227 * 1024) / OCC - 1024 * (OCC > 1) - fixed_b) / (8 * slice_w));       // 1 KB per CTA is reserved by the system
     static constexpr int RING = R_fit > 8 ? 8 : R_fit;
     static_assert(RING >= 2, "key ring does not fit shared memory");
     __host__ __device__ static constexpr size_t ms_stride(int n) { return (((size_t)(n + 1) * 2 + 15) / 16) * 16; }
@@ -1391,10 +1391,10 @@ __device__ __forceinline__ void st_async_u32(u32 remote_addr, u32 v, u32 remote_
 {
     asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(remote_addr), "r"(v), "r"(remote_bar) : "memory");
 }
-template <int LOGN, int K, int M, int LOGC>
-__global__ void __launch_bounds__(2 * (K + 1) * (1 << (LOGN - LOGC)) / 8, 1) k_blind_rotate_cs(BRArgs a)
+template <int LOGN, int K, int M, int LOGC, int OCC = 1>
+__global__ void __launch_bounds__(2 * (K + 1) * (1 << (LOGN - LOGC)) / 8, OCC) k_blind_rotate_cs(BRArgs a)
 {
-    using Cf = BRCCfg<LOGN, K, M, LOGC>;
+    using Cf = BRCCfg<LOGN, K, M, LOGC, OCC>;
     using P = NttPlan<Cf::LOGNS>;
     constexpr int NC = Cf::NC, N = Cf::N, G = Cf::G, C = Cf::C, Ns = Cf::Ns, Ts = Cf::Ts, R = Cf::R, T = Cf::T, RING = Cf::RING, LOGNS = Cf::LOGNS;
     constexpr int THREADS = 2 * Cf::THREADS;
