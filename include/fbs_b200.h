@@ -101,8 +101,7 @@ int fbs_keygen(fbs_ctx *ctx);                 /* seeded, deterministic: identica
 int fbs_ctx_destroy(fbs_ctx *ctx);
 /* Blind-rotation kernel choice for launches with fewer jobs than SMs: 0 = auto (split each bootstrap over a thread-block
  * cluster of up to 8 CTAs when that still fits one wave), 1 = never, 2 / 4 / 8 = always that cluster size (tests, sweeps),
- * 12 / 14 / 18 = that size with two threads per ring element (one per RNS prime), 24 = prime-split clusters of 4 sized for two
- * CTAs per SM (twice the co-resident clusters).  All choices produce bit-identical ciphertexts. */
+ * 12 / 14 / 18 = that size with two threads per ring element (one per RNS prime).  All choices produce bit-identical ciphertexts. */
 int fbs_ctx_set_cluster(fbs_ctx *ctx, int32_t mode);
 int fbs_ctx_info(const fbs_ctx *ctx, int32_t *sm_count, int64_t *bsk_bytes, int64_t *ksk_bytes, int32_t *br_smem_bytes);
 

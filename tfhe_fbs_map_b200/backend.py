@@ -173,8 +173,8 @@ class B200Backend:
         self.have_keys = True
 
     def set_cluster(self, mode: int):
-        """0 auto, 1 off, 2 / 4 / 8: force the cluster-split blind rotation of that size, 12 / 14 / 18: its prime-split twin, 24: prime-split
-        clusters of 4 sized for two CTAs per SM (bit-identical results)."""
+        """0 auto, 1 off, 2 / 4 / 8: force the cluster-split blind rotation of that size, 12 / 14 / 18: its prime-split twin
+        (bit-identical results)."""
         self._check(self.lib.fbs_ctx_set_cluster(self.ctx, mode))
 
     def info(self):

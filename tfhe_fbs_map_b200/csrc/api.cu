@@ -110,7 +110,6 @@ static const BRCVariant g_brc_variants[] = {
     BRCV(11, 1, 2, 1, false, 1), BRCV(11, 1, 2, 2, false, 1), BRCV(11, 1, 2, 3, false, 1),      // sets A2 / toy5u
     BRCV(11, 1, 3, 1, true, 1), BRCV(11, 1, 3, 2, true, 1), BRCV(11, 1, 3, 3, true, 1),         // prime-split twins
     BRCV(11, 1, 2, 1, true, 1), BRCV(11, 1, 2, 2, true, 1), BRCV(11, 1, 2, 3, true, 1),
-    BRCV(11, 1, 3, 2, true, 2), BRCV(11, 1, 2, 2, true, 2),                                       // prime-split clusters of 4, two CTAs per SM
 };
 
 typedef void (*ntt_launch_fn)(const u64 *, u64 *, int, const fq_tw *, const fq_tw *, u32, u32, long long, cudaStream_t, int);
@@ -596,7 +595,7 @@ static int run_level_impl(fbs_ctx *c, fbs_prog *g, int level, int nb, int ne, in
     // Preference: the fastest kind whose clusters are all co-resident.  Results are bit-identical to the one-CTA kernels.
     auto pick_cluster = [&](long long nj) -> int {              // returns log2 C + 8 * kind (0 packed, 1 prime-split, 2 prime-split x2), 0 = none
         if (c->cluster_mode == 0) {
-            static const int pref[][2] = {{1, 3}, {1, 2}, {0, 2}, {2, 2}, {0, 3}, {0, 1}, {1, 1}};     // {kind, log2 C}
+            static const int pref[][2] = {{1, 3}, {1, 2}, {0, 2}, {0, 3}, {0, 1}, {1, 1}};     // {kind, log2 C}; kind 2 (two CTAs per SM) measured slower than packed C = 2
             for (auto &pc : pref) if (c->brc[pc[0]][pc[1]] && nj <= c->brc_max[pc[0]][pc[1]]) return pc[1] + 8 * pc[0];
             return 0;
         }

@@ -16,7 +16,7 @@ for count in counts:
     tables = np.concatenate([low, 1 - low], axis=1)
     lens = np.full(count, 2 * p, np.uint8)
     msgs = rng.integers(0, 2 * p, count).astype(np.uint8)
-    for mode in (1, 2, 4, 8, 12, 14, 18, 24, 0):
+    for mode in (1, 2, 4, 8, 12, 14, 18, 0):
         if mode > 1 and count * (mode % 10) > 4 * 148:
             continue
         be.set_cluster(mode)
