@@ -31,3 +31,21 @@ def test_node_sharded_exchanges_bit_identical_to_one_gpu(param_set, lbf, p, batc
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert r.stdout.count("MULTI_OK") == world, r.stdout[-3000:]
+
+
+def test_cli_instance_sharded_over_two_gpus():
+    """`map_circuit ... --exec b200 --gpus 2`: the batch of self-check vectors is split over two GPUs driven from one process
+    (keys replicated by the seed, no collective); the encrypted result must pass the CLI's own self-check."""
+    if _ngpu() < 2:
+        pytest.skip("needs at least two GPUs")
+    import ast
+    import json
+    gold = os.path.join(ROOT, "tests", "golden", "blif", "aes_sbox.blif")
+    r = subprocess.run([sys.executable, "-m", "tfhe_fbs_map_b200.map_circuit", gold, "--fbs_size", "11", "--exec", "b200", "--gpus", "2", "--batch", "96"],
+                       capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    lines = r.stdout.strip().splitlines()
+    info = json.loads(next(ln for ln in lines if ln.startswith("{\"exec\"")))
+    assert info["gpus"] == 2 and info["n_pbs"] == 38 * 96
+    d = ast.literal_eval(lines[-1])
+    assert d["nb_bootstrap"] == 38

@@ -712,7 +712,10 @@ extern "C" int fbs_eval_bits(fbs_ctx *c, fbs_prog *g, const uint8_t *in, int64_t
     const fbs_params &P = c->P;
     const size_t CT = ct_words(c) * 8;
     const size_t R = (size_t)P.k * P.N * P.ks_l;
-    const size_t per_inst = (size_t)g->n_slots * CT + (size_t)std::max(1, g->max_lc_per_level) * (R + 8 + 2 * (size_t)(P.n + 1));
+    int max_grp = 0;                                            // multi-value: one accumulator (32 KB at N = 2048) per group and instance
+    for (int lv = 0; lv < g->n_levels && g->n_groups > 0; lv++) max_grp = std::max(max_grp, g->grp_level_ptr[lv + 1] - g->grp_level_ptr[lv]);
+    const size_t per_inst = (size_t)g->n_slots * CT + (size_t)std::max(1, g->max_lc_per_level) * (R + 8 + 2 * (size_t)(P.n + 1)) +
+                            (size_t)max_grp * (P.k + 1) * P.N * 8;
     if (max_wire_bytes == 0) {
         size_t fr = 0, tot = 0;
         CK(cudaMemGetInfo(&fr, &tot));
