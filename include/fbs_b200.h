@@ -122,7 +122,8 @@ int fbs_eval_bits(fbs_ctx *ctx, fbs_prog *prog, const uint8_t *in, int64_t B, in
 int fbs_wires_bytes(const fbs_ctx *ctx, const fbs_prog *prog, int64_t B, size_t *bytes);
 int fbs_encrypt_inputs(fbs_ctx *ctx, fbs_prog *prog, const uint8_t *in_dev, int64_t B, int64_t inst_offset,
                        int64_t B_total, uint64_t enc_seed, uint64_t *wires_dev, void *stream);
-/* runs bootstraps [node_begin, node_end) of level `level` (indices relative to the level; -1,-1 = all).  A proper
+/* runs bootstraps [node_begin, node_end) of level `level` (indices relative to the level; -1,-1 = all; for a multi-value
+ * program, n_groups > 0, the indices count GROUPS: all tables of a group are produced by the rank that rotates it).  A proper
  * sub-range needs a program with contiguous_levels != 0 (recycled slots would be corrupted otherwise: refused). */
 int fbs_run_level(fbs_ctx *ctx, fbs_prog *prog, int32_t level, int32_t node_begin, int32_t node_end, int64_t B,
                   uint64_t *wires_dev, void *stream, fbs_run_stats *stats);

@@ -275,7 +275,8 @@ def test_fused_peer_store_epilogue_single_gpu(ctxs):
             be.wires_free(buf)
 
 
-def test_device_side_level_handoff_two_ranks_one_gpu():
+@pytest.mark.parametrize("circuit,multi", [("aes_sbox", False), ("_2_input_gates", True)])
+def test_device_side_level_handoff_two_ranks_one_gpu(circuit, multi):
     """Node-sharded levels with the fused peer-store exchange AND the device-side level hand-off (per-level epoch flags,
     no host synchronisation between levels), with both "ranks" living on this one GPU: two backends (same seeded keys), two
     streams, each rank's peer is the other rank's wire buffer.  All levels of both ranks are enqueued without any host
@@ -284,8 +285,8 @@ def test_device_side_level_handoff_two_ranks_one_gpu():
     import torch
     from tfhe_fbs_map_b200.backend import B200Backend
     from tfhe_fbs_map_b200.dist import level_node_range
-    e = next(x for x in load_ref_mapped() if x["circuit"] == "aes_sbox" and x["p"] == 11 and x["mapper"] == "search" and not x.get("strict"))
-    prog = levelize(read_lbf(e["lbf"]), 11, shard_pad=2)
+    e = next(x for x in load_ref_mapped() if x["circuit"] == circuit and x["p"] == 11 and x["mapper"] == "search" and not x.get("strict"))
+    prog = levelize(read_lbf(e["lbf"]), 11, shard_pad=2, multi_value=multi)       # multi-value: the sharding unit is the group (one rotation)
     B, world = 4, 2
     bes = [B200Backend("toy3", device=0, seed=21) for _ in range(world)]
     cps = [be.load(prog) for be in bes]
@@ -312,7 +313,7 @@ def test_device_side_level_handoff_two_ranks_one_gpu():
         a = prog.arrays
         for rep in range(2):                                 # the epochs keep counting across runs
             for lv in range(prog.n_levels):
-                width = int(a["bs_level_ptr"][lv + 1] - a["bs_level_ptr"][lv])
+                width = int(a["grp_level_ptr"][lv + 1] - a["grp_level_ptr"][lv]) if multi else int(a["bs_level_ptr"][lv + 1] - a["bs_level_ptr"][lv])
                 for r in range(world):
                     nb, ne, _ = level_node_range(width, world, r)
                     bes[r].run_level(cps[r], lv, B, bufs[r], nb, ne, stream=streams[r].cuda_stream)

@@ -526,9 +526,12 @@ static int run_level_impl(fbs_ctx *c, fbs_prog *g, int level, int nb, int ne, in
     cudaEvent_t *E = evq ? evq : c->ev;
     const bool rec = timed || evq;
     const int b0 = g->bs_level_ptr[level], b1 = g->bs_level_ptr[level + 1];
-    const bool whole = (nb < 0 && ne < 0) || (nb == 0 && ne == b1 - b0);
-    if (nb < 0 && ne < 0) { nb = 0; ne = b1 - b0; }
-    if (nb < 0 || ne > b1 - b0 || nb > ne) return fail(FBS_ERR_ARG, "fbs_run_level: node range outside the level");
+    const bool multi = g->n_groups > 0;
+    // the unit of a node range: bootstraps -- or, for a multi-value program, GROUPS (all tables of a group share one rotation)
+    const int grp0 = multi ? g->grp_level_ptr[level] : 0, units = multi ? g->grp_level_ptr[level + 1] - grp0 : b1 - b0;
+    const bool whole = (nb < 0 && ne < 0) || (nb == 0 && ne == units);
+    if (nb < 0 && ne < 0) { nb = 0; ne = units; }
+    if (nb < 0 || ne > units || nb > ne) return fail(FBS_ERR_ARG, "fbs_run_level: node range outside the level");
     if (!whole && !g->contiguous_levels)
         return fail(FBS_ERR_ARG, "fbs_run_level: a node sub-range needs a program levelised with contiguous_levels (slots are recycled otherwise)");
     // Node-sharded level on the registered, peer-mapped wire buffer: wait (on the device) until every rank has finished the
@@ -546,9 +549,7 @@ static int run_level_impl(fbs_ctx *c, fbs_prog *g, int level, int nb, int ne, in
     if (nb == ne) return FBS_OK;
     const fbs_params &P = c->P;
     const int D = P.k * P.N, n = P.n;
-    const bool multi = g->n_groups > 0;
-    if (multi && !whole) return fail(FBS_ERR_ARG, "fbs_run_level: a multi-value program runs whole levels (node sub-ranges are not supported)");
-    const int node0 = b0 + nb, node1 = b0 + ne;
+    const int node0 = multi ? g->grp_first[grp0 + nb] : b0 + nb, node1 = multi ? g->grp_first[grp0 + ne] : b0 + ne;
     const int lc0 = g->bs_lc[node0], lc1 = g->bs_lc[node1 - 1] + 1;     // bootstraps are sorted by lincomb
     const long long M = (long long)(lc1 - lc0) * B, tiles = (M + 15) / 16, mtiles = (M + KS_BM - 1) / KS_BM;
     const size_t R = (size_t)D * P.ks_l;
@@ -579,10 +580,9 @@ static int run_level_impl(fbs_ctx *c, fbs_prog *g, int level, int nb, int ne, in
     ba.ms = c->d_ms; ba.bsk = c->d_bsk; ba.psi_rev = c->d_psi_rev; ba.psi_inv_rev = c->d_psi_inv_rev; ba.psi_pow = c->d_psi_pow;
     ba.bs_lc = g->d_bs_lc; ba.bs_slot = g->d_bs_slot; ba.bs_tab_ptr = g->d_bs_tab_ptr; ba.bs_mode = g->d_bs_mode; ba.bs_tab = g->d_tab;
     // multi-value: one job per (group, instance); the kernels index groups and leave the accumulators in d_mvacc for k_multi_extract
-    const int grp0 = multi ? g->grp_level_ptr[level] : 0, grp1 = multi ? g->grp_level_ptr[level + 1] : 0;
-    const long long jobs = multi ? (long long)(grp1 - grp0) * B : (long long)(node1 - node0) * B;
+    const long long jobs = multi ? (long long)(ne - nb) * B : (long long)(node1 - node0) * B;
     if (multi && !tap_acc) { CKR(grow(&c->d_mvacc, &c->cap_mvacc, (size_t)jobs * (P.k + 1) * P.N)); tap_acc = c->d_mvacc; }
-    ba.wires = wires; ba.tap_acc = tap_acc; ba.B = B; ba.jobs = jobs; ba.node_begin = multi ? grp0 : node0;
+    ba.wires = wires; ba.tap_acc = tap_acc; ba.B = B; ba.jobs = jobs; ba.node_begin = multi ? grp0 + nb : node0;
     ba.grp_first = multi ? g->d_grp_first : nullptr;
     ba.n_peers = fused ? c->n_peers : 0;      // peers are bound to the registered buffer only (never to c->d_wires or a tap buffer)
     for (int pr = 0; pr < ba.n_peers; pr++) ba.peer_wires[pr] = c->peers[pr];
@@ -621,7 +621,7 @@ static int run_level_impl(fbs_ctx *c, fbs_prog *g, int level, int nb, int ne, in
     if (multi) {
         MVArgs ma{};
         ma.acc = tap_acc; ma.grp_first = g->d_grp_first; ma.bs_slot = g->d_bs_slot; ma.bs_tab_ptr = g->d_bs_tab_ptr; ma.bs_mode = g->d_bs_mode; ma.bs_tab = g->d_tab;
-        ma.wires = wires; ma.B = B; ma.grp_begin = grp0; ma.N = P.N; ma.K = P.k; ma.p = g->p;
+        ma.wires = wires; ma.B = B; ma.grp_begin = grp0 + nb; ma.N = P.N; ma.K = P.k; ma.p = g->p;
         ma.n_peers = ba.n_peers; for (int pr = 0; pr < ba.n_peers; pr++) ma.peer_wires[pr] = ba.peer_wires[pr];
         k_multi_extract<<<(unsigned)jobs, 256, 0, st>>>(ma);
         CK(cudaGetLastError());

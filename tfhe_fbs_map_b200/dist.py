@@ -168,9 +168,13 @@ def run_node_sharded(engine, program, dist, world: int, rank: int, in_place: boo
         "program must be levelised with shard_pad=world (reuse_slots=False when world == 1)"
     a = program.arrays
     exchanged = 0
+    multi = getattr(program, "multi_value", False)
+    assert not multi or world == 1 or getattr(engine, "fused", False), \
+        "multi-value programs shard by groups: their outputs are not equal contiguous slot chunks, use the fused exchange"
     for lv in range(program.n_levels):
         b0, b1 = int(a["bs_level_ptr"][lv]), int(a["bs_level_ptr"][lv + 1])
-        width = b1 - b0
+        # the sharding unit: bootstraps, or (multi-value) the groups of bootstraps that share one blind rotation
+        width = int(a["grp_level_ptr"][lv + 1] - a["grp_level_ptr"][lv]) if multi else b1 - b0
         nb, ne, chunk = level_node_range(width, world, rank)
         fused = getattr(engine, "fused", False) and world > 1
         if ne > nb or fused:                     # fused: an empty range still waits for / signals the level on the device
@@ -178,7 +182,7 @@ def run_node_sharded(engine, program, dist, world: int, rank: int, in_place: boo
         if world == 1:
             continue
         if fused:                                # outputs already sit in every replica, levels are ordered by device flags
-            exchanged += chunk * world * engine.B * engine.ct_words
+            exchanged += (b1 - b0 if multi else chunk * world) * engine.B * engine.ct_words
             continue
         first_slot = int(a["bs_slot"][b0])
         region = engine.slot_view(first_slot, chunk * world)
