@@ -1271,16 +1271,8 @@ __global__ void __launch_bounds__((K + 1) * (1 << (LOGN - LOGC)) / 8, 1) k_blind
             __syncwarp();
             if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(empty + slot)) : "memory");
             if (tid == 0) {
-                // Refill one slice LATE (the slot released one element ago): by now every warp is past that slice, so the producer
-                // thread does not stall in the wait and stops being the straggler of the next barrier; the ring still runs
-                // RING - 1 slices ahead.  Shallow rings (RING < 4) refill at once.
-                constexpr int DEFER = RING >= 4 ? 1 : 0;
-                const int prev = 8 * t + e - DEFER, nxt = prev + RING;
-                if (prev >= 0 && nxt < n_slices) {
-                    const int ps = slot >= DEFER ? slot - DEFER : slot - DEFER + RING;
-                    mbar_wait(empty + ps, slot >= DEFER ? par : par ^ 1u);
-                    issue_slice(nxt, ps);
-                }
+                const int nxt = 8 * t + e + RING;
+                if (nxt < n_slices) { mbar_wait(empty + slot, par); issue_slice(nxt, slot); }
             }
             if (++slot == RING) { slot = 0; par ^= 1; }
         };
@@ -1534,16 +1526,8 @@ __global__ void __launch_bounds__(2 * (K + 1) * (1 << (LOGN - LOGC)) / 8, OCC) k
             __syncwarp();
             if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(empty + slot)) : "memory");
             if (tid == 0) {
-                // Refill one slice LATE (the slot released one element ago): by now every warp is past that slice, so the producer
-                // thread does not stall in the wait and stops being the straggler of the next barrier; the ring still runs
-                // RING - 1 slices ahead.  Shallow rings (RING < 4) refill at once.
-                constexpr int DEFER = RING >= 4 ? 1 : 0;
-                const int prev = 8 * t + e - DEFER, nxt = prev + RING;
-                if (prev >= 0 && nxt < n_slices) {
-                    const int ps = slot >= DEFER ? slot - DEFER : slot - DEFER + RING;
-                    mbar_wait(empty + ps, slot >= DEFER ? par : par ^ 1u);
-                    issue_slice(nxt, ps);
-                }
+                const int nxt = 8 * t + e + RING;
+                if (nxt < n_slices) { mbar_wait(empty + slot, par); issue_slice(nxt, slot); }
             }
             if (++slot == RING) { slot = 0; par ^= 1; }
         };
