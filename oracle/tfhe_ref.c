@@ -583,7 +583,7 @@ int ref_eval_prog_mv(const ref_ctx *c, const ref_prog_desc *g, const u8 *in, int
                     continue;
                 }
                 /* multi-value: the maximal run of bootstraps on the same lincomb (they are sorted by lincomb) shares one rotation */
-                int q1 = q; while (q1 < g->bs_level_ptr[lv + 1] && g->bs_lc[q1] == g->bs_lc[q]) q1++;
+                int q1 = q; while (q1 < g->bs_level_ptr[lv + 1] && g->bs_lc[q1] == g->bs_lc[q] && q1 - q < 64) q1++;   /* at most 64 tables per call (buffers below); a longer run continues with another rotation of the same input: same accumulator, same results */
                 int T = q1 - q; u8 tabs[64 * 64]; u8 lens[64]; int32_t md[64]; u64 *outs = malloc((size_t)T * CT * 8);
                 for (int t = 0; t < T; t++) {
                     lens[t] = (u8)(g->bs_tab_ptr[q + t + 1] - g->bs_tab_ptr[q + t]); md[t] = g->bs_mode[q + t];
