@@ -62,6 +62,9 @@ template <int LOGN, int K, int PB, int TP, int M> static size_t br2_smem(int n) 
 #ifndef FBS_SETA_TP
 #define FBS_SETA_TP 2     /* bootstraps per thread in the set-A kernel: 2 = every thread carries both bootstraps of its CTA */
 #endif
+#ifndef FBS_A3_TP
+#define FBS_A3_TP 2       /* 1 = 1024 threads, one bootstrap per thread, 64 registers (experiment) */
+#endif
 static const BRVariant g_br_variants[] = {
     BRV(11, 1, 1, true, 2, FBS_SETA_TP),   // set A: two bootstraps per CTA share the TMA-streamed BSK row (192 KB shared memory)
     BRV(11, 1, 1, true, 1, 1),             // set A, one bootstrap per CTA: used when a launch has no more jobs than SMs
@@ -70,7 +73,7 @@ static const BRVariant g_br_variants[] = {
     BRV(8, 1, 2, true, 2, 2), BRV(8, 2, 1, true, 2, 1), BRV(9, 1, 1, true, 2, 2), BRV(10, 1, 3, true, 1, 1),   // toy sets (tests)
     BRV2(11, 1, 2, 2, 2), BRV2(11, 1, 1, 1, 2),    // set A2 (two key bits per step)
     BRV2(9, 1, 2, 2, 2), BRV2(8, 2, 2, 1, 2),      // toy3u / toy7u, toy2u
-    BRV2(11, 1, 2, 2, 3), BRV2(11, 1, 1, 1, 3),    // set A3 (three key bits per step)
+    BRV2(11, 1, 2, FBS_A3_TP, 3), BRV2(11, 1, 1, 1, 3),    // set A3 (three key bits per step)
     BRV2(9, 1, 2, 2, 3),                           // toy3v
 };
 

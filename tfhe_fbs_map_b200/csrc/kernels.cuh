@@ -890,9 +890,11 @@ __global__ void __launch_bounds__((PB / TP) * (K + 1) * (1 << LOGN) / 8, 1) k_bl
     // Digit spectra are exchanged between the G threads that hold the SAME spectrum positions (same tau, one per group):
     // a named barrier over those G warps replaces a CTA-wide one, so the groups only couple warp by warp.
     constexpr int BAR_X0 = 1 + PB * G + PB;                       // after the group (bar_g) and bootstrap (bar_p) barrier ids
-    static_assert(BAR_X0 + (PB / TP) * (T / 32) <= 16, "named barriers");
-    const int bar_x = BAR_X0 + pb0 * (T / 32) + (tau >> 5);
-    auto xsync = [bar_x] { bar_sync_named(bar_x, G * 32); };
+    // 16 hardware barriers: when (bootstraps) x (warps per group) pairs do not fit, XG neighbouring warp positions share one
+    constexpr int XW = (PB / TP) * (T / 32), XG = BAR_X0 + XW <= 16 ? 1 : BAR_X0 + XW / 2 <= 16 ? 2 : 4;
+    static_assert(BAR_X0 + XW / XG <= 16 && (T / 32) % XG == 0, "named barriers");
+    const int bar_x = BAR_X0 + pb0 * (T / 32 / XG) + (tau >> 5) / XG;
+    auto xsync = [bar_x] { bar_sync_named(bar_x, G * 32 * XG); };
     const int beta = a.beta;
     const u64 rc = 1ULL << (62 - beta);
     constexpr int SH = LOGN + 3;
