@@ -801,6 +801,9 @@ struct BR2Cfg {
     static constexpr size_t slice_w = NC * (size_t)G * G * T;
     static constexpr size_t fixed_b = 8 * (PB * s_w + psi_w + tw_w) + PB * 2048 + 256;   // ms rows budgeted for n < 1024
     static constexpr int R_fit = (int)((227 * 1024 - fixed_b) / (8 * slice_w));
+#ifndef FBS_REFILL_LAST
+#define FBS_REFILL_LAST 1   /* key-ring slot refilled by the last warp to release it (0: by thread 0, which waits for the others) */
+#endif
 #ifndef FBS_RING_MAX
 #define FBS_RING_MAX 3      /* measured at set A2: 2 slots 45.8 k, 3 slots 46.3 k, 4 45.8 k, 5 45.1 k PBS/s -- deeper rings only take L1 from the twiddles */
 #endif
@@ -843,14 +846,22 @@ __global__ void __launch_bounds__((PB / TP) * (K + 1) * (1 << LOGN) / 8, 1) k_bl
         u16 *dst = (u16 *)((unsigned char *)s_ms + (size_t)q * ms_stride);
         for (int i = ptid; i <= n; i += C::PT) dst[i] = ms[i];
     }
-    // psi^x table, low index nibble XOR-folded with the next two: the lanes of a warp look up exponents that differ by
-    // multiples of 16 E (bit-reversed evaluation points), which would all fall into one bank pair otherwise
-    auto psw = [](u32 x) { return x ^ (((x >> 4) ^ (x >> 8)) & 15u); };
+    // psi^x table, low index nibble XOR-folded with higher index bits: the lanes of a half-warp look up exponents that differ by
+    // multiples of 32 E (bit-reversed evaluation points), which would all fall into one bank pair otherwise.  At N = 2048 the fold
+    // takes index bits 5..8 only (any bijection of the four lane-dependent bits below the element bits 9..11 gives the same
+    // conflict count as folding the top nibble in too -- tools/psi_hash_model.py: 2.34 against 2.38 wavefronts per half-warp
+    // request), so the three bits that differ between a thread's 8 elements stay a plain ADDITIVE field of the byte offset.
+    constexpr bool fast_psi = (LOGN - 2 >= 9) && (LOGN + 1 <= 12);
+    auto psw = [](u32 x) { return fast_psi ? x ^ ((x >> 5) & 15u) : x ^ (((x >> 4) ^ (x >> 8)) & 15u); };
     for (int i = tid; i < 2 * N; i += C::THREADS) PSI[psw((u32)i)] = a.psi_pow[i];
     if (C::TWS) for (int i = tid; i < 2 * N; i += C::THREADS) TW[i] = ((const u64 *)a.psi_rev)[i];
     const fq_tw *twp = C::TWS ? (const fq_tw *)TW : a.psi_rev;
     if (tid == 0) {
+#if FBS_REFILL_LAST
+        for (int r = 0; r < R; r++) { mbar_init(full + r, 1); empty[r] = 0; }       // empty[r]: plain arrival counter
+#else
         for (int r = 0; r < R; r++) { mbar_init(full + r, 1); mbar_init(empty + r, C::THREADS / 32); }
+#endif
     }
     __syncthreads();
     if (tid == 0) {                                             // prologue: the first R slices
@@ -938,6 +949,23 @@ __global__ void __launch_bounds__((PB / TP) * (K + 1) * (1 << LOGN) / 8, 1) k_bl
         // slot with the slice R ahead, so the copy overlaps the other elements' arithmetic or the transforms
         auto release_slot = [&](int e) {
             __syncwarp();
+#if FBS_REFILL_LAST
+            // the warp that arrives LAST refills the slot: nobody ever waits for the slowest warp (with a fixed producer thread
+            // the refill is late whenever that thread is, and the thread stalls -- and becomes late -- whenever it is early)
+            if ((tid & 31) == 0) {
+                u32 seen;
+                asm volatile("atom.acq_rel.cta.shared::cta.add.u32 %0, [%1], 1;" : "=r"(seen) : "r"(smem_u32(empty + slot)) : "memory");
+                if (seen == (u32)(C::THREADS / 32 - 1)) {
+                    *(volatile u32 *)(empty + slot) = 0u;      // next arrivals come after the refilled slice has landed and been used
+                    const int nxt = 8 * t + e + R;
+                    if (nxt < n_slices) {
+                        fence_proxy_async();
+                        mbar_expect_tx(full + slot, (u32)(C::slice_w * 8));
+                        tma_load_1d(RING + (size_t)slot * C::slice_w, a.bsk + (size_t)nxt * C::slice_w, (u32)(C::slice_w * 8), full + slot);
+                    }
+                }
+            }
+#else
             if ((tid & 31) == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(empty + slot)) : "memory");
             if (tid == 0) {
                 const int nxt = 8 * t + e + R;
@@ -948,18 +976,17 @@ __global__ void __launch_bounds__((PB / TP) * (K + 1) * (1 << LOGN) / 8, 1) k_bl
                     tma_load_1d(RING + (size_t)slot * C::slice_w, a.bsk + (size_t)nxt * C::slice_w, (u32)(C::slice_w * 8), full + slot);
                 }
             }
+#endif
             if (++slot == R) { slot = 0; par ^= 1; }
-
         };
         static_assert(M == 2 || G == 2, "the M = 3 sums are sized for k = 1");
         // Exponents of the NC monomial factors, E_c = sum of the a_i in subset c.  Element e evaluates X^E at
         // psi^(E*odd0 + (brev3(e) << (LOGN-2)) * E): the low LOGN-2 bits of the table index are the same for the 8 elements,
-        // only the top three move (by brev3(e) * E mod 8).  With the table's XOR fold (psw) that is: byte offset =
-        // lo8 ^ (h * HMUL), h = (hb + brev3(e)*E) & 7, where lo8 has the fold of the fixed bits applied and HMUL places h at
-        // bits LOGN-2.. and (its part of nibble 2) into the low nibble.  One packed word per (bootstrap, factor): fast path
-        // lo8 | hb << 16 | (E & 7) << 20, generic x0 | (E & 7) << 20.
-        constexpr bool fast_psi = (LOGN - 2 >= 9) && (LOGN + 1 <= 12);
-        constexpr u32 HMUL = 8u * ((1u << (LOGN - 2)) | (fast_psi ? (1u << (LOGN - 2 - 8)) : 0u));
+        // only the top three move (by brev3(e) * E mod 8).  One packed word per (bootstrap, factor).  Fast path (N = 2048): the
+        // table's fold does not touch those three bits, so with PK = byte offset of element 0 | (E & 7) -- E mod 8 parked in the
+        // three low bits that are zero in an 8-byte offset -- element e's offset is (PK * (1 + (brev3(e) << (LOGN + 1)))) & mask:
+        // the multiply adds brev3(e) * (E & 7) into the field at bits LOGN+1.. (overflow and the parked bits are masked off).
+        // One IMAD (or shift-add), one LOP3 and the load per look-up.  Generic path: x0 | (E & 7) << 20.
         u32 PK[TP][NC];
 #pragma unroll
         for (int q = 0; q < TP; q++) {
@@ -973,10 +1000,8 @@ __global__ void __launch_bounds__((PB / TP) * (K + 1) * (1 << LOGN) / 8, 1) k_bl
 #pragma unroll
                 for (int i = 0; i < M; i++) if ((fbs_unroll_mask(M, c) >> i) & 1) E += ai[i];
                 const u32 x0 = (E * odd0) & (2 * N - 1);
-                if constexpr (fast_psi) {
-                    const u32 lo = x0 & ((1u << (LOGN - 2)) - 1);
-                    PK[q][c] = (8u * (lo ^ (((lo >> 4) ^ (lo >> 8)) & 15u))) | ((x0 >> (LOGN - 2)) << 16) | ((E & 7u) << 20);
-                } else PK[q][c] = x0 | ((E & 7u) << 20);
+                if constexpr (fast_psi) PK[q][c] = (8u * psw(x0)) | (E & 7u);
+                else PK[q][c] = x0 | ((E & 7u) << 20);
             }
         }
         xsync();                                             // the partner warps' spectra are in shared memory
@@ -989,8 +1014,8 @@ __global__ void __launch_bounds__((PB / TP) * (K + 1) * (1 << LOGN) / 8, 1) k_bl
             auto factor = [&](int q, int c) -> rns2 {        // X^{E_c} - 1 at this thread's element e
                 const u32 pk = PK[q][c];
                 if constexpr (fast_psi) {
-                    const u32 h = ((pk >> 16) + (u32)BR3[e] * (pk >> 20)) & 7u;
-                    return rns_split(*(const u64 *)((const unsigned char *)PSI + ((pk & 0xFFFFu) ^ (h * HMUL))));
+                    const u32 off = (pk * (1u + ((u32)BR3[e] << (LOGN + 1)))) & ((2u * N - 1u) << 3);
+                    return rns_split(*(const u64 *)((const unsigned char *)PSI + off));
                 } else {
                     const u32 xi = ((pk & 0xFFFFu) + (((u32)BR3[e] * (pk >> 20)) << (LOGN - 2))) & (2 * N - 1);
                     return rns_split(PSI[psw(xi)]);
@@ -1166,7 +1191,8 @@ __global__ void __launch_bounds__((K + 1) * (1 << (LOGN - LOGC)) / 8, 1) k_blind
         for (int i = tid; i <= n; i += Cf::THREADS) s_ms[i] = ms[i];
     }
     const int tab0 = a.bs_tab_ptr[node], tabL = a.bs_tab_ptr[node + 1] - tab0, mode = a.bs_mode[node];
-    auto psw = [](u32 x) { return x ^ (((x >> 4) ^ (x >> 8)) & 15u); };
+    constexpr bool fast_psi = (LOGN - 2 >= 9) && (LOGN + 1 <= 12);                    // as in k_blind_rotate2
+    auto psw = [](u32 x) { return fast_psi ? x ^ ((x >> 5) & 15u) : x ^ (((x >> 4) ^ (x >> 8)) & 15u); };
     for (int i = tid; i < 2 * N; i += Cf::THREADS) PSI[psw((u32)i)] = a.psi_pow[i];
     for (int i = 1 + tid; i < Ns; i += Cf::THREADS) {
         ((uint4 *)TWF)[i] = __ldg((const uint4 *)a.psi_rev + ntt_local_src(i, C + h));
@@ -1278,8 +1304,6 @@ __global__ void __launch_bounds__((K + 1) * (1 << (LOGN - LOGC)) / 8, 1) k_blind
             }
             if (++slot == RING) { slot = 0; par ^= 1; }
         };
-        constexpr bool fast_psi = (LOGN - 2 >= 9) && (LOGN + 1 <= 12);
-        constexpr u32 HMUL = 8u * ((1u << (LOGN - 2)) | (fast_psi ? (1u << (LOGN - 2 - 8)) : 0u));
         u32 PK[NC];
         {
             u32 ai[M];
@@ -1291,10 +1315,8 @@ __global__ void __launch_bounds__((K + 1) * (1 << (LOGN - LOGC)) / 8, 1) k_blind
 #pragma unroll
                 for (int i = 0; i < M; i++) if ((fbs_unroll_mask(M, c) >> i) & 1) E += ai[i];
                 const u32 x0 = (E * odd0) & (2 * N - 1);
-                if constexpr (fast_psi) {
-                    const u32 lo = x0 & ((1u << (LOGN - 2)) - 1);
-                    PK[c] = (8u * (lo ^ (((lo >> 4) ^ (lo >> 8)) & 15u))) | ((x0 >> (LOGN - 2)) << 16) | ((E & 7u) << 20);
-                } else PK[c] = x0 | ((E & 7u) << 20);
+                if constexpr (fast_psi) PK[c] = (8u * psw(x0)) | (E & 7u);                  // see k_blind_rotate2
+                else PK[c] = x0 | ((E & 7u) << 20);
             }
         }
         xsync();
@@ -1307,8 +1329,8 @@ __global__ void __launch_bounds__((K + 1) * (1 << (LOGN - LOGC)) / 8, 1) k_blind
             auto factor = [&](int c) -> rns2 {
                 const u32 pk = PK[c];
                 if constexpr (fast_psi) {
-                    const u32 hh = ((pk >> 16) + (u32)BR3[e] * (pk >> 20)) & 7u;
-                    return rns_split(*(const u64 *)((const unsigned char *)PSI + ((pk & 0xFFFFu) ^ (hh * HMUL))));
+                    const u32 off = (pk * (1u + ((u32)BR3[e] << (LOGN + 1)))) & ((2u * N - 1u) << 3);
+                    return rns_split(*(const u64 *)((const unsigned char *)PSI + off));
                 } else {
                     const u32 xi = ((pk & 0xFFFFu) + (((u32)BR3[e] * (pk >> 20)) << (LOGN - 2))) & (2 * N - 1);
                     return rns_split(PSI[psw(xi)]);
@@ -1424,7 +1446,8 @@ __global__ void __launch_bounds__(2 * (K + 1) * (1 << (LOGN - LOGC)) / 8, OCC) k
         for (int i = tid; i <= n; i += THREADS) s_ms[i] = ms[i];
     }
     const int tab0 = a.bs_tab_ptr[node], tabL = a.bs_tab_ptr[node + 1] - tab0, mode = a.bs_mode[node];
-    auto psw = [](u32 x) { return x ^ (((x >> 4) ^ (x >> 8)) & 15u); };
+    constexpr bool fast_psi = (LOGN - 2 >= 9) && (LOGN + 1 <= 12);                    // as in k_blind_rotate2
+    auto psw = [](u32 x) { return fast_psi ? x ^ ((x >> 5) & 15u) : x ^ (((x >> 4) ^ (x >> 8)) & 15u); };
     for (int i = tid; i < 2 * N; i += THREADS) PSI[psw((u32)i)] = a.psi_pow[i];
     for (int i = 1 + tid; i < Ns; i += THREADS) {
         ((uint4 *)TWF)[i] = __ldg((const uint4 *)a.psi_rev + ntt_local_src(i, C + h));
@@ -1533,8 +1556,6 @@ __global__ void __launch_bounds__(2 * (K + 1) * (1 << (LOGN - LOGC)) / 8, OCC) k
             }
             if (++slot == RING) { slot = 0; par ^= 1; }
         };
-        constexpr bool fast_psi = (LOGN - 2 >= 9) && (LOGN + 1 <= 12);
-        constexpr u32 HMUL = 8u * ((1u << (LOGN - 2)) | (fast_psi ? (1u << (LOGN - 2 - 8)) : 0u));
         u32 PK[NC];
         {
             u32 ai[M];
@@ -1546,10 +1567,8 @@ __global__ void __launch_bounds__(2 * (K + 1) * (1 << (LOGN - LOGC)) / 8, OCC) k
 #pragma unroll
                 for (int i = 0; i < M; i++) if ((fbs_unroll_mask(M, c) >> i) & 1) E += ai[i];
                 const u32 x0 = (E * odd0) & (2 * N - 1);
-                if constexpr (fast_psi) {
-                    const u32 lo = x0 & ((1u << (LOGN - 2)) - 1);
-                    PK[c] = (8u * (lo ^ (((lo >> 4) ^ (lo >> 8)) & 15u))) | ((x0 >> (LOGN - 2)) << 16) | ((E & 7u) << 20);
-                } else PK[c] = x0 | ((E & 7u) << 20);
+                if constexpr (fast_psi) PK[c] = (8u * psw(x0)) | (E & 7u);                  // see k_blind_rotate2
+                else PK[c] = x0 | ((E & 7u) << 20);
             }
         }
         xsync();
@@ -1562,8 +1581,8 @@ __global__ void __launch_bounds__(2 * (K + 1) * (1 << (LOGN - LOGC)) / 8, OCC) k
             auto factor = [&](int c) -> u32 {
                 const u32 pk = PK[c];
                 if constexpr (fast_psi) {
-                    const u32 hh = ((pk >> 16) + (u32)BR3[e] * (pk >> 20)) & 7u;
-                    return *(const u32 *)(PSIb + ((pk & 0xFFFFu) ^ (hh * HMUL)));
+                    const u32 off = (pk * (1u + ((u32)BR3[e] << (LOGN + 1)))) & ((2u * N - 1u) << 3);
+                    return *(const u32 *)(PSIb + off);
                 } else {
                     const u32 xi = ((pk & 0xFFFFu) + (((u32)BR3[e] * (pk >> 20)) << (LOGN - 2))) & (2 * N - 1);
                     return *(const u32 *)(PSIb + 8u * psw(xi));
