@@ -29,8 +29,13 @@ __device__ __forceinline__ void mbar_expect_tx(u64 *bar, u32 bytes)
 __device__ __forceinline__ bool mbar_try_wait(u64 *bar, u32 parity)
 {
     u32 ok;
+#ifdef FBS_WAIT_HINT_NS
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity), "r"((u32)FBS_WAIT_HINT_NS) : "memory");
+#else
     asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                  : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+#endif
     return ok != 0;
 }
 __device__ __forceinline__ void mbar_wait(u64 *bar, u32 parity) { while (!mbar_try_wait(bar, parity)) { } }
@@ -799,10 +804,10 @@ struct BR2Cfg {
     // Key slice = every key word the CTA needs for ONE of the 8 elements a thread holds: [tau >> 5][c < NC][u < G][v < G][tau & 31]; a
     // step consumes 8 slices in element order.  HBM layout [key group][element][tau >> 5][c][u][v][tau & 31]: one bulk copy per slice.
     static constexpr size_t slice_w = NC * (size_t)G * G * T;
-    static constexpr size_t fixed_b = 8 * (PB * s_w + psi_w + tw_w) + PB * 2048 + 256;   // ms rows budgeted for n < 1024
+    static constexpr size_t fixed_b = 8 * (PB * s_w + psi_w + tw_w) + PB * 2048 + 512;   // ms rows budgeted for n < 1024; barriers
     static constexpr int R_fit = (int)((227 * 1024 - fixed_b) / (8 * slice_w));
-#ifndef FBS_REFILL_LAST
-#define FBS_REFILL_LAST 1   /* key-ring slot refilled by the last warp to release it (0: by thread 0, which waits for the others) */
+#ifndef FBS_BLOCK_RING
+#define FBS_BLOCK_RING 1    /* one key ring per block of 32 thread positions (0: one ring of whole slices, refilled by thread 0) */
 #endif
 #ifndef FBS_RING_MAX
 #define FBS_RING_MAX 3      /* measured at set A2: 2 slots 45.8 k, 3 slots 46.3 k, 4 45.8 k, 5 45.1 k PBS/s -- deeper rings only take L1 from the twiddles */
@@ -810,7 +815,8 @@ struct BR2Cfg {
     static constexpr int R = R_fit > FBS_RING_MAX ? FBS_RING_MAX : R_fit;                   // ring slots (prefetch distance)
     static_assert(R >= 2, "key ring does not fit shared memory");
     __host__ __device__ static constexpr size_t ms_stride(int n) { return (((size_t)(n + 1) * 2 + 15) / 16) * 16; }
-    __host__ __device__ static constexpr size_t smem_bytes(int n) { return 8 * (PB * s_w + psi_w + tw_w + R * slice_w + 2 * R) + PB * ms_stride(n); }
+    static constexpr int KBMAX = T / 32;                          // rings when FBS_BLOCK_RING (barrier space is reserved either way)
+    __host__ __device__ static constexpr size_t smem_bytes(int n) { return 8 * (PB * s_w + psi_w + tw_w + R * slice_w + 2 * R * KBMAX) + PB * ms_stride(n); }
 };
 template <int LOGN, int K, int PB, int TP, int M>
 __global__ void __launch_bounds__((PB / TP) * (K + 1) * (1 << LOGN) / 8, 1) k_blind_rotate2(BRArgs a)
@@ -826,9 +832,20 @@ __global__ void __launch_bounds__((PB / TP) * (K + 1) * (1 << LOGN) / 8, 1) k_bl
     u64 *PSI = (u64 *)smem_raw + (size_t)PB * PW;
     u64 *TW = PSI + C::psi_w;                                    // twiddles (when C::TWS)
     u64 *RING = TW + C::tw_w;
-    u64 *full = RING + (size_t)R * C::slice_w, *empty = full + R;  // mbarriers: slice landed / slice consumed by every warp
+    // Key ring.  FBS_BLOCK_RING: the 32 thread positions of block kb = tau >> 5 only ever read block kb of a slice (7 KB at M = 3),
+    // so every block has its OWN ring entries, full/empty mbarriers and issuing lane: the (PB / TP) * G warps that share a block
+    // refill it as soon as THEY are through with it, in 7 KB copies, instead of the CTA waiting for its slowest warp and for a
+    // 56 KB copy.  Otherwise one ring of whole slices, refilled by thread 0 when all warps have released a slot.
+    constexpr int KB = FBS_BLOCK_RING ? T / 32 : 1;               // independent rings
+    constexpr size_t KW = C::slice_w / KB;                        // words per ring entry
+    constexpr u32 KBYTES = (u32)(KW * 8);
+    const int kb = FBS_BLOCK_RING ? tau >> 5 : 0;
+    u64 *ring = RING + (size_t)kb * R * KW;
+    u64 *full = RING + (size_t)R * C::slice_w + (size_t)kb * 2 * R, *empty = full + R;   // mbarriers: entry landed / entry released by its warps
+    const u64 *ksrc = a.bsk + (size_t)kb * KW;
+    const bool issuer = FBS_BLOCK_RING ? (pb0 == 0 && g == 0 && (tau & 31) == 0) : tid == 0;
     const size_t ms_stride = C::ms_stride(a.n);
-    u16 *s_ms = (u16 *)((unsigned char *)(empty + R) + (size_t)pb0 * ms_stride);
+    u16 *s_ms = (u16 *)((unsigned char *)(RING + (size_t)R * C::slice_w + (size_t)C::KBMAX * 2 * R) + (size_t)pb0 * ms_stride);
     const int n = a.n, p = a.p;
     const int n_pairs = (n + M - 1) / M, n_slices = 8 * n_pairs;  // key groups; n is padded with zero key bits (a_i = 0) to a multiple of M
 
@@ -856,19 +873,15 @@ __global__ void __launch_bounds__((PB / TP) * (K + 1) * (1 << LOGN) / 8, 1) k_bl
     for (int i = tid; i < 2 * N; i += C::THREADS) PSI[psw((u32)i)] = a.psi_pow[i];
     if (C::TWS) for (int i = tid; i < 2 * N; i += C::THREADS) TW[i] = ((const u64 *)a.psi_rev)[i];
     const fq_tw *twp = C::TWS ? (const fq_tw *)TW : a.psi_rev;
-    if (tid == 0) {
-#if FBS_REFILL_LAST
-        for (int r = 0; r < R; r++) { mbar_init(full + r, 1); empty[r] = 0; }       // empty[r]: plain arrival counter
-#else
-        for (int r = 0; r < R; r++) { mbar_init(full + r, 1); mbar_init(empty + r, C::THREADS / 32); }
-#endif
+    if (issuer) {
+        for (int r = 0; r < R; r++) { mbar_init(full + r, 1); mbar_init(empty + r, FBS_BLOCK_RING ? (PB / TP) * G : C::THREADS / 32); }
     }
     __syncthreads();
-    if (tid == 0) {                                             // prologue: the first R slices
+    if (issuer) {                                               // prologue: the first R slices
         fence_proxy_async();
         for (int sl = 0; sl < R && sl < n_slices; sl++) {
-            mbar_expect_tx(full + sl, (u32)(C::slice_w * 8));
-            tma_load_1d(RING + (size_t)sl * C::slice_w, a.bsk + (size_t)sl * C::slice_w, (u32)(C::slice_w * 8), full + sl);
+            mbar_expect_tx(full + sl, KBYTES);
+            tma_load_1d(ring + (size_t)sl * KW, ksrc + (size_t)sl * C::slice_w, KBYTES, full + sl);
         }
     }
     // ---- accumulator init in registers: ACC = (0, .., 0, X^{-b~} * TV); this thread holds coefficients j = tau + e*T of polynomial g
@@ -918,7 +931,7 @@ __global__ void __launch_bounds__((PB / TP) * (K + 1) * (1 << LOGN) / 8, 1) k_bl
     // key words of this thread inside a slice: (((tau >> 5)*NC + c)*G*G + u*G + g)*32 + (tau & 31), u = (g + og) mod G
     u32 koff[G];
 #pragma unroll
-    for (int og = 0; og < G; og++) { int gg = g + og; if (gg >= G) gg -= G; koff[og] = (u32)((((tau >> 5) * NC * G * G + gg * G + g) * 32 + (tau & 31)) * 8); }
+    for (int og = 0; og < G; og++) { int gg = g + og; if (gg >= G) gg -= G; koff[og] = (u32)((((FBS_BLOCK_RING ? 0 : tau >> 5) * NC * G * G + gg * G + g) * 32 + (tau & 31)) * 8); }
     int slot = 0; u32 par = 0;                                    // ring position of the next slice to consume
 
     for (int t = 0; t < n_pairs; t++) {
@@ -949,34 +962,16 @@ __global__ void __launch_bounds__((PB / TP) * (K + 1) * (1 << LOGN) / 8, 1) k_bl
         // slot with the slice R ahead, so the copy overlaps the other elements' arithmetic or the transforms
         auto release_slot = [&](int e) {
             __syncwarp();
-#if FBS_REFILL_LAST
-            // the warp that arrives LAST refills the slot: nobody ever waits for the slowest warp (with a fixed producer thread
-            // the refill is late whenever that thread is, and the thread stalls -- and becomes late -- whenever it is early)
-            if ((tid & 31) == 0) {
-                u32 seen;
-                asm volatile("atom.acq_rel.cta.shared::cta.add.u32 %0, [%1], 1;" : "=r"(seen) : "r"(smem_u32(empty + slot)) : "memory");
-                if (seen == (u32)(C::THREADS / 32 - 1)) {
-                    *(volatile u32 *)(empty + slot) = 0u;      // next arrivals come after the refilled slice has landed and been used
-                    const int nxt = 8 * t + e + R;
-                    if (nxt < n_slices) {
-                        fence_proxy_async();
-                        mbar_expect_tx(full + slot, (u32)(C::slice_w * 8));
-                        tma_load_1d(RING + (size_t)slot * C::slice_w, a.bsk + (size_t)nxt * C::slice_w, (u32)(C::slice_w * 8), full + slot);
-                    }
-                }
-            }
-#else
             if ((tid & 31) == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(empty + slot)) : "memory");
-            if (tid == 0) {
+            if (issuer) {
                 const int nxt = 8 * t + e + R;
                 if (nxt < n_slices) {
                     mbar_wait(empty + slot, par);
                     fence_proxy_async();
-                    mbar_expect_tx(full + slot, (u32)(C::slice_w * 8));
-                    tma_load_1d(RING + (size_t)slot * C::slice_w, a.bsk + (size_t)nxt * C::slice_w, (u32)(C::slice_w * 8), full + slot);
+                    mbar_expect_tx(full + slot, KBYTES);
+                    tma_load_1d(ring + (size_t)slot * KW, ksrc + (size_t)nxt * C::slice_w, KBYTES, full + slot);
                 }
             }
-#endif
             if (++slot == R) { slot = 0; par ^= 1; }
         };
         static_assert(M == 2 || G == 2, "the M = 3 sums are sized for k = 1");
@@ -1010,7 +1005,7 @@ __global__ void __launch_bounds__((PB / TP) * (K + 1) * (1 << LOGN) / 8, 1) k_bl
             const u32 o = bo[0] ^ P::elem_boff(e, 0);
             constexpr int BR3[8] = {0, 4, 2, 6, 1, 5, 3, 7};
             mbar_wait(full + slot, par);
-            const unsigned char *ks = (const unsigned char *)(RING + (size_t)slot * C::slice_w);
+            const unsigned char *ks = (const unsigned char *)(ring + (size_t)slot * KW);
             auto factor = [&](int q, int c) -> rns2 {        // X^{E_c} - 1 at this thread's element e
                 const u32 pk = PK[q][c];
                 if constexpr (fast_psi) {
