@@ -49,13 +49,13 @@ template <int LOGN, int K, int PB, int TP, int M>
 static cudaError_t br2_launch(const BRArgs &a, long long jobs, size_t smem, cudaStream_t st)
 {
     const long long grid = (jobs - a.job_begin + PB - 1) / PB;
-    k_blind_rotate2<LOGN, K, PB, TP, M><<<(unsigned)grid, BR2Cfg<LOGN, K, PB, TP, M>::THREADS, smem, st>>>(a);
+    k_blind_rotate2<LOGN, K, PB, TP, M><<<(unsigned)grid, BR2Cfg<LOGN, K, PB, TP, M>::THREADS, smem - BR2Cfg<LOGN, K, PB, TP, M>::static_b, st>>>(a);   // smem = static + dynamic
     return cudaGetLastError();
 }
 template <int LOGN, int K, int PB, int TP, int M>
 static cudaError_t br2_prepare(size_t smem)
 {
-    return cudaFuncSetAttribute(k_blind_rotate2<LOGN, K, PB, TP, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    return cudaFuncSetAttribute(k_blind_rotate2<LOGN, K, PB, TP, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem - BR2Cfg<LOGN, K, PB, TP, M>::static_b));
 }
 template <int LOGN, int K, int PB, int TP, int M> static size_t br2_smem(int n) { return BR2Cfg<LOGN, K, PB, TP, M>::smem_bytes(n); }
 #define BRV2(LOGN, K, PB, TP, M) { LOGN, K, 1, false, PB, TP, BR2Cfg<LOGN, K, PB, TP, M>::THREADS, br2_smem<LOGN, K, PB, TP, M>, br2_launch<LOGN, K, PB, TP, M>, br2_prepare<LOGN, K, PB, TP, M>, M }

@@ -806,6 +806,9 @@ struct BR2Cfg {
     static constexpr size_t slice_w = NC * (size_t)G * G * T;
     static constexpr size_t fixed_b = 8 * (PB * s_w + psi_w + tw_w) + PB * 2048 + 512;   // ms rows budgeted for n < 1024; barriers
     static constexpr int R_fit = (int)((227 * 1024 - fixed_b) / (8 * slice_w));
+#ifndef FBS_PSI_STATIC
+#define FBS_PSI_STATIC 1    /* psi^x table in static shared memory (constant address folded into the look-up) */
+#endif
 #ifndef FBS_BLOCK_RING
 #define FBS_BLOCK_RING 1    /* one key ring per block of 32 thread positions (0: one ring of whole slices, refilled by thread 0) */
 #endif
@@ -816,6 +819,7 @@ struct BR2Cfg {
     static_assert(R >= 2, "key ring does not fit shared memory");
     __host__ __device__ static constexpr size_t ms_stride(int n) { return (((size_t)(n + 1) * 2 + 15) / 16) * 16; }
     static constexpr int KBMAX = T / 32;                          // rings when FBS_BLOCK_RING (barrier space is reserved either way)
+    static constexpr size_t static_b = FBS_PSI_STATIC ? 8 * psi_w : 0;   // part of smem_bytes() that is static shared memory
     __host__ __device__ static constexpr size_t smem_bytes(int n) { return 8 * (PB * s_w + psi_w + tw_w + R * slice_w + 2 * R * KBMAX) + PB * ms_stride(n); }
 };
 template <int LOGN, int K, int PB, int TP, int M>
@@ -829,8 +833,15 @@ __global__ void __launch_bounds__((PB / TP) * (K + 1) * (1 << LOGN) / 8, 1) k_bl
     const int tid = threadIdx.x, pb0 = (TP == 1) ? tid / C::PT : 0, ptid = tid % C::PT, g = ptid / T, tau = ptid % T;
     constexpr size_t PW = C::s_w, PWB = PW * 8;
     u64 *S = (u64 *)smem_raw + (size_t)pb0 * PW;                 // bootstrap q of this thread: S + q*PW
+#if FBS_PSI_STATIC
+    // psi^x table in STATIC shared memory: its address is a link-time constant, so a look-up is LDS [offset + constant] and needs
+    // no add of the table base (one IMAD.IADD per look-up less, 98 per warp and step)
+    __shared__ __align__(16) u64 PSI[2 * N];
+    u64 *TW = (u64 *)smem_raw + (size_t)PB * PW;                 // twiddles (when C::TWS)
+#else
     u64 *PSI = (u64 *)smem_raw + (size_t)PB * PW;
     u64 *TW = PSI + C::psi_w;                                    // twiddles (when C::TWS)
+#endif
     u64 *RING = TW + C::tw_w;
     // Key ring.  FBS_BLOCK_RING: the 32 thread positions of block kb = tau >> 5 only ever read block kb of a slice (7 KB at M = 3),
     // so every block has its OWN ring entries, full/empty mbarriers and issuing lane: the (PB / TP) * G warps that share a block
