@@ -86,7 +86,7 @@ template <int LOGN, int K, int M, int LOGC, bool PS, int OCC> struct BrcKernel {
     static void config(cudaLaunchConfig_t &cfg, cudaLaunchAttribute *at, unsigned clusters, size_t smem, cudaStream_t st)
     {
         cfg = cudaLaunchConfig_t{};
-        cfg.gridDim = dim3(clusters << LOGC); cfg.blockDim = dim3((PS ? 2 : 1) * Cf::THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+        cfg.gridDim = dim3(clusters << LOGC); cfg.blockDim = dim3((PS ? 2 : 1) * Cf::THREADS); cfg.dynamicSmemBytes = smem - Cf::static_b; cfg.stream = st;      // smem = static + dynamic
         at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 1 << LOGC; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
         cfg.attrs = at; cfg.numAttrs = 1;
     }
@@ -96,7 +96,7 @@ template <int LOGN, int K, int M, int LOGC, bool PS, int OCC> struct BrcKernel {
         config(cfg, at, (unsigned)(jobs - a.job_begin), smem, st);
         return cudaLaunchKernelEx(&cfg, fn(), a);
     }
-    static cudaError_t prepare(size_t smem) { return cudaFuncSetAttribute(fn(), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); }
+    static cudaError_t prepare(size_t smem) { return cudaFuncSetAttribute(fn(), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem - Cf::static_b)); }
     static size_t smem(int n) { return Cf::smem_bytes(n); }
     // how many clusters of this kernel the device can hold at once (the hardware may strand SMs: 33 clusters of 4 on a 148-SM B200)
     static cudaError_t max_clusters(size_t smem, int *out)

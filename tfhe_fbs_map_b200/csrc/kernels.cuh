@@ -1139,6 +1139,7 @@ struct BRCCfg {
     static_assert(RING >= 2, "key ring does not fit shared memory");
     __host__ __device__ static constexpr size_t ms_stride(int n) { return (((size_t)(n + 1) * 2 + 15) / 16) * 16; }
     __host__ __device__ static constexpr size_t smem_bytes(int n) { return 8 * (s_w + 2 * inbox_w + psi_w + 2 * tw_w + RING * slice_w + 2 * RING + 2) + ms_stride(n); }
+    static constexpr size_t static_b = FBS_PSI_STATIC ? 8 * psi_w : 0;    // part of smem_bytes() that is static shared memory
 };
 __device__ __forceinline__ u32 cluster_ctarank() { u32 r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
 __device__ __forceinline__ u32 mapa_shared(u32 local_addr, u32 cta) { u32 r; asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(cta)); return r; }
@@ -1181,8 +1182,13 @@ __global__ void __launch_bounds__((K + 1) * (1 << (LOGN - LOGC)) / 8, 1) k_blind
     const int tau_g = h * Ts + tau;                               // spectrum positions 8*tau_g + e of the full transform
     u64 *S = (u64 *)smem_raw;
     u64 *INF = S + Cf::s_w, *INI = INF + Cf::inbox_w;             // inboxes: forward / inverse exchange, [g][e][tau]
+#if FBS_PSI_STATIC
+    __shared__ __align__(16) u64 PSI[2 * N];                      // static: constant address folded into the look-ups (see k_blind_rotate2)
+    u64 *TWF = INI + Cf::inbox_w, *TWI = TWF + Cf::tw_w;          // local twiddle tables (fq_tw entries)
+#else
     u64 *PSI = INI + Cf::inbox_w;
     u64 *TWF = PSI + Cf::psi_w, *TWI = TWF + Cf::tw_w;            // local twiddle tables (fq_tw entries)
+#endif
     u64 *RNG = TWI + Cf::tw_w;
     u64 *full = RNG + (size_t)RING * Cf::slice_w, *empty = full + RING, *xbar = empty + RING;   // xbar[0]: forward inbox full, xbar[1]: inverse
     u16 *s_ms = (u16 *)(xbar + 2);
@@ -1436,8 +1442,13 @@ __global__ void __launch_bounds__(2 * (K + 1) * (1 << (LOGN - LOGC)) / 8, OCC) k
     const int tau_g = h * Ts + tau;
     u64 *S = (u64 *)smem_raw;
     u64 *INF = S + Cf::s_w, *INI = INF + Cf::inbox_w;
+#if FBS_PSI_STATIC
+    __shared__ __align__(16) u64 PSI[2 * N];
+    u64 *TWF = INI + Cf::inbox_w, *TWI = TWF + Cf::tw_w;
+#else
     u64 *PSI = INI + Cf::inbox_w;
     u64 *TWF = PSI + Cf::psi_w, *TWI = TWF + Cf::tw_w;
+#endif
     u64 *RNG = TWI + Cf::tw_w;
     u64 *full = RNG + (size_t)RING * Cf::slice_w, *empty = full + RING, *xbar = empty + RING;
     u16 *s_ms = (u16 *)(xbar + 2);
