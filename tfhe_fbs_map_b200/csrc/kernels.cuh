@@ -1020,7 +1020,11 @@ __global__ void __launch_bounds__((PB / TP) * (K + 1) * (1 << LOGN) / 8, 1) k_bl
             auto factor = [&](int q, int c) -> rns2 {        // X^{E_c} - 1 at this thread's element e
                 const u32 pk = PK[q][c];
                 if constexpr (fast_psi) {
+#ifdef FBS_PSI_FAKE   /* timing experiment only (wrong results): the same instructions, but conflict-free addresses */
+                    const u32 off = ((pk * (1u + ((u32)BR3[e] << (LOGN + 1)))) & (7u << (LOGN + 1))) | ((u32)(tid & 31) << 3);
+#else
                     const u32 off = (pk * (1u + ((u32)BR3[e] << (LOGN + 1)))) & ((2u * N - 1u) << 3);
+#endif
                     return rns_split(*(const u64 *)((const unsigned char *)PSI + off));
                 } else {
                     const u32 xi = ((pk & 0xFFFFu) + (((u32)BR3[e] * (pk >> 20)) << (LOGN - 2))) & (2 * N - 1);
