@@ -254,6 +254,7 @@ static int ctx_create_impl(const fbs_params *params, int device, uint64_t seed, 
     // the attribute belongs to the FUNCTION, not to this context: contexts with different n share a kernel instantiation,
     // so it is raised to the device limit once instead of to this context's need (a later, smaller context would lower it)
     CK(br->prepare((size_t)prop.sharedMemPerBlockOptin));
+    CK(cudaFuncSetAttribute(k_keyswitch_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KS_SMEM_BYTES));
     c->br1_smem = c->br1->smem(P.n);
     if (c->br1 != c->br) CK(c->br1->prepare((size_t)prop.sharedMemPerBlockOptin));
     for (const BRCVariant &v : g_brc_variants) if (v.logN == logN && v.k == P.k && v.unr == unroll && P.bsk_l == 1) {
@@ -576,7 +577,7 @@ static int run_level_impl(fbs_ctx *c, fbs_prog *g, int level, int nb, int ne, in
     ka.digits = c->d_digits; ka.body = c->d_body; ka.kbt = c->d_kbt; ka.colsum = c->d_colsum; ka.ms = c->d_ms; ka.tap_ks = tap_ks;
     ka.M = M; ka.R = (int)R; ka.n = n; ka.ks_beta = P.ks_beta; ka.log2_2N = c->logN + 1;
     const unsigned ngrid = (unsigned)(((n + 1 + 7) / 8 * 8 * 8 + KS_BN - 1) / KS_BN);
-    k_keyswitch_mma<<<dim3((unsigned)mtiles, ngrid), 256, 0, st>>>(ka);
+    k_keyswitch_mma<<<dim3((unsigned)mtiles, ngrid), 256, KS_SMEM_BYTES, st>>>(ka);
     CK(cudaGetLastError());
     if (rec) CK(cudaEventRecord(E[2], st));
     BRArgs ba{};

@@ -371,7 +371,7 @@ __global__ void __launch_bounds__(256) k_lincomb_decomp(LCArgs a)
 // This is the one GEMM-shaped step of the path: 8x more MACs than the integer-pipe version
 // (2 IMAD.WIDE per MAC), but on a unit that is otherwise idle -- measured 18.3 -> 1.3 ms per 4736 ciphertexts (profiles/README.md).
 // KbT[(c*8+b)][r] is the byte-transposed key (k-contiguous "col" operand), CTA tile 64 ciphertexts x 8 columns x 128 rows,
-// cp.async double buffering, 144-byte padded rows (bank-conflict-free 32-bit fragment loads).
+// 4-stage cp.async pipeline, 144-byte padded rows (bank-conflict-free 32-bit fragment loads).
 // ------------------------------------------------------------------------------------------------------
 struct KSArgs {
     const u8 *digits; const u64 *body; const u8 *kbt; const u64 *colsum;
@@ -391,10 +391,15 @@ __device__ __forceinline__ void mma_u8(int (&c)[4], u32 a0, u32 a1, u32 a2, u32 
     asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.u8.u8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                  : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
+#ifndef KS_STAGES
+#define KS_STAGES 4      /* cp.async pipeline depth: with 2 a narrow level's key switch is one L2 round trip per 128 key rows (80 in a row) */
+#endif
+#define KS_SMEM_BYTES ((size_t)KS_STAGES * (KS_BM + KS_BN) * KS_LD)
 __global__ void __launch_bounds__(256) k_keyswitch_mma(KSArgs a)
 {
-    __shared__ __align__(16) u8 sA[2][KS_BM * KS_LD];
-    __shared__ __align__(16) u8 sB[2][KS_BN * KS_LD];
+    extern __shared__ __align__(16) unsigned char ks_smem[];
+    u8 (*sA)[KS_BM * KS_LD] = (u8 (*)[KS_BM * KS_LD])ks_smem;
+    u8 (*sB)[KS_BN * KS_LD] = (u8 (*)[KS_BN * KS_LD])(ks_smem + (size_t)KS_STAGES * KS_BM * KS_LD);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
     const int wm = warp & 3, wn = warp >> 2;
     const long long m0 = (long long)blockIdx.x * KS_BM;
@@ -414,13 +419,18 @@ __global__ void __launch_bounds__(256) k_keyswitch_mma(KSArgs a)
 #pragma unroll
     for (int j = 0; j < 4; j++) { acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0; }
     const int nk = a.R / KS_BK;
-    load_stage(0, 0);
+    // KS_STAGES - 1 stages in flight; every iteration commits exactly one group (an empty one past the end), so that
+    // wait_group KS_STAGES - 2 always means "stage ks has landed"
+    for (int st = 0; st < KS_STAGES - 1; st++) {
+        if (st < nk) load_stage(st, st * KS_BK); else asm volatile("cp.async.commit_group;" ::: "memory");
+    }
     for (int ks = 0; ks < nk; ks++) {
-        if (ks + 1 < nk) { load_stage((ks + 1) & 1, (ks + 1) * KS_BK); asm volatile("cp.async.wait_group 1;" ::: "memory"); }
-        else asm volatile("cp.async.wait_group 0;" ::: "memory");
-        __syncthreads();
-        const u8 *A = sA[ks & 1] + (wm * 16 + g) * KS_LD + t * 4;
-        const u8 *Bp = sB[ks & 1] + (wn * 32 + g) * KS_LD + t * 4;
+        asm volatile("cp.async.wait_group %0;" ::"n"(KS_STAGES - 2) : "memory");
+        __syncthreads();                                 // stage ks visible to all; everybody is done with stage ks - 1 (refilled next)
+        if (ks + KS_STAGES - 1 < nk) load_stage((ks + KS_STAGES - 1) % KS_STAGES, (ks + KS_STAGES - 1) * KS_BK);
+        else asm volatile("cp.async.commit_group;" ::: "memory");
+        const u8 *A = sA[ks % KS_STAGES] + (wm * 16 + g) * KS_LD + t * 4;
+        const u8 *Bp = sB[ks % KS_STAGES] + (wn * 32 + g) * KS_LD + t * 4;
 #pragma unroll
         for (int kk = 0; kk < KS_BK / 32; kk++) {
             const u32 a0 = *(const u32 *)(A + kk * 32), a1 = *(const u32 *)(A + 8 * KS_LD + kk * 32);
@@ -431,7 +441,6 @@ __global__ void __launch_bounds__(256) k_keyswitch_mma(KSArgs a)
                 mma_u8(acc[j], a0, a1, a2, a3, b0, b1);
             }
         }
-        __syncthreads();
     }
     // ---- epilogue: recombine the 8 byte sums of each column, remove the digit offset, add the body, modulus switch
     const int cols = a.n + 1;
