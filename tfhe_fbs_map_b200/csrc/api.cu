@@ -1117,3 +1117,15 @@ extern "C" int fbs_sync_status(fbs_ctx *c, int32_t *timed_out)
     *timed_out = v;
     return FBS_OK;
 }
+
+#ifdef FBS_PHASE_CLK
+// profiling builds only (not part of include/fbs_b200.h): read and reset the per-phase clock sums of k_blind_rotate2
+extern "C" int fbs_debug_phase_clk(unsigned long long *out8)
+{
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpyFromSymbol(out8, g_phase_clk, sizeof(unsigned long long) * 8));
+    unsigned long long z[8] = {0};
+    CK(cudaMemcpyToSymbol(g_phase_clk, z, sizeof(z)));
+    return FBS_OK;
+}
+#endif

@@ -831,6 +831,12 @@ struct BR2Cfg {
     static constexpr size_t static_b = FBS_PSI_STATIC ? 8 * psi_w : 0;   // part of smem_bytes() that is static shared memory
     __host__ __device__ static constexpr size_t smem_bytes(int n) { return 8 * (PB * s_w + psi_w + tw_w + R * slice_w + 2 * R * KBMAX) + PB * ms_stride(n); }
 };
+#ifdef FBS_PHASE_CLK   /* profiling builds only: SM clocks warp 0 of every CTA spends per phase of a step (tools/phase_clock.py) */
+__device__ unsigned long long g_phase_clk[8];
+#define PHASE_MARK(i) do { if (tid == 0) { const long long now_ = clock64(); ph_[i] += now_ - last_; last_ = now_; } } while (0)
+#else
+#define PHASE_MARK(i) do { } while (0)
+#endif
 template <int LOGN, int K, int PB, int TP, int M>
 __global__ void __launch_bounds__((PB / TP) * (K + 1) * (1 << LOGN) / 8, 1) k_blind_rotate2(BRArgs a)
 {
@@ -954,6 +960,9 @@ __global__ void __launch_bounds__((PB / TP) * (K + 1) * (1 << LOGN) / 8, 1) k_bl
     for (int og = 0; og < G; og++) { int gg = g + og; if (gg >= G) gg -= G; koff[og] = (u32)((((FBS_BLOCK_RING ? 0 : tau >> 5) * NC * G * G + gg * G + g) * 32 + (tau & 31)) * 8); }
     int slot = 0; u32 par = 0;                                    // ring position of the next slice to consume
 
+#ifdef FBS_PHASE_CLK
+    long long ph_[5] = {0, 0, 0, 0, 0}, last_ = clock64();
+#endif
     for (int t = 0; t < n_pairs; t++) {
         // ---- decompose ACC_g itself: one balanced digit per coefficient (L = 1), lazy residues in (0, 2p)
         rns2 dg[1][TP][8];
@@ -966,7 +975,9 @@ __global__ void __launch_bounds__((PB / TP) * (K + 1) * (1 << LOGN) / 8, 1) k_bl
                 dg[0][q][e].a = d + FQ_P1;
                 dg[0][q][e].b = d + FQ_P2;
             }
+        PHASE_MARK(0);                                       // decomposition
         ntt_fwd1_from<LOGN, 0, TP, decltype(gsync), C::TWS>(dg[0], tau, Sb, PWB, bo, twp, gsync, true, a.zero);
+        PHASE_MARK(1);                                       // forward transform
 #pragma unroll
         for (int e = 0; e < 8; e++) {
             const u32 o = bo[0] ^ P::elem_boff(e, 0);
@@ -1024,7 +1035,13 @@ __global__ void __launch_bounds__((PB / TP) * (K + 1) * (1 << LOGN) / 8, 1) k_bl
         for (int e = 0; e < 8; e++) {
             const u32 o = bo[0] ^ P::elem_boff(e, 0);
             constexpr int BR3[8] = {0, 4, 2, 6, 1, 5, 3, 7};
+#ifdef FBS_PHASE_CLK
+            const long long w0_ = clock64();
+#endif
             mbar_wait(full + slot, par);
+#ifdef FBS_PHASE_CLK
+            if (tid == 0) ph_[4] += clock64() - w0_;         // part of phase 2 spent waiting for the key block
+#endif
             const unsigned char *ks = (const unsigned char *)(ring + (size_t)slot * KW);
             auto factor = [&](int q, int c) -> rns2 {        // X^{E_c} - 1 at this thread's element e
                 const u32 pk = PK[q][c];
@@ -1075,8 +1092,10 @@ __global__ void __launch_bounds__((PB / TP) * (K + 1) * (1 << LOGN) / 8, 1) k_bl
             }
             release_slot(e);
         }
+        PHASE_MARK(2);                                           // spectra exchange + point-wise products
         auto after_pass0 = [&] { xsync(); };                     // the partner warps have read this step's digit spectra
         ntt_inv1_from<LOGN, 0, TP, decltype(after_pass0), decltype(gsync), C::TWS>(x, tau, Sb, PWB, bo, twp, after_pass0, gsync, a.zero);
+        PHASE_MARK(3);                                           // inverse transform
 #pragma unroll
         for (int e = 0; e < 8; e++)
 #pragma unroll
@@ -1085,6 +1104,9 @@ __global__ void __launch_bounds__((PB / TP) * (K + 1) * (1 << LOGN) / 8, 1) k_bl
                 av[q][e].b = r32_csub(r32_fold(av[q][e].b + x[q][e].b + a.zero, 2 * FQ_P2), FQ_P2);
             }
     }
+#ifdef FBS_PHASE_CLK
+    if (tid == 0) for (int i = 0; i < 5; i++) atomicAdd(&g_phase_clk[i], (unsigned long long)ph_[i]);
+#endif
     // ---- accumulator to shared memory (natural order), then K3 as in k_blind_rotate
     gsync();                                             // the group's last transposed reads are done
 #pragma unroll
