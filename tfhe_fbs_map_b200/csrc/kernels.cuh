@@ -818,6 +818,9 @@ struct BR2Cfg {
 #ifndef FBS_PSI_STATIC
 #define FBS_PSI_STATIC 1    /* psi^x table in static shared memory (constant address folded into the look-up) */
 #endif
+#ifndef FBS_EARLY_RELEASE
+#define FBS_EARLY_RELEASE 1 /* release a key-ring entry (and wait for the next) right after its last load instead of at the end of the element */
+#endif
 #ifndef FBS_BLOCK_RING
 #define FBS_BLOCK_RING 1    /* one key ring per block of 32 thread positions (0: one ring of whole slices, refilled by thread 0) */
 #endif
@@ -1038,7 +1041,7 @@ __global__ void __launch_bounds__((PB / TP) * (K + 1) * (1 << LOGN) / 8, 1) k_bl
 #ifdef FBS_PHASE_CLK
             const long long w0_ = clock64();
 #endif
-            mbar_wait(full + slot, par);
+            if (!FBS_EARLY_RELEASE || e == 0) mbar_wait(full + slot, par);      // (elements 1..7: waited for below, one element ahead)
 #ifdef FBS_PHASE_CLK
             if (tid == 0) ph_[4] += clock64() - w0_;         // part of phase 2 spent waiting for the key block
 #endif
@@ -1075,22 +1078,38 @@ __global__ void __launch_bounds__((PB / TP) * (K + 1) * (1 << LOGN) / 8, 1) k_bl
                     }                                                                    // < NC p^2 <= 7 p^2 < 2^63
                 }
             }
+            rns2 dsp[TP][G];                                 // digit spectra of this element (< 2p): own group's and the partner groups'
+#pragma unroll
+            for (int q = 0; q < TP; q++)
+#pragma unroll
+                for (int og = 0; og < G; og++) {
+                    int gg = g + og; if (gg >= G) gg -= G;
+                    const u32 xg = (og == 0) ? 0u : (G == 2) ? (1u << SH) : ((u32)(g ^ gg) << SH);
+                    dsp[q][og] = rns_split(*(const u64 *)(Sb + q * PWB + (o ^ xg)));
+                }
+#if FBS_EARLY_RELEASE
+            // The key words of this element are in registers: release its ring entry and wait for the next element's entry NOW, so
+            // that the reductions below (no key loads) overlap the first loads of the next element instead of sitting between two
+            // scheduling barriers.  (mbarrier.arrive has release semantics: the loads above are performed before it is observed.)
+            release_slot(e);
+            if (e < 7) mbar_wait(full + slot, par);
+#endif
 #pragma unroll
             for (int q = 0; q < TP; q++) {
                 u64 oa = 0, ob = 0;
 #pragma unroll
                 for (int og = 0; og < G; og++) {
                     const u32 ba = r32_redc(pa[q][og], FQ_P1, FQ_P1_INVNEG), bb = r32_redc(pb2[q][og], FQ_P2, FQ_P2_INVNEG);   // < (NC/4 + 1) p + 1
-                    int gg = g + og; if (gg >= G) gg -= G;
-                    const u32 xg = (og == 0) ? 0u : (G == 2) ? (1u << SH) : ((u32)(g ^ gg) << SH);
-                    const rns2 d = rns_split(*(const u64 *)(Sb + q * PWB + (o ^ xg)));            // digit spectrum, < 2p
+                    const rns2 d = dsp[q][og];
                     if (og == 0) { oa = r32_mulwide(d.a, ba); ob = r32_mulwide(d.b, bb); }
                     else { oa = r32_madwide(d.a, ba, oa); ob = r32_madwide(d.b, bb, ob); }        // < G * 2 (NC/4 + 1) p^2 < 2^64 (M = 2: G <= 3, M = 3: G = 2)
                 }
                 x[q][e].a = r32_fold(r32_redc(oa, FQ_P1, FQ_P1_INVNEG), 2 * FQ_P1);               // < 4 p before the fold
                 x[q][e].b = r32_fold(r32_redc(ob, FQ_P2, FQ_P2_INVNEG), 2 * FQ_P2);
             }
+#if !FBS_EARLY_RELEASE
             release_slot(e);
+#endif
         }
         PHASE_MARK(2);                                           // spectra exchange + point-wise products
         auto after_pass0 = [&] { xsync(); };                     // the partner warps have read this step's digit spectra
@@ -1371,7 +1390,7 @@ __global__ void __launch_bounds__((K + 1) * (1 << (LOGN - LOGC)) / 8, 1) k_blind
         for (int e = 0; e < 8; e++) {
             const u32 o = bo[0] ^ P::elem_boff(e, 0);
             constexpr int BR3[8] = {0, 4, 2, 6, 1, 5, 3, 7};
-            mbar_wait(full + slot, par);
+            if (!FBS_EARLY_RELEASE || e == 0) mbar_wait(full + slot, par);      // elements 1..7: waited for one element ahead (see k_blind_rotate2)
             const unsigned char *ks = (const unsigned char *)(RNG + (size_t)slot * Cf::slice_w);
             auto factor = [&](int c) -> rns2 {
                 const u32 pk = PK[c];
@@ -1394,6 +1413,10 @@ __global__ void __launch_bounds__((K + 1) * (1 << (LOGN - LOGC)) / 8, 1) k_blind
                     else { pa[og] = r32_madwide(f.a, kk.a, pa[og]); pb2[og] = r32_madwide(f.b, kk.b, pb2[og]); }
                 }
             }
+#if FBS_EARLY_RELEASE
+            release_slot(e);                                 // key words are in registers: free the entry, wait for the next one now
+            if (e < 7) mbar_wait(full + slot, par);
+#endif
             u64 oa = 0, ob = 0;
 #pragma unroll
             for (int og = 0; og < G; og++) {
@@ -1406,7 +1429,9 @@ __global__ void __launch_bounds__((K + 1) * (1 << (LOGN - LOGC)) / 8, 1) k_blind
             }
             x[0][e].a = r32_fold(r32_redc(oa, FQ_P1, FQ_P1_INVNEG), 2 * FQ_P1);
             x[0][e].b = r32_fold(r32_redc(ob, FQ_P2, FQ_P2_INVNEG), 2 * FQ_P2);
+#if !FBS_EARLY_RELEASE
             release_slot(e);
+#endif
         }
         // ---- local inverse transform, inverse exchange, cross butterflies, accumulate
         auto after_pass0 = [&] { xsync(); };
@@ -1628,7 +1653,7 @@ __global__ void __launch_bounds__(2 * (K + 1) * (1 << (LOGN - LOGC)) / 8, OCC) k
         for (int e = 0; e < 8; e++) {
             const u32 o = bo[0] ^ P::elem_boff(e, 0);
             constexpr int BR3[8] = {0, 4, 2, 6, 1, 5, 3, 7};
-            mbar_wait(full + slot, par);
+            if (!FBS_EARLY_RELEASE || e == 0) mbar_wait(full + slot, par);      // elements 1..7: waited for one element ahead (see k_blind_rotate2)
             const unsigned char *ks = (const unsigned char *)(RNG + (size_t)slot * Cf::slice_w);
             auto factor = [&](int c) -> u32 {
                 const u32 pk = PK[c];
@@ -1650,6 +1675,10 @@ __global__ void __launch_bounds__(2 * (K + 1) * (1 << (LOGN - LOGC)) / 8, OCC) k
                     pa[og] = (c == 0) ? r32_mulwide(f, kk) : r32_madwide(f, kk, pa[og]);
                 }
             }
+#if FBS_EARLY_RELEASE
+            release_slot(e);                                 // key words are in registers: free the entry, wait for the next one now
+            if (e < 7) mbar_wait(full + slot, par);
+#endif
             u64 oa = 0;
 #pragma unroll
             for (int og = 0; og < G; og++) {
@@ -1660,7 +1689,9 @@ __global__ void __launch_bounds__(2 * (K + 1) * (1 << (LOGN - LOGC)) / 8, OCC) k
                 oa = (og == 0) ? r32_mulwide(d, ba) : r32_madwide(d, ba, oa);
             }
             x[e] = r32_fold(r32_redc(oa, pr, pinv), pr2);
+#if !FBS_EARLY_RELEASE
             release_slot(e);
+#endif
         }
         auto after_pass0 = [&] { xsync(); };
         ntt_inv1p_from<LOGNS, 0, 4, decltype(after_pass0), decltype(gsync), true>(x, tau, Sb, bo, twi, l, pr, after_pass0, gsync, a.zero);
