@@ -818,6 +818,9 @@ struct BR2Cfg {
 #ifndef FBS_PSI_STATIC
 #define FBS_PSI_STATIC 1    /* psi^x table in static shared memory (constant address folded into the look-up) */
 #endif
+#ifndef FBS_LAST_REFILLS
+#define FBS_LAST_REFILLS 0  /* 1: a block's ring entry is refilled by whichever of its warps releases it last (no waiting issuer) */
+#endif
 #ifndef FBS_EARLY_RELEASE
 #define FBS_EARLY_RELEASE 1 /* release a key-ring entry (and wait for the next) right after its last load instead of at the end of the element */
 #endif
@@ -996,6 +999,22 @@ __global__ void __launch_bounds__((PB / TP) * (K + 1) * (1 << LOGN) / 8, 1) k_bl
         // slot with the slice R ahead, so the copy overlaps the other elements' arithmetic or the transforms
         auto release_slot = [&](int e) {
             __syncwarp();
+#if FBS_LAST_REFILLS && FBS_BLOCK_RING
+            // The warp whose arrival completes the entry's "empty" phase refills it -- known from the state the arrive returns (pending
+            // count 1 before the arrive = this was the last one): exactly one lane issues the copy and nobody ever waits for a partner.
+            if ((tid & 31) == 0) {
+                u64 st_; u32 pend_;
+                asm volatile("mbarrier.arrive.shared::cta.b64 %0, [%1];" : "=l"(st_) : "r"(smem_u32(empty + slot)) : "memory");
+                asm("mbarrier.pending_count.b64 %0, %1;" : "=r"(pend_) : "l"(st_));
+                const int nxt = 8 * t + e + R;
+                if (pend_ == 1u && nxt < n_slices) {
+                    asm volatile("fence.acq_rel.cta;" ::: "memory");        // the other warps' reads of the entry (released by their arrives)
+                    fence_proxy_async();
+                    mbar_expect_tx(full + slot, KBYTES);
+                    tma_load_1d(ring + (size_t)slot * KW, ksrc + (size_t)nxt * C::slice_w, KBYTES, full + slot);
+                }
+            }
+#else
             if ((tid & 31) == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(empty + slot)) : "memory");
             if (issuer) {
                 const int nxt = 8 * t + e + R;
@@ -1006,6 +1025,7 @@ __global__ void __launch_bounds__((PB / TP) * (K + 1) * (1 << LOGN) / 8, 1) k_bl
                     tma_load_1d(ring + (size_t)slot * KW, ksrc + (size_t)nxt * C::slice_w, KBYTES, full + slot);
                 }
             }
+#endif
             if (++slot == R) { slot = 0; par ^= 1; }
         };
         static_assert(M == 2 || G == 2, "the M = 3 sums are sized for k = 1");
