@@ -818,6 +818,9 @@ struct BR2Cfg {
 #ifndef FBS_PSI_STATIC
 #define FBS_PSI_STATIC 1    /* psi^x table in static shared memory (constant address folded into the look-up) */
 #endif
+#ifndef FBS_LATE_XSYNC
+#define FBS_LATE_XSYNC 1   /* wait for the partner warps' digit spectra after element 0's key products instead of before the point-wise loop */
+#endif
 #ifndef FBS_LAST_REFILLS
 #define FBS_LAST_REFILLS 0  /* 1: a block's ring entry is refilled by whichever of its warps releases it last (no waiting issuer) */
 #endif
@@ -1053,7 +1056,9 @@ __global__ void __launch_bounds__((PB / TP) * (K + 1) * (1 << LOGN) / 8, 1) k_bl
                 else PK[q][c] = x0 | ((E & 7u) << 20);
             }
         }
+#if !FBS_LATE_XSYNC
         xsync();                                             // the partner warps' spectra are in shared memory
+#endif
 #pragma unroll
         for (int e = 0; e < 8; e++) {
             const u32 o = bo[0] ^ P::elem_boff(e, 0);
@@ -1098,6 +1103,9 @@ __global__ void __launch_bounds__((PB / TP) * (K + 1) * (1 << LOGN) / 8, 1) k_bl
                     }                                                                    // < NC p^2 <= 7 p^2 < 2^63
                 }
             }
+#if FBS_LATE_XSYNC
+            if (e == 0) xsync();                             // the partner warps' spectra are only needed from here on: element 0's key
+#endif                                                       // products do not wait for the partner
             rns2 dsp[TP][G];                                 // digit spectra of this element (< 2p): own group's and the partner groups'
 #pragma unroll
             for (int q = 0; q < TP; q++)
@@ -1405,7 +1413,9 @@ __global__ void __launch_bounds__((K + 1) * (1 << (LOGN - LOGC)) / 8, 1) k_blind
                 else PK[c] = x0 | ((E & 7u) << 20);
             }
         }
+#if !FBS_LATE_XSYNC
         xsync();
+#endif
 #pragma unroll
         for (int e = 0; e < 8; e++) {
             const u32 o = bo[0] ^ P::elem_boff(e, 0);
@@ -1433,6 +1443,9 @@ __global__ void __launch_bounds__((K + 1) * (1 << (LOGN - LOGC)) / 8, 1) k_blind
                     else { pa[og] = r32_madwide(f.a, kk.a, pa[og]); pb2[og] = r32_madwide(f.b, kk.b, pb2[og]); }
                 }
             }
+#if FBS_LATE_XSYNC
+            if (e == 0) xsync();                             // partner spectra are needed from here on (see k_blind_rotate2)
+#endif
 #if FBS_EARLY_RELEASE
             release_slot(e);                                 // key words are in registers: free the entry, wait for the next one now
             if (e < 7) mbar_wait(full + slot, par);
@@ -1668,7 +1681,9 @@ __global__ void __launch_bounds__(2 * (K + 1) * (1 << (LOGN - LOGC)) / 8, OCC) k
                 else PK[c] = x0 | ((E & 7u) << 20);
             }
         }
+#if !FBS_LATE_XSYNC
         xsync();
+#endif
 #pragma unroll
         for (int e = 0; e < 8; e++) {
             const u32 o = bo[0] ^ P::elem_boff(e, 0);
@@ -1695,6 +1710,9 @@ __global__ void __launch_bounds__(2 * (K + 1) * (1 << (LOGN - LOGC)) / 8, OCC) k
                     pa[og] = (c == 0) ? r32_mulwide(f, kk) : r32_madwide(f, kk, pa[og]);
                 }
             }
+#if FBS_LATE_XSYNC
+            if (e == 0) xsync();                             // partner spectra are needed from here on (see k_blind_rotate2)
+#endif
 #if FBS_EARLY_RELEASE
             release_slot(e);                                 // key words are in registers: free the entry, wait for the next one now
             if (e < 7) mbar_wait(full + slot, par);
