@@ -96,8 +96,8 @@ class ClockSampler(threading.Thread):
 
 
 # DRAM bytes (read + write) of one blind-rotate launch, from ncu --set full captures under profiles/ (NOT measured in the bench run itself)
-TRAFFIC_GB = {3: 0.23845, 2: 0.15463, 1: 0.06195, 0: 0.06195}
-TRAFFIC_SOURCE = ("GB per 592-PBS launch from profiles/r2_v6_hot_kernels_summary.txt (ncu dram__bytes_read.sum + dram__bytes_write.sum), not measured in this run; "
+TRAFFIC_GB = {3: 0.23771, 2: 0.15463, 1: 0.06195, 0: 0.06195}
+TRAFFIC_SOURCE = ("GB per 592-PBS launch from profiles/r2_v7_hot_kernels_summary.txt (ncu dram__bytes_read.sum + dram__bytes_write.sum), not measured in this run; "
                   "the key-unrolled BSK (114 MB at 3 bits per step) does not stay L2-resident between waves and is re-read from HBM once per wave")
 
 
