@@ -14,7 +14,7 @@ parsed by experiments/build_csv.py:24-25), check that the mapped circuit reprodu
                              ``b200`` = the mapped circuit runs ENCRYPTED (TFHE) on the GPU and is decrypted,
                              ``none`` = map and write files only (no GPU needed)
     --batch N                number of random vectors (default 1000, the reference's value)
-    --param-set NAME         TFHE parameter set for --exec b200 (default A)
+    --param-set NAME         TFHE parameter set for --exec b200 (default: the library default, A3)
 """
 import argparse
 import json
